@@ -1,0 +1,480 @@
+/*
+ * ref_harness.cpp -- TEST INFRASTRUCTURE (oracle/_ref).
+ *
+ * C entry points over the REFERENCE'S OWN translation units, which oracle/Makefile compiles
+ * verbatim from /root/reference into oracle/_ref/libup_ref.so (nothing is copied into this
+ * repository).  The only restated arithmetic underneath is FastNoiseLite (shims/FastNoiseLite.h).
+ * Used to (1) validate the oracle restatement, (2) generate tests/golden/ fixtures
+ * (tests/golden/make_golden.py), (3) serve as the "reference" CPU baseline in bench.py.
+ * The product never links or loads this.
+ *
+ * One loaded copy of the library == one planet configuration: the reference keeps its noise
+ * objects in function-local statics (e.g. sources/elevationModes.cpp:131-140), initialised once.
+ * oracle/ref.py loads a private copy of the .so per configuration.
+ */
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <FastNoiseLite.h> // the shim (registry of constructed noise objects)
+
+#include <cage-core/color.h>
+#include <cage-core/config.h>
+#include <cage-core/geometry.h>
+#include <cage-core/image.h>
+#include <cage-core/imageAlgorithms.h>
+#include <cage-core/marchingCubes.h>
+#include <cage-core/mesh.h>
+#include <cage-core/meshAlgorithms.h>
+#include <cage-core/random.h>
+
+#include <dualmc.h>
+
+#include "planets.h" // -iquote $(REF)/sources
+
+namespace unnatural
+{
+	// sources/modesConfiguration.cpp:230-315
+	Real terrainSdfElevation(const Vec3 &pos);
+	Real terrainSdfElevationRaw(const Vec3 &pos);
+	Real terrainSdfLand(const Vec3 &pos);
+	Real terrainSdfWater(const Vec3 &pos);
+	Real terrainSdfNavigation(const Vec3 &pos);
+	void terrainTile(Tile &tile);
+	void terrainPreseed();
+	void terrainApplyConfig();
+	// sources/textures.cpp:86-96
+	void generateTexturesLand(const Holder<Mesh> &renderMesh, uint32 width, uint32 height, Holder<Image> &albedo, Holder<Image> &special, Holder<Image> &heightMap);
+	void generateTexturesWater(const Holder<Mesh> &renderMesh, uint32 width, uint32 height, Holder<Image> &albedo, Holder<Image> &special, Holder<Image> &heightMap);
+	// sources/math.cpp:73-77
+	uint32 noiseSeed();
+
+	// globals the reference defines in generator.cpp / doodads.cpp etc. (not compiled here)
+	std::vector<Tile> tiles;
+}
+
+using namespace cage;
+using namespace unnatural;
+
+namespace
+{
+	thread_local std::string lastError;
+
+	template<class F>
+	int guarded(F &&f)
+	{
+		try
+		{
+			f();
+			return 0;
+		}
+		catch (const cage::Exception &e)
+		{
+			lastError = std::string("cage::Exception: ") + (const char *)e.message;
+		}
+		catch (const std::exception &e)
+		{
+			lastError = std::string("std::exception: ") + e.what();
+		}
+		catch (...)
+		{
+			lastError = "unknown exception";
+		}
+		return 1;
+	}
+
+	using Sdf = Real (*)(const Vec3 &);
+	Sdf pickField(int what)
+	{
+		switch (what)
+		{
+			case 0:
+				return &terrainSdfWater; // == the base shape
+			case 1:
+				return &terrainSdfElevationRaw;
+			case 2:
+				return &terrainSdfLand;
+			case 3:
+				return &terrainSdfNavigation;
+			case 4:
+				return &terrainSdfElevation;
+		}
+		return nullptr;
+	}
+
+	MarchingCubesCreateConfig gridConfig(float boxSize, int res)
+	{
+		// sources/meshGeneration.cpp:34-37
+		MarchingCubesCreateConfig cfg;
+		cfg.box = Aabb(Vec3(boxSize * -0.5), Vec3(boxSize * 0.5));
+		cfg.resolution = Vec3i(res);
+		return cfg;
+	}
+}
+
+extern "C"
+{
+	const char *upref_last_error()
+	{
+		return lastError.c_str();
+	}
+
+	// configure + preseed exactly as main.cpp:17-54 / generator.cpp:424-431 would, with an explicit RNG state
+	int upref_init(const char *shape, const char *elevation, const char *coloring, int poles, int flowers, uint64_t s0, uint64_t s1)
+	{
+		return guarded(
+			[&]()
+			{
+				configSetString("unnatural-planets/shape/mode", shape);
+				configSetString("unnatural-planets/elevation/mode", elevation);
+				configSetString("unnatural-planets/coloring/mode", coloring);
+				configSetBool("unnatural-planets/poles/enable", !!poles);
+				configSetBool("unnatural-planets/flowers/enable", !!flowers);
+				detail::randomGenerator() = RandomGenerator(s0, s1);
+				terrainApplyConfig();
+				terrainPreseed();
+			});
+	}
+
+	// state of the calling thread's RNG (to check how many draws the preseed consumed)
+	void upref_rng_state(uint64_t *s)
+	{
+		s[0] = detail::randomGenerator().s[0];
+		s[1] = detail::randomGenerator().s[1];
+	}
+	void upref_rng_set(uint64_t s0, uint64_t s1)
+	{
+		detail::randomGenerator() = RandomGenerator(s0, s1);
+	}
+
+	// KAT helpers over cage's RandomGenerator (test-core/random.cpp:37-79)
+	void upref_rng_kat(uint64_t s0, uint64_t s1, int n, uint64_t *raw)
+	{
+		RandomGenerator g(s0, s1);
+		for (int i = 0; i < n; i++)
+			raw[i] = g.next();
+	}
+	void upref_rng_range3(uint64_t s0, uint64_t s1, float a, float b, float *out3, int32_t *out3i, int ia, int ib)
+	{
+		RandomGenerator g(s0, s1);
+		const Vec3i vi = g.randomRange3i(ia, ib);
+		const Vec3 v = g.randomRange3(a, b);
+		for (int i = 0; i < 3; i++)
+		{
+			out3[i] = v[i].value;
+			out3i[i] = vi[i];
+		}
+	}
+
+	int upref_noise_count()
+	{
+		return (int)upo_shim_registry().size();
+	}
+	void upref_noise_get(int i, upo_noise_cfg *out)
+	{
+		*out = upo_shim_registry()[i]->cfg;
+	}
+	// direct access to one registered noise object (3-D and the 1-D overload cage maps to (x, 0))
+	void upref_noise_eval(int i, const float *pos, int n, float *out)
+	{
+		const FastNoiseLite *f = upo_shim_registry()[i];
+		for (int k = 0; k < n; k++)
+			out[k] = f->GetNoise(pos[k * 3 + 0], pos[k * 3 + 1], pos[k * 3 + 2]);
+	}
+
+	int upref_eval(int what, const float *pos, int n, float *out)
+	{
+		return guarded(
+			[&]()
+			{
+				Sdf f = pickField(what);
+				for (int i = 0; i < n; i++)
+					out[i] = f(Vec3(pos[i * 3 + 0], pos[i * 3 + 1], pos[i * 3 + 2])).value;
+			});
+	}
+
+	// grid positions only (externals/cage/sources/libcore/mesh/marchingCubes.cpp:247-257)
+	void upref_grid_positions(float boxSize, int res, float *out /* res*3: x(i) y(i) z(i) share one axis */)
+	{
+		const MarchingCubesCreateConfig cfg = gridConfig(boxSize, res);
+		for (int i = 0; i < res; i++)
+			out[i] = cfg.position(i, 0, 0)[0].value;
+	}
+
+	// marchingCubes.cpp:149-165 driven with the reference field functions; threads > 1 splits z (same arithmetic per sample)
+	int upref_grid(int what, float boxSize, int res, int z0, int z1, float *out /* (z1-z0)*res*res */, int threads)
+	{
+		return guarded(
+			[&]()
+			{
+				Sdf f = pickField(what);
+				const MarchingCubesCreateConfig cfg = gridConfig(boxSize, res);
+				if (threads <= 1 && z0 == 0 && z1 == res)
+				{
+					Holder<MarchingCubes> cubes = newMarchingCubes(cfg);
+					struct Bound
+					{
+						Sdf f;
+						Real call(const Vec3 &p) { return f(p); }
+					} bound{ f };
+					Delegate<Real(const Vec3 &)> d;
+					d.bind<Bound, &Bound::call>(&bound);
+					cubes->updateByPosition(d);
+					std::memcpy(out, cubes->densities().data(), sizeof(float) * (size_t)res * res * res);
+					return;
+				}
+				std::atomic<int> next{ z0 };
+				std::atomic<bool> failed{ false };
+				auto work = [&]()
+				{
+					try
+					{
+						for (;;)
+						{
+							const int z = next++;
+							if (z >= z1)
+								break;
+							float *o = out + (size_t)(z - z0) * res * res;
+							for (int y = 0; y < res; y++)
+								for (int x = 0; x < res; x++)
+									*o++ = f(cfg.position(x, y, z)).value;
+						}
+					}
+					catch (...)
+					{
+						failed = true;
+					}
+				};
+				std::vector<std::thread> pool;
+				for (int t = 1; t < threads; t++)
+					pool.emplace_back(work);
+				work();
+				for (auto &t : pool)
+					t.join();
+				if (failed)
+					CAGE_THROW_ERROR(Exception, "sampling failed");
+			});
+	}
+
+	// raw dualmc output (externals/cage/externals/dualmc/dualmc/include/dualmc.tpp:222-249), iso 0
+	struct upref_buf
+	{
+		void *ptr;
+		uint64_t count;
+	};
+	void upref_free(void *p)
+	{
+		std::free(p);
+	}
+
+	int upref_dualmc(const float *dens, int rx, int ry, int rz, float iso, int manifold, upref_buf *vertices /* float3 */, upref_buf *quads /* int4 */)
+	{
+		return guarded(
+			[&]()
+			{
+				dualmc::DualMC<float> mc;
+				std::vector<dualmc::Vertex> v;
+				std::vector<dualmc::Quad> q;
+				mc.build(dens, rx, ry, rz, iso, !!manifold, false, v, q);
+				vertices->count = v.size();
+				vertices->ptr = std::malloc(sizeof(float) * 3 * v.size() + 16);
+				std::memcpy(vertices->ptr, v.data(), sizeof(float) * 3 * v.size());
+				quads->count = q.size();
+				quads->ptr = std::malloc(sizeof(int32_t) * 4 * q.size() + 16);
+				std::memcpy(quads->ptr, q.data(), sizeof(int32_t) * 4 * q.size());
+			});
+	}
+
+	// MarchingCubes::makeMesh (marchingCubes.cpp:176-245) and the tail of meshGenerateGeneric (sources/meshGeneration.cpp:40-43)
+	// stages: bit0 = makeMesh with clip (as the generator does), bit1 = meshRemoveDisconnected, bit2 = meshFlipNormals;
+	// bit3 = makeMesh WITHOUT clip/merge is not offered by cage (clip=false merges close vertices instead), see cfg.clip
+	int upref_make_mesh(const float *dens, float boxSize, int res, int clip, int stages, upref_buf *positions, upref_buf *normals, upref_buf *indices)
+	{
+		return guarded(
+			[&]()
+			{
+				MarchingCubesCreateConfig cfg = gridConfig(boxSize, res);
+				cfg.clip = !!clip;
+				Holder<MarchingCubes> cubes = newMarchingCubes(cfg);
+				cubes->densities(PointerRange<const Real>((const Real *)dens, (const Real *)dens + (size_t)res * res * res));
+				Holder<Mesh> poly = cubes->makeMesh();
+				if (stages & 2)
+					meshRemoveDisconnected(+poly);
+				if (stages & 4)
+					meshFlipNormals(+poly);
+				const uint32 nv = poly->verticesCount();
+				const uint32 ni = poly->indicesCount();
+				positions->count = nv;
+				positions->ptr = std::malloc(sizeof(float) * 3 * nv + 16);
+				std::memcpy(positions->ptr, poly->positions().data(), sizeof(float) * 3 * nv);
+				normals->count = poly->normals().size();
+				normals->ptr = std::malloc(sizeof(float) * 3 * nv + 16);
+				std::memcpy(normals->ptr, poly->normals().data(), sizeof(float) * 3 * poly->normals().size());
+				indices->count = ni;
+				indices->ptr = std::malloc(sizeof(uint32_t) * ni + 16);
+				std::memcpy(indices->ptr, poly->indices().data(), sizeof(uint32_t) * ni);
+			});
+	}
+
+	// terrainTile (sources/modesConfiguration.cpp:281-286) on explicit position/normal pairs
+	// out per tile: albedo rgb, roughness, metallic, height, elevation, slope(rad), temperature, precipitation, opacity, biome, type  (13 floats)
+	int upref_tiles(int purpose /* 1 land, 2 water, 3 navigation */, const float *pos, const float *nrm, int n, float *out)
+	{
+		return guarded(
+			[&]()
+			{
+				for (int i = 0; i < n; i++)
+				{
+					Tile t;
+					t.position = Vec3(pos[i * 3 + 0], pos[i * 3 + 1], pos[i * 3 + 2]);
+					t.normal = Vec3(nrm[i * 3 + 0], nrm[i * 3 + 1], nrm[i * 3 + 2]);
+					t.meshPurpose = (MeshPurposeEnum)purpose;
+					terrainTile(t);
+					float *o = out + (size_t)i * 13;
+					o[0] = t.albedo[0].value;
+					o[1] = t.albedo[1].value;
+					o[2] = t.albedo[2].value;
+					o[3] = t.roughness.value;
+					o[4] = t.metallic.value;
+					o[5] = t.height.value;
+					o[6] = t.elevation.value;
+					o[7] = Real(t.slope).value;
+					o[8] = t.temperature.value;
+					o[9] = t.precipitation.value;
+					o[10] = t.opacity.value;
+					o[11] = (float)(int)t.biome;
+					o[12] = (float)(int)t.type;
+				}
+			});
+	}
+
+	// generateTexturesLand / Water (sources/textures.cpp:86-96): rasterise + colour + 7 dilations + u8
+	int upref_bake(int water, const float *pos, const float *nrm, const float *uv, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *special, uint8_t *height)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> msh = newMesh();
+				msh->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nverts));
+				msh->normals(PointerRange<const Vec3>((const Vec3 *)nrm, (const Vec3 *)nrm + nverts));
+				msh->uvs(PointerRange<const Vec2>((const Vec2 *)uv, (const Vec2 *)uv + nverts));
+				msh->indices(PointerRange<const uint32>(idx, idx + nidx));
+				Holder<Image> a, s, hm;
+				if (water)
+					generateTexturesWater(msh, w, h, a, s, hm);
+				else
+					generateTexturesLand(msh, w, h, a, s, hm);
+				std::memcpy(albedo, a->rawViewU8().data(), a->rawViewU8().size());
+				std::memcpy(special, s->rawViewU8().data(), s->rawViewU8().size());
+				std::memcpy(height, hm->rawViewU8().data(), hm->rawViewU8().size());
+			});
+	}
+
+	// meshGenerateTexture coverage only (externals/cage/sources/libcore/mesh/meshAlgorithms.cpp:1676-1729):
+	// owner[y*w+x] = index of the LAST triangle whose scan covers the texel (0xffffffff if none), weights of that visit
+	int upref_raster(const float *pos, const float *uv, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t *owner, float *weights /* w*h*3 */, uint64_t *callbacks)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> msh = newMesh();
+				msh->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nverts));
+				msh->uvs(PointerRange<const Vec2>((const Vec2 *)uv, (const Vec2 *)uv + nverts));
+				msh->indices(PointerRange<const uint32>(idx, idx + nidx));
+				struct Rec
+				{
+					uint32_t w, h;
+					uint32_t *owner;
+					float *weights;
+					uint64_t calls = 0;
+					const uint32_t *idx;
+					uint32_t nidx;
+					void pixel(const Vec2i &xy, const Vec3i &ids, const Vec3 &wg)
+					{
+						calls++;
+						if (xy[0] < 0 || xy[1] < 0 || (uint32_t)xy[0] >= w || (uint32_t)xy[1] >= h)
+							return;
+						const size_t o = (size_t)xy[1] * w + xy[0];
+						// recover the triangle index: the rasteriser walks triangles in order, track via ids match
+						owner[o] = cur;
+						weights[o * 3 + 0] = wg[0].value;
+						weights[o * 3 + 1] = wg[1].value;
+						weights[o * 3 + 2] = wg[2].value;
+					}
+					uint32_t cur = 0;
+				} rec{ w, h, owner, weights };
+				for (size_t i = 0; i < (size_t)w * h; i++)
+					owner[i] = 0xffffffffu;
+				// one triangle at a time so that the callback knows the triangle index
+				for (uint32_t t = 0; t < nidx / 3; t++)
+				{
+					Holder<Mesh> one = newMesh();
+					one->positions(msh->positions());
+					one->uvs(msh->uvs());
+					const uint32 tri[3] = { idx[t * 3 + 0], idx[t * 3 + 1], idx[t * 3 + 2] };
+					one->indices(tri);
+					rec.cur = t;
+					MeshGenerateTextureConfig cfg;
+					cfg.width = w;
+					cfg.height = h;
+					cfg.generator.bind<Rec, &Rec::pixel>(&rec);
+					meshGenerateTexture(+one, cfg);
+				}
+				*callbacks = rec.calls;
+			});
+	}
+
+	// colour KATs (externals/cage/sources/libcore/color.cpp)
+	void upref_color(int what, const float *in3, float *out3)
+	{
+		const Vec3 v(in3[0], in3[1], in3[2]);
+		Vec3 r;
+		switch (what)
+		{
+			case 0:
+				r = colorRgbToHsv(v);
+				break;
+			case 1:
+				r = colorHsvToRgb(v);
+				break;
+			case 2:
+				r = colorRgbToHsluv(v);
+				break;
+			case 3:
+				r = colorHsluvToRgb(v);
+				break;
+		}
+		out3[0] = r[0].value;
+		out3[1] = r[1].value;
+		out3[2] = r[2].value;
+	}
+	void upref_color_interpolate(const float *a3, const float *b3, float f, float *out3)
+	{
+		const Vec3 r = interpolateColor(Vec3(a3[0], a3[1], a3[2]), Vec3(b3[0], b3[1], b3[2]), f);
+		out3[0] = r[0].value;
+		out3[1] = r[1].value;
+		out3[2] = r[2].value;
+	}
+
+	// imageDilation(float image, rounds, useNan) + imageConvert(U8) (imageAlgorithms.cpp:504-527, 100-113)
+	int upref_dilate(float *img, uint32_t w, uint32_t h, uint32_t ch, uint32_t rounds, int useNan, uint8_t *u8out /* may be null */)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Image> im = newImage();
+				im->importRaw(PointerRange<const char>((const char *)img, (const char *)img + sizeof(float) * (size_t)w * h * ch), w, h, ch, ImageFormatEnum::Float);
+				imageDilation(+im, rounds, !!useNan);
+				std::memcpy(img, im->rawViewFloat().data(), sizeof(float) * (size_t)w * h * ch);
+				if (u8out)
+				{
+					imageConvert(+im, ImageFormatEnum::U8);
+					std::memcpy(u8out, im->rawViewU8().data(), (size_t)w * h * ch);
+				}
+			});
+	}
+}
