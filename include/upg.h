@@ -1,0 +1,129 @@
+/*
+ * upg.h -- C ABI of the B200 generation core ("unnatural-planets GPU"), libupg.so.
+ *
+ * The reference generator (unnatural-worlds/unnatural-planets) has no FFI: its plug-in surface for the
+ * hot path is a pair of function-pointer types selected by name,
+ *     using TerrainFunctor  = Real (*)(const Vec3 &);      sources/modesConfiguration.cpp:29-31
+ *     using ColoringFunctor = void (*)(Tile &tile);        sources/modesConfiguration.cpp:33-34
+ * consumed by two drivers whose C++ signatures stay unchanged in a patched build
+ * (see INTEGRATION.md for the shim a maintainer would add):
+ *     Holder<Mesh> meshGenerateBaseLand / Water / Navigation();          sources/meshGeneration.cpp:47,57,100
+ *     void generateTexturesLand / Water(const Holder<Mesh>&, uint32 w, uint32 h,
+ *                                       Holder<Image>&, Holder<Image>&, Holder<Image>&);   sources/textures.cpp:86,92
+ * Each entry point below cites the reference interface it stands in for.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * UPG_ERR_* code on failure with a message in upg_last_error() (thread local).  No exception
+ * crosses this boundary (the reference throws cage::Exception, include/cage-core/core.h:263-274;
+ * the host shim re-throws).  All entry points are re-entrant: the reference calls the three field
+ * pipelines concurrently from three pool threads (sources/generator.cpp:432-439); every call uses
+ * its own CUDA stream and a planet is immutable after creation.
+ * There is NO CPU execution path: without a usable CUDA device every compute call fails with
+ * UPG_ERR_CUDA.
+ */
+#ifndef UPG_H_INCLUDED
+#define UPG_H_INCLUDED
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPG_API_VERSION 1
+
+enum
+{
+	UPG_OK = 0,
+	UPG_ERR_ARGUMENT = 1, /* unknown mode name / id, null pointer, resolution <= 5 (marchingCubes.cpp:21-23) */
+	UPG_ERR_CUDA = 2, /* no device, launch or allocation failure */
+	UPG_ERR_INVALID_VALUE = 3, /* a NaN sample: "invalid land sdf value" (sources/modesConfiguration.cpp:255-256) */
+	UPG_ERR_EMPTY_MESH = 4 /* "generated empty base land mesh" (sources/meshGeneration.cpp:51-52) */
+};
+
+/* terrainSdf* of sources/modesConfiguration.cpp:230-279 */
+enum
+{
+	UPG_FIELD_LAND = 0, /* terrainSdfLand:       shape - elevation / 10 */
+	UPG_FIELD_WATER = 1, /* terrainSdfWater:      shape */
+	UPG_FIELD_NAVIGATION = 2, /* terrainSdfNavigation: shape - max(elevation, 0) / 10 */
+	UPG_FIELD_ELEVATION_RAW = 3, /* terrainSdfElevationRaw: elevation */
+	UPG_FIELD_ELEVATION = 4 /* terrainSdfElevation:  shape * 10 */
+};
+
+typedef struct upg_planet upg_planet;
+
+/*
+ * One planet == one process run of the reference: the mode names chosen by applyConfiguration
+ * (sources/main.cpp:17-54 -> terrainApplyConfig, sources/modesConfiguration.cpp:308-315) plus the state of
+ * the random generator that noiseSeed() copies (sources/math.cpp:73-77).  The reference seeds that generator
+ * from std::random_device and has no seed option; `seed` is the injection point SURVEY.md F4 asks for.
+ */
+typedef struct upg_planet_desc
+{
+	uint32_t struct_size; /* sizeof(upg_planet_desc), for ABI evolution */
+	int32_t shape; /* index into the reference's shapeModeNames order; see upg_shape_id() */
+	int32_t elevation; /* index into elevationModeNames */
+	int32_t coloring; /* index into tileModeNames */
+	int32_t poles; /* unnatural-planets/poles/enable */
+	int32_t flowers; /* unnatural-planets/flowers/enable */
+	uint64_t seed[2]; /* xoroshiro128** state (both non-zero, random.cpp:14-17) */
+	float box_size; /* meshing box side, reference constant 4000 (sources/meshGeneration.cpp:19) */
+	int32_t grid_resolution; /* samples per axis, reference constant 500 (110 in debug builds) (:20-28) */
+	int32_t device; /* CUDA device ordinal */
+} upg_planet_desc;
+
+/* fills the reference's defaults: shape "random" is NOT resolved here (pass an explicit id), elevation lakes,
+ * coloring default, poles/flowers off (sources/main.cpp:19-44), box 4000, grid 500, device 0, the seed pair of
+ * cage's own RNG test (externals/cage/sources/test-core/random.cpp:38) */
+void upg_planet_desc_default(upg_planet_desc *desc);
+
+/* name <-> id in the order of the reference's tables (sources/modesConfiguration.cpp:78-113, 176-183, 207-211);
+ * -1 / NULL when unknown (the reference throws "unknown shape mode configuration", :131-132) */
+int upg_shape_id(const char *name);
+int upg_elevation_id(const char *name);
+int upg_coloring_id(const char *name);
+const char *upg_shape_name(int id);
+const char *upg_elevation_name(int id);
+const char *upg_coloring_name(int id);
+int upg_shape_count(void);
+
+/* replaces terrainApplyConfig + terrainPreseed (sources/modesConfiguration.cpp:288-315): fixes the modes, draws the
+ * shape constants and every noise seed in static-initialisation order, uploads nothing yet (parameters travel as
+ * kernel arguments) */
+int upg_planet_create(const upg_planet_desc *desc, upg_planet **out);
+void upg_planet_destroy(upg_planet *planet);
+
+/* the 32-bit seeds in the order noiseSeed() handed them out; returns how many were drawn (for parity checks) */
+int upg_planet_seed_log(const upg_planet *planet, uint32_t *out, int capacity);
+
+/*
+ * K1.  Replaces MarchingCubes::updateByPosition (externals/cage/sources/libcore/mesh/marchingCubes.cpp:149-165)
+ * bound to one of the terrainSdf* functions: samples z-slices [z0, z1) of the res^3 grid, layout
+ * out[((z - z0) * res + y) * res + x] exactly as MarchingCubesCreateConfig::index (:259-265); the result can be
+ * handed to MarchingCubes::densities(PointerRange<const Real>) (include/cage-core/marchingCubes.h:16).
+ * `host_out` is host memory (pinned or pageable), (z1 - z0) * res * res floats.
+ */
+int upg_field_samples(upg_planet *planet, int field, int z0, int z1, float *host_out);
+
+/* same, into DEVICE memory on `cuda_stream` (a cudaStream_t, NULL = default stream), asynchronous: for callers that
+ * keep the field on the GPU (bench.py's device-resident metric, the isosurface stage) */
+int upg_field_samples_device(upg_planet *planet, int field, int z0, int z1, float *device_out, void *cuda_stream);
+
+/* one terrainSdf* value per explicit position (n x 3 floats): the per-vertex terrainSdfElevationRaw loop of the water
+ * mesh culling (sources/meshGeneration.cpp:62-68) and the parity probes */
+int upg_field_points(upg_planet *planet, int field, const float *host_positions, uint64_t n, float *host_out);
+
+/* measurement helper for bench.py: the FP32 FMA ceiling (TFLOP/s, FMA = 2 flop) of `device`, measured live with a
+ * dependent-free FFMA kernel -- the roofline denominator of the compute-bound kernels (K1 sampling, K6 texel baking);
+ * MEASURED_PEAKS.json only carries HBM and tensor-core peaks */
+int upg_measure_fp32_peak(int device, float *tflops_out);
+
+/* thread-local description of the last failure on this thread ("" if none) */
+const char *upg_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* UPG_H_INCLUDED */

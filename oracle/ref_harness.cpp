@@ -60,6 +60,12 @@ namespace unnatural
 using namespace cage;
 using namespace unnatural;
 
+std::vector<const FastNoiseLite *> &upo_shim_registry()
+{
+	static std::vector<const FastNoiseLite *> r;
+	return r;
+}
+
 namespace
 {
 	thread_local std::string lastError;

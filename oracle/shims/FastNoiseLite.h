@@ -18,11 +18,8 @@
 
 class FastNoiseLite;
 /* every noise object the reference constructs, in construction order (== noiseSeed() order per SURVEY A.6) */
-inline std::vector<const FastNoiseLite *> &upo_shim_registry()
-{
-	static std::vector<const FastNoiseLite *> r;
-	return r;
-}
+/* defined once in ref_harness.cpp (a plain global: one per loaded copy of the library) */
+std::vector<const FastNoiseLite *> &upo_shim_registry();
 
 class FastNoiseLite
 {

@@ -1,0 +1,86 @@
+"""ctypes declarations for include/upg.h.  Loading is lazy and LOUD: a missing library is an error, never a fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FIELDS = {"land": 0, "water": 1, "navigation": 2, "elevation_raw": 3, "elevation": 4}
+
+
+class UpgError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("upg error %d: %s" % (code, message))
+        self.code = code
+
+
+class PlanetDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("shape", C.c_int32),
+        ("elevation", C.c_int32),
+        ("coloring", C.c_int32),
+        ("poles", C.c_int32),
+        ("flowers", C.c_int32),
+        ("seed", C.c_uint64 * 2),
+        ("box_size", C.c_float),
+        ("grid_resolution", C.c_int32),
+        ("device", C.c_int32),
+    ]
+
+
+class Mesh(C.Structure):
+    _fields_ = [
+        ("positions", C.POINTER(C.c_float)),
+        ("normals", C.POINTER(C.c_float)),
+        ("indices", C.POINTER(C.c_uint32)),
+        ("vertex_count", C.c_uint32),
+        ("index_count", C.c_uint32),
+        ("quad_count", C.c_uint32),
+        ("active_cells", C.c_uint32),
+        ("near_zero_samples", C.c_uint64),
+        ("_owner", C.c_void_p),
+    ]
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libupg.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Returns the loaded libupg.so.  Raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError("libupg.so is not built: run `make -C unnatural_planets_b200/csrc -j8` (there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i32, u64, fp = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p
+    L.upg_last_error.restype = C.c_char_p
+    L.upg_planet_desc_default.argtypes = [C.POINTER(PlanetDesc)]
+    L.upg_planet_desc_default.restype = None
+    for n in ("upg_shape_id", "upg_elevation_id", "upg_coloring_id"):
+        getattr(L, n).argtypes = [C.c_char_p]
+    for n in ("upg_shape_name", "upg_elevation_name", "upg_coloring_name"):
+        getattr(L, n).argtypes = [i32]
+        getattr(L, n).restype = C.c_char_p
+    L.upg_planet_create.argtypes = [C.POINTER(PlanetDesc), C.POINTER(vp)]
+    L.upg_planet_destroy.argtypes = [vp]
+    L.upg_planet_destroy.restype = None
+    L.upg_planet_seed_log.argtypes = [vp, fp, i32]
+    L.upg_field_samples.argtypes = [vp, i32, i32, i32, fp]
+    L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
+    L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
+    L.upg_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise UpgError(rc, load_library().upg_last_error().decode())

@@ -1,0 +1,399 @@
+// upg_api.cu -- the C ABI (include/upg.h) over the CUDA kernels.  Host logic only: mode tables, seed
+// stream, parameter marshalling, stream / memory management, error codes.  No compute happens on the CPU.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/upg.h"
+#include "upg_internal.h"
+
+namespace upg
+{
+	// ---- error plumbing ---------------------------------------------------------------------------
+	static thread_local std::string t_lastError;
+
+	int fail(int code, const char *fmt, ...)
+	{
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof(buf), fmt, ap);
+		va_end(ap);
+		t_lastError = buf;
+		return code;
+	}
+
+	int cuda_fail(cudaError_t e, const char *what)
+	{
+		return fail(UPG_ERR_CUDA, "CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+	}
+
+	// ---- mode tables, in the reference's order (sources/modesConfiguration.cpp:78-113, 176-183, 207-211) ----
+	static const char *const shapeNames[SH_COUNT] = {
+		"asteroid", "belt", "bowl", "box", "bunny", "capsule", "cube", "disk", "doubletorus", "fibers", "gear", "h2o", "h3o", "h4o", "hemispheres", "hexagon", "hexagonalprism", "insidecube", "knot", "mandelbulb", "mobiusstrip", "monkeyhead", "octahedron", "pipe", "sphere", "square", "tetrahedron", "torus", "toruscross", "triangularprism", "tube", "twistedhexagonalprism", "twistedplane", "wormhole",
+	};
+	static const char *const elevationNames[EL_COUNT] = { "none", "simple", "legacy", "lakes", "islands", "craters" };
+	static const char *const coloringNames[CL_COUNT] = { "default", "barren", "debug" };
+
+	static int lookup(const char *const *table, int n, const char *name)
+	{
+		if (!name)
+			return -1;
+		for (int i = 0; i < n; i++)
+			if (std::strcmp(table[i], name) == 0)
+				return i;
+		return -1;
+	}
+
+	// ---- K1 dispatch: one launcher per (elevation, shape range) translation unit ----------------------------
+#define UPG_DECL_LAUNCHERS(E) \
+	bool field_launch_e##E##_p0(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launch_e##E##_p1(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launch_e##E##_p2(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launch_e##E##_p3(int, const PlanetParams &, const FieldLaunch &, void *);
+	UPG_DECL_LAUNCHERS(0)
+	UPG_DECL_LAUNCHERS(1)
+	UPG_DECL_LAUNCHERS(2)
+	UPG_DECL_LAUNCHERS(3)
+	UPG_DECL_LAUNCHERS(4)
+	UPG_DECL_LAUNCHERS(5)
+#define UPG_LIST_LAUNCHERS(E) { field_launch_e##E##_p0, field_launch_e##E##_p1, field_launch_e##E##_p2, field_launch_e##E##_p3 }
+	static const FieldLauncher fieldLaunchers[EL_COUNT][4] = {
+		UPG_LIST_LAUNCHERS(0), UPG_LIST_LAUNCHERS(1), UPG_LIST_LAUNCHERS(2), UPG_LIST_LAUNCHERS(3), UPG_LIST_LAUNCHERS(4), UPG_LIST_LAUNCHERS(5),
+	};
+
+	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream)
+	{
+		if (L.count == 0)
+			return UPG_OK;
+		const PlanetParams &P = planet->params;
+		bool done = false;
+		for (int part = 0; part < 4 && !done; part++)
+			done = fieldLaunchers[P.elevation][part](P.shape, P, L, (void *)stream);
+		if (!done)
+			return fail(UPG_ERR_ARGUMENT, "no kernel for shape %d elevation %d", P.shape, P.elevation);
+		const cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(e, "sdf_sample_kernel launch");
+		return UPG_OK;
+	}
+
+	int check_status(Planet *planet, cudaStream_t stream, const char *what)
+	{
+		uint32_t st = 0;
+		cudaError_t e = cudaMemcpyAsync(&st, planet->status, sizeof(st), cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(stream);
+		if (e != cudaSuccess)
+			return cuda_fail(e, what);
+		if (st & 1u)
+		{
+			cudaMemsetAsync(planet->status, 0, sizeof(uint32_t), stream);
+			cudaStreamSynchronize(stream);
+			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in %s", what);
+		}
+		return UPG_OK;
+	}
+
+	static bool valid_field(int field)
+	{
+		return field >= 0 && field < FD_COUNT;
+	}
+}
+
+using namespace upg;
+
+extern "C"
+{
+	const char *upg_last_error(void)
+	{
+		return t_lastError.c_str();
+	}
+
+	void upg_planet_desc_default(upg_planet_desc *d)
+	{
+		if (!d)
+			return;
+		std::memset(d, 0, sizeof(*d));
+		d->struct_size = sizeof(*d);
+		d->shape = SH_SPHERE;
+		d->elevation = EL_LAKES;
+		d->coloring = CL_DEFAULT;
+		d->poles = 0;
+		d->flowers = 0;
+		d->seed[0] = 1346519564496ull;
+		d->seed[1] = 42245614964156ull;
+		d->box_size = 4000.0f;
+		d->grid_resolution = 500;
+		d->device = 0;
+	}
+
+	int upg_shape_id(const char *name)
+	{
+		return lookup(shapeNames, SH_COUNT, name);
+	}
+	int upg_elevation_id(const char *name)
+	{
+		return lookup(elevationNames, EL_COUNT, name);
+	}
+	int upg_coloring_id(const char *name)
+	{
+		return lookup(coloringNames, CL_COUNT, name);
+	}
+	const char *upg_shape_name(int id)
+	{
+		return id >= 0 && id < SH_COUNT ? shapeNames[id] : nullptr;
+	}
+	const char *upg_elevation_name(int id)
+	{
+		return id >= 0 && id < EL_COUNT ? elevationNames[id] : nullptr;
+	}
+	const char *upg_coloring_name(int id)
+	{
+		return id >= 0 && id < CL_COUNT ? coloringNames[id] : nullptr;
+	}
+	int upg_shape_count(void)
+	{
+		return SH_COUNT;
+	}
+
+	int upg_planet_create(const upg_planet_desc *d, upg_planet **out)
+	{
+		if (!d || !out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		*out = nullptr;
+		if (d->struct_size != sizeof(upg_planet_desc))
+			return fail(UPG_ERR_ARGUMENT, "upg_planet_desc::struct_size mismatch (%u, expected %zu)", d->struct_size, sizeof(upg_planet_desc));
+		if (d->shape < 0 || d->shape >= SH_COUNT)
+			return fail(UPG_ERR_ARGUMENT, "unknown shape mode configuration (%d)", d->shape);
+		if (d->elevation < 0 || d->elevation >= EL_COUNT)
+			return fail(UPG_ERR_ARGUMENT, "unknown elevation mode configuration (%d)", d->elevation);
+		if (d->coloring < 0 || d->coloring >= CL_COUNT)
+			return fail(UPG_ERR_ARGUMENT, "unknown coloring mode configuration (%d)", d->coloring);
+		if (d->grid_resolution <= 5 || d->grid_resolution > 2048)
+			return fail(UPG_ERR_ARGUMENT, "grid resolution %d outside (5, 2048]", d->grid_resolution);
+		if (d->seed[0] == 0 || d->seed[1] == 0)
+			return fail(UPG_ERR_ARGUMENT, "seed words must be non-zero");
+		if (!(d->box_size > 0))
+			return fail(UPG_ERR_ARGUMENT, "box size must be positive");
+
+		Planet *p = new (std::nothrow) Planet();
+		if (!p)
+			return fail(UPG_ERR_ARGUMENT, "out of memory");
+		std::memset(&p->params, 0, sizeof(p->params));
+		p->params.shape = d->shape;
+		p->params.elevation = d->elevation;
+		p->params.coloring = d->coloring;
+		p->params.poles = d->poles;
+		p->params.flowers = d->flowers;
+		set_grid(p->params, d->box_size, d->grid_resolution);
+		p->boxSize = d->box_size;
+		p->device = d->device;
+
+		// terrainPreseed order (sources/modesConfiguration.cpp:288-306): shape statics, then elevation statics, ...
+		PlanetBuilder b;
+		b.thread.s[0] = d->seed[0];
+		b.thread.s[1] = d->seed[1];
+		b.shapeStatics(p->params);
+		b.elevationStatics(p->params);
+		p->seedLog = b.log;
+
+		// the device side: fails loudly when there is no GPU (no CPU fallback exists)
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e == cudaSuccess)
+		{
+			// keep freed stream-ordered allocations cached in the pool: the per-call scratch (up to res^3 floats) is
+			// re-used by the next call instead of going back to the driver at every synchronisation
+			cudaMemPool_t pool = nullptr;
+			if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess)
+			{
+				uint64_t threshold = UINT64_MAX;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+			}
+		}
+		if (e == cudaSuccess)
+			e = cudaMalloc(&p->status, sizeof(uint32_t) * 4);
+		if (e == cudaSuccess)
+			e = cudaMemset(p->status, 0, sizeof(uint32_t) * 4);
+		if (e != cudaSuccess)
+		{
+			delete p;
+			return cuda_fail(e, "upg_planet_create");
+		}
+		*out = reinterpret_cast<upg_planet *>(p);
+		return UPG_OK;
+	}
+
+	void upg_planet_destroy(upg_planet *planet)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p)
+			return;
+		cudaSetDevice(p->device);
+		if (p->status)
+			cudaFree(p->status);
+		delete p;
+	}
+
+	int upg_planet_seed_log(const upg_planet *planet, uint32_t *out, int capacity)
+	{
+		const Planet *p = reinterpret_cast<const Planet *>(planet);
+		if (!p)
+			return 0;
+		for (int i = 0; i < p->seedLog.count && i < capacity && out; i++)
+			out[i] = p->seedLog.seeds[i];
+		return p->seedLog.count;
+	}
+
+	int upg_field_samples_device(upg_planet *planet, int field, int z0, int z1, float *device_out, void *cuda_stream)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !device_out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		const int res = p->params.grid.res;
+		if (!valid_field(field) || z0 < 0 || z1 > res || z0 > z1)
+			return fail(UPG_ERR_ARGUMENT, "bad field %d or slice range [%d, %d)", field, z0, z1);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		FieldLaunch L;
+		L.out = device_out;
+		L.positions = nullptr;
+		L.count = (uint64_t)(z1 - z0) * res * res;
+		L.z0 = (uint32_t)z0;
+		L.field = field;
+		L.status = p->status;
+		return launch_field(p, L, (cudaStream_t)cuda_stream);
+	}
+
+	int upg_field_samples(upg_planet *planet, int field, int z0, int z1, float *host_out)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !host_out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		const int res = p->params.grid.res;
+		if (!valid_field(field) || z0 < 0 || z1 > res || z0 > z1)
+			return fail(UPG_ERR_ARGUMENT, "bad field %d or slice range [%d, %d)", field, z0, z1);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+
+		// slab pipeline: sample slab k on the compute stream while slab k-1 drains to the host on the copy stream
+		const uint64_t sliceElems = (uint64_t)res * res;
+		const int slabSlices = (int)((((uint64_t)64 << 20) / sizeof(float) + sliceElems - 1) / sliceElems); // ~64 MiB slabs
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		float *buf[2] = { nullptr, nullptr };
+		cudaEvent_t sampled[2] = { nullptr, nullptr }, drained[2] = { nullptr, nullptr };
+		for (int i = 0; i < 2 && e == cudaSuccess; i++)
+		{
+			e = cudaMallocAsync(&buf[i], sizeof(float) * sliceElems * slabSlices, cs.compute);
+			if (e == cudaSuccess)
+				e = cudaEventCreateWithFlags(&sampled[i], cudaEventDisableTiming);
+			if (e == cudaSuccess)
+				e = cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming);
+		}
+		int slab = 0;
+		for (int z = z0; z < z1 && e == cudaSuccess && rc == UPG_OK; z += slabSlices, slab++)
+		{
+			const int b = slab & 1;
+			const int ze = z + slabSlices < z1 ? z + slabSlices : z1;
+			if (slab >= 2)
+				e = cudaStreamWaitEvent(cs.compute, drained[b], 0);
+			if (e != cudaSuccess)
+				break;
+			FieldLaunch L;
+			L.out = buf[b];
+			L.positions = nullptr;
+			L.count = (uint64_t)(ze - z) * sliceElems;
+			L.z0 = (uint32_t)z;
+			L.field = field;
+			L.status = p->status;
+			rc = launch_field(p, L, cs.compute);
+			if (rc)
+				break;
+			e = cudaEventRecord(sampled[b], cs.compute);
+			if (e == cudaSuccess)
+				e = cudaStreamWaitEvent(cs.copy, sampled[b], 0);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(host_out + (uint64_t)(z - z0) * sliceElems, buf[b], sizeof(float) * L.count, cudaMemcpyDeviceToHost, cs.copy);
+			if (e == cudaSuccess)
+				e = cudaEventRecord(drained[b], cs.copy);
+		}
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs.copy);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs.compute);
+		for (int i = 0; i < 2; i++)
+		{
+			if (buf[i])
+				cudaFreeAsync(buf[i], cs.compute);
+			if (sampled[i])
+				cudaEventDestroy(sampled[i]);
+			if (drained[i])
+				cudaEventDestroy(drained[i]);
+		}
+		if (rc == UPG_OK && e != cudaSuccess)
+			rc = cuda_fail(e, "upg_field_samples");
+		if (rc == UPG_OK)
+			rc = check_status(p, cs.compute, "upg_field_samples");
+		cs.close();
+		return rc;
+	}
+
+	int upg_field_points(upg_planet *planet, int field, const float *host_positions, uint64_t n, float *host_out)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || (n && (!host_positions || !host_out)))
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (!valid_field(field))
+			return fail(UPG_ERR_ARGUMENT, "bad field %d", field);
+		if (n == 0)
+			return UPG_OK;
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		float *dpos = nullptr, *dout = nullptr;
+		e = cudaMallocAsync(&dpos, sizeof(float) * 3 * n, cs.compute);
+		if (e == cudaSuccess)
+			e = cudaMallocAsync(&dout, sizeof(float) * n, cs.compute);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dpos, host_positions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs.compute);
+		if (e == cudaSuccess)
+		{
+			FieldLaunch L;
+			L.out = dout;
+			L.positions = dpos;
+			L.count = n;
+			L.z0 = 0;
+			L.field = field;
+			L.status = p->status;
+			rc = launch_field(p, L, cs.compute);
+		}
+		if (e == cudaSuccess && rc == UPG_OK)
+			e = cudaMemcpyAsync(host_out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost, cs.compute);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(cs.compute);
+		if (dpos)
+			cudaFreeAsync(dpos, cs.compute);
+		if (dout)
+			cudaFreeAsync(dout, cs.compute);
+		if (rc == UPG_OK && e != cudaSuccess)
+			rc = cuda_fail(e, "upg_field_points");
+		if (rc == UPG_OK)
+			rc = check_status(p, cs.compute, "upg_field_points");
+		cs.close();
+		return rc;
+	}
+}

@@ -1,0 +1,49 @@
+// upg_field_inst.cu -- instantiates K1 for ONE elevation mode and a range of shapes.
+// Compiled once per (UPG_ELEV, UPG_PART) by the Makefile so that the 34 x 6 specialisations build in parallel.
+#include <cuda_runtime.h>
+
+#include "upg_field.cuh"
+
+#ifndef UPG_ELEV
+#error "compile with -DUPG_ELEV=<0..5> -DUPG_PART=<0..3>"
+#endif
+
+#define UPG_CAT2(a, b, c, d) a##b##c##d
+#define UPG_CAT(a, b, c, d) UPG_CAT2(a, b, c, d)
+
+namespace upg
+{
+	namespace
+	{
+		constexpr int PARTS = 4;
+		constexpr int LO = (SH_COUNT * UPG_PART) / PARTS;
+		constexpr int HI = (SH_COUNT * (UPG_PART + 1)) / PARTS;
+
+		template<int S>
+		struct Dispatch
+		{
+			static bool run(int shape, const PlanetParams &P, const FieldLaunch &L, cudaStream_t stream)
+			{
+				if (shape == S)
+				{
+					const uint64_t blocks = (L.count + FIELD_BLOCK - 1) / FIELD_BLOCK;
+					sdf_sample_kernel<S, UPG_ELEV><<<(unsigned)blocks, FIELD_BLOCK, 0, stream>>>(P, L);
+					return true;
+				}
+				return Dispatch<S + 1>::run(shape, P, L, stream);
+			}
+		};
+		template<>
+		struct Dispatch<HI>
+		{
+			static bool run(int, const PlanetParams &, const FieldLaunch &, cudaStream_t) { return false; }
+		};
+	}
+
+	bool UPG_CAT(field_launch_e, UPG_ELEV, _p, UPG_PART)(int shape, const PlanetParams &P, const FieldLaunch &L, void *stream)
+	{
+		if (shape < LO || shape >= HI)
+			return false;
+		return Dispatch<LO>::run(shape, P, L, (cudaStream_t)stream);
+	}
+}

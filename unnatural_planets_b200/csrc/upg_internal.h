@@ -1,0 +1,54 @@
+// upg_internal.h -- host-side objects shared by the translation units of libupg.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "upg_field.cuh"
+#include "upg_planet_host.h"
+
+namespace upg
+{
+	int fail(int code, const char *fmt, ...);
+	int cuda_fail(cudaError_t e, const char *what);
+
+	// what upg_planet* points to; immutable after upg_planet_create except for the device status word
+	struct Planet
+	{
+		PlanetParams params;
+		SeedLog seedLog;
+		float boxSize = 4000;
+		int device = 0;
+		uint32_t *status = nullptr; // device: bit 0 = NaN sample seen
+	};
+
+	// a private pair of streams per API call: calls arrive concurrently from the reference's pool threads
+	// (sources/generator.cpp:432-439, :159) and must not serialise on the default stream
+	struct CallStreams
+	{
+		cudaStream_t compute = nullptr;
+		cudaStream_t copy = nullptr;
+		int open()
+		{
+			cudaError_t e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
+			if (e == cudaSuccess)
+				e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
+			if (e != cudaSuccess)
+			{
+				close();
+				return cuda_fail(e, "cudaStreamCreate");
+			}
+			return 0;
+		}
+		void close()
+		{
+			if (compute)
+				cudaStreamDestroy(compute);
+			if (copy)
+				cudaStreamDestroy(copy);
+			compute = copy = nullptr;
+		}
+	};
+
+	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
+	int check_status(Planet *planet, cudaStream_t stream, const char *what);
+}

@@ -1,0 +1,582 @@
+// upg_noise.cuh -- GPU coherent-noise library: integer hash lattice, Value / ValueCubic / Perlin /
+// OpenSimplex2 / OpenSimplex2S / Cellular generators and the FBm / Ridged / PingPong fractal drivers,
+// FP32 with register-resident octave loops.
+//
+// Replaces, for the hot path, cage's NoiseFunction::evaluate (externals/cage/sources/libcore/
+// noiseFunction.cpp:111-127) and what it forwards to: FastNoiseLite::GetNoise of the un-vendored
+// submodule Auburn/FastNoiseLite @785f37a9 (configuration mapping: noiseFunction.cpp:14-107).
+// Integer work (primes, hash, value bits, gradient index) must be bit-exact; float work follows
+// the reference's operation order with no FMA contraction (see upg_common.cuh).
+//
+// Noise kind / fractal kind / octave count are template parameters: each call site in the
+// reference fixes them at compile time (e.g. sources/elevationModes.cpp:131-140), only the seed
+// (and, for the asteroid shape, the frequency) are per-planet data.
+#pragma once
+
+#include "upg_common.cuh"
+
+namespace upg
+{
+	// values follow cage's enums (include/cage-core/noiseFunction.h:8-43)
+	enum NoiseType : int
+	{
+		NT_SIMPLEX = 0, // OpenSimplex2
+		NT_SIMPLEX_REDUCED = 1, // OpenSimplex2S
+		NT_CELLULAR = 2,
+		NT_PERLIN = 3,
+		NT_CUBIC = 4, // ValueCubic
+		NT_VALUE = 5,
+	};
+	enum FractalType : int
+	{
+		FT_NONE = 0,
+		FT_FBM = 1,
+		FT_RIDGED = 2,
+		FT_PINGPONG = 3,
+	};
+	enum CellDistance : int
+	{
+		CD_EUCLIDEAN = 0,
+		CD_EUCLIDEAN_SQ = 1,
+		CD_MANHATTAN = 2,
+		CD_HYBRID = 3,
+	};
+	enum CellOperation : int
+	{
+		CO_CELL = 0,
+		CO_DISTANCE = 1,
+		CO_DISTANCE2 = 2,
+		CO_ADD = 3,
+		CO_SUBTRACT = 4,
+		CO_MULTIPLY = 5,
+		CO_DIVIDE = 6,
+	};
+
+	// per-planet data of one noise instance (the compile-time part lives in the template arguments)
+	struct NoiseInst
+	{
+		int32_t seed;
+		float frequency;
+		float lacunarity;
+		float gain;
+		float bounding; // 1 / sum |gain|^i, computed on the host with the same float loop
+	};
+
+	constexpr int32_t PRIME_X = 501125321;
+	constexpr int32_t PRIME_Y = 1136930381;
+	constexpr int32_t PRIME_Z = 1720413743;
+
+	UPG_HD int32_t imul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+	UPG_HD int32_t iadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+	UPG_HD int32_t isub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+	UPG_HD int32_t ishl(int32_t a, int s) { return (int32_t)((uint32_t)a << s); }
+
+	UPG_HD int32_t lattice_hash(int32_t seed, int32_t xp, int32_t yp, int32_t zp) { return imul(seed ^ xp ^ yp ^ zp, 0x27d4eb2d); }
+	UPG_HD int32_t lattice_hash(int32_t seed, int32_t xp, int32_t yp) { return imul(seed ^ xp ^ yp, 0x27d4eb2d); }
+
+	UPG_HD float value_from_hash(int32_t h)
+	{
+		h = imul(h, h);
+		h ^= ishl(h, 19);
+		return (float)h * (1.0f / 2147483648.0f);
+	}
+	UPG_HD float val_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp) { return value_from_hash(lattice_hash(seed, xp, yp, zp)); }
+	UPG_HD float val_coord(int32_t seed, int32_t xp, int32_t yp) { return value_from_hash(lattice_hash(seed, xp, yp)); }
+
+	// Gradient dot product.  The library indexes a 64-entry table of directions (the 12 cube-edge
+	// vectors five times over, then (1,1,0) (0,-1,1) (-1,1,0) (0,-1,-1)).  Every entry has one zero
+	// component and two +-1 components, so x*gx + y*gy + z*gz (evaluated left to right) is exactly
+	// (+-a) + (+-b) for two of the three offsets: selecting and sign-flipping reproduces the table
+	// result bit for bit without a divergent memory lookup.
+	UPG_HD float grad_dot(int32_t h, float xd, float yd, float zd)
+	{
+		h ^= h >> 15;
+		const uint32_t e = ((uint32_t)h >> 2) & 63u;
+		// e < 60: e % 12; fillers 60..63 -> entries 8, 1, 9, 3 of the 12
+		uint32_t c = e - 12u * ((e * 43u) >> 9);
+		if (e >= 60u)
+			c = (0x3918u >> ((e - 60u) * 4u)) & 15u;
+		const uint32_t grp = c >> 2; // 0: (0,s1,s2)  1: (s1,0,s2)  2: (s1,s2,0)
+		const float a = grp == 0u ? yd : xd;
+		const float b = grp == 2u ? yd : zd;
+		const float sa = (c & 1u) ? -a : a;
+		const float sb = (c & 2u) ? -b : b;
+		return sa + sb;
+	}
+	UPG_HD float grad_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) { return grad_dot(lattice_hash(seed, xp, yp, zp), xd, yd, zd); }
+
+	UPG_HD int32_t fast_floor(float f) { return f >= 0 ? (int32_t)f : (int32_t)f - 1; }
+	UPG_HD int32_t fast_round(float f) { return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f); }
+	UPG_HD float nlerp(float a, float b, float t) { return a + t * (b - a); }
+	UPG_HD float interp_hermite(float t) { return t * t * (3 - 2 * t); }
+	UPG_HD float interp_quintic(float t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+	UPG_HD float cubic_lerp(float a, float b, float c, float d, float t)
+	{
+		const float p = (d - c) - (a - b);
+		return t * t * t * p + t * t * ((a - b) - p) + t * (c - a) + b;
+	}
+
+	// ---- single-octave generators --------------------------------------------------------------
+
+	UPG_HD float single_value(int32_t seed, float x, float y, float z)
+	{
+		int32_t x0 = fast_floor(x), y0 = fast_floor(y), z0 = fast_floor(z);
+		const float xs = interp_hermite(x - (float)x0);
+		const float ys = interp_hermite(y - (float)y0);
+		const float zs = interp_hermite(z - (float)z0);
+		x0 = imul(x0, PRIME_X);
+		y0 = imul(y0, PRIME_Y);
+		z0 = imul(z0, PRIME_Z);
+		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y), z1 = iadd(z0, PRIME_Z);
+		// hoist the seed ^ y ^ z part of the eight hashes
+		const int32_t s00 = seed ^ y0 ^ z0, s10 = seed ^ y1 ^ z0, s01 = seed ^ y0 ^ z1, s11 = seed ^ y1 ^ z1;
+		const float xf00 = nlerp(value_from_hash(imul(s00 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s00 ^ x1, 0x27d4eb2d)), xs);
+		const float xf10 = nlerp(value_from_hash(imul(s10 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s10 ^ x1, 0x27d4eb2d)), xs);
+		const float xf01 = nlerp(value_from_hash(imul(s01 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s01 ^ x1, 0x27d4eb2d)), xs);
+		const float xf11 = nlerp(value_from_hash(imul(s11 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s11 ^ x1, 0x27d4eb2d)), xs);
+		const float yf0 = nlerp(xf00, xf10, ys);
+		const float yf1 = nlerp(xf01, xf11, ys);
+		return nlerp(yf0, yf1, zs);
+	}
+
+	// 2-D value noise: what cage's evaluate(Real) reaches as GetNoise(x, 0) (noiseFunction.cpp:111-115)
+	UPG_HD float single_value2(int32_t seed, float x, float y)
+	{
+		int32_t x0 = fast_floor(x), y0 = fast_floor(y);
+		const float xs = interp_hermite(x - (float)x0);
+		const float ys = interp_hermite(y - (float)y0);
+		x0 = imul(x0, PRIME_X);
+		y0 = imul(y0, PRIME_Y);
+		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y);
+		const float xf0 = nlerp(val_coord(seed, x0, y0), val_coord(seed, x1, y0), xs);
+		const float xf1 = nlerp(val_coord(seed, x0, y1), val_coord(seed, x1, y1), xs);
+		return nlerp(xf0, xf1, ys);
+	}
+
+	UPG_HD float single_perlin(int32_t seed, float x, float y, float z)
+	{
+		int32_t x0 = fast_floor(x), y0 = fast_floor(y), z0 = fast_floor(z);
+		const float xd0 = x - (float)x0, yd0 = y - (float)y0, zd0 = z - (float)z0;
+		const float xd1 = xd0 - 1, yd1 = yd0 - 1, zd1 = zd0 - 1;
+		const float xs = interp_quintic(xd0), ys = interp_quintic(yd0), zs = interp_quintic(zd0);
+		x0 = imul(x0, PRIME_X);
+		y0 = imul(y0, PRIME_Y);
+		z0 = imul(z0, PRIME_Z);
+		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y), z1 = iadd(z0, PRIME_Z);
+		const int32_t s00 = seed ^ y0 ^ z0, s10 = seed ^ y1 ^ z0, s01 = seed ^ y0 ^ z1, s11 = seed ^ y1 ^ z1;
+		const float xf00 = nlerp(grad_dot(imul(s00 ^ x0, 0x27d4eb2d), xd0, yd0, zd0), grad_dot(imul(s00 ^ x1, 0x27d4eb2d), xd1, yd0, zd0), xs);
+		const float xf10 = nlerp(grad_dot(imul(s10 ^ x0, 0x27d4eb2d), xd0, yd1, zd0), grad_dot(imul(s10 ^ x1, 0x27d4eb2d), xd1, yd1, zd0), xs);
+		const float xf01 = nlerp(grad_dot(imul(s01 ^ x0, 0x27d4eb2d), xd0, yd0, zd1), grad_dot(imul(s01 ^ x1, 0x27d4eb2d), xd1, yd0, zd1), xs);
+		const float xf11 = nlerp(grad_dot(imul(s11 ^ x0, 0x27d4eb2d), xd0, yd1, zd1), grad_dot(imul(s11 ^ x1, 0x27d4eb2d), xd1, yd1, zd1), xs);
+		const float yf0 = nlerp(xf00, xf10, ys);
+		const float yf1 = nlerp(xf01, xf11, ys);
+		return nlerp(yf0, yf1, zs) * 0.964921414852142333984375f;
+	}
+
+	UPG_HD float single_cubic(int32_t seed, float x, float y, float z)
+	{
+		int32_t x1 = fast_floor(x), y1 = fast_floor(y), z1 = fast_floor(z);
+		const float xs = x - (float)x1, ys = y - (float)y1, zs = z - (float)z1;
+		x1 = imul(x1, PRIME_X);
+		y1 = imul(y1, PRIME_Y);
+		z1 = imul(z1, PRIME_Z);
+		const int32_t xi0 = isub(x1, PRIME_X), xi2 = iadd(x1, PRIME_X), xi3 = iadd(x1, ishl(PRIME_X, 1));
+		const int32_t yb = isub(y1, PRIME_Y), zb = isub(z1, PRIME_Z);
+		float zr[4];
+		int32_t zp = zb;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		{
+			float yr[4];
+			int32_t yp = yb;
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+			{
+				const int32_t s = seed ^ yp ^ zp;
+				yr[j] = cubic_lerp(value_from_hash(imul(s ^ xi0, 0x27d4eb2d)), value_from_hash(imul(s ^ x1, 0x27d4eb2d)), value_from_hash(imul(s ^ xi2, 0x27d4eb2d)), value_from_hash(imul(s ^ xi3, 0x27d4eb2d)), xs);
+				yp = iadd(yp, PRIME_Y);
+			}
+			zr[k] = cubic_lerp(yr[0], yr[1], yr[2], yr[3], ys);
+			zp = iadd(zp, PRIME_Z);
+		}
+		return cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * (1 / (1.5f * 1.5f * 1.5f));
+	}
+
+	// OpenSimplex2, 3-D: two half-offset cubic lattices (seed and ~seed), <= 2 kernel terms from each
+	UPG_HD float single_simplex(int32_t seed, float x, float y, float z)
+	{
+		int32_t i = fast_round(x), j = fast_round(y), k = fast_round(z);
+		float x0 = x - (float)i, y0 = y - (float)j, z0 = z - (float)k;
+
+		int32_t xNSign = (int32_t)(-1.0f - x0) | 1;
+		int32_t yNSign = (int32_t)(-1.0f - y0) | 1;
+		int32_t zNSign = (int32_t)(-1.0f - z0) | 1;
+
+		float ax0 = (float)xNSign * -x0;
+		float ay0 = (float)yNSign * -y0;
+		float az0 = (float)zNSign * -z0;
+
+		i = imul(i, PRIME_X);
+		j = imul(j, PRIME_Y);
+		k = imul(k, PRIME_Z);
+
+		float value = 0;
+		float a = (0.6f - x0 * x0) - (y0 * y0 + z0 * z0);
+
+#pragma unroll
+		for (int l = 0; l < 2; l++)
+		{
+			if (a > 0)
+				value += (a * a) * (a * a) * grad_coord(seed, i, j, k, x0, y0, z0);
+
+			if (ax0 >= ay0 && ax0 >= az0)
+			{
+				float b = a + ax0 + ax0;
+				if (b > 1)
+				{
+					b -= 1;
+					value += (b * b) * (b * b) * grad_coord(seed, isub(i, imul(xNSign, PRIME_X)), j, k, x0 + (float)xNSign, y0, z0);
+				}
+			}
+			else if (ay0 > ax0 && ay0 >= az0)
+			{
+				float b = a + ay0 + ay0;
+				if (b > 1)
+				{
+					b -= 1;
+					value += (b * b) * (b * b) * grad_coord(seed, i, isub(j, imul(yNSign, PRIME_Y)), k, x0, y0 + (float)yNSign, z0);
+				}
+			}
+			else
+			{
+				float b = a + az0 + az0;
+				if (b > 1)
+				{
+					b -= 1;
+					value += (b * b) * (b * b) * grad_coord(seed, i, j, isub(k, imul(zNSign, PRIME_Z)), x0, y0, z0 + (float)zNSign);
+				}
+			}
+
+			if (l == 1)
+				break;
+
+			ax0 = 0.5f - ax0;
+			ay0 = 0.5f - ay0;
+			az0 = 0.5f - az0;
+
+			x0 = (float)xNSign * ax0;
+			y0 = (float)yNSign * ay0;
+			z0 = (float)zNSign * az0;
+
+			a += (0.75f - ax0) - (ay0 + az0);
+
+			i = iadd(i, (xNSign >> 1) & PRIME_X);
+			j = iadd(j, (yNSign >> 1) & PRIME_Y);
+			k = iadd(k, (zNSign >> 1) & PRIME_Z);
+
+			xNSign = -xNSign;
+			yNSign = -yNSign;
+			zNSign = -zNSign;
+
+			seed = ~seed;
+		}
+		return value * 32.69428253173828125f;
+	}
+
+	// OpenSimplex2S, 3-D: floor-based, kernel 0.75 - r^2; two fixed terms + up to eight optional ones
+	UPG_HD float s2s_term(float a, int32_t seed, int32_t xp, int32_t yp, int32_t zp, float dx, float dy, float dz) { return (a * a) * (a * a) * grad_coord(seed, xp, yp, zp, dx, dy, dz); }
+
+	UPG_HD float single_simplex_s(int32_t seed, float x, float y, float z)
+	{
+		int32_t i = fast_floor(x), j = fast_floor(y), k = fast_floor(z);
+		const float xi = x - (float)i, yi = y - (float)j, zi = z - (float)k;
+
+		i = imul(i, PRIME_X);
+		j = imul(j, PRIME_Y);
+		k = imul(k, PRIME_Z);
+		const int32_t seed2 = iadd(seed, 1293373);
+
+		const int32_t xNMask = (int32_t)(-0.5f - xi);
+		const int32_t yNMask = (int32_t)(-0.5f - yi);
+		const int32_t zNMask = (int32_t)(-0.5f - zi);
+
+		const float x0 = xi + (float)xNMask;
+		const float y0 = yi + (float)yNMask;
+		const float z0 = zi + (float)zNMask;
+		const float a0 = 0.75f - x0 * x0 - y0 * y0 - z0 * z0;
+		float value = s2s_term(a0, seed, iadd(i, xNMask & PRIME_X), iadd(j, yNMask & PRIME_Y), iadd(k, zNMask & PRIME_Z), x0, y0, z0);
+
+		const float x1 = xi - 0.5f;
+		const float y1 = yi - 0.5f;
+		const float z1 = zi - 0.5f;
+		const float a1 = 0.75f - x1 * x1 - y1 * y1 - z1 * z1;
+		value += s2s_term(a1, seed2, iadd(i, PRIME_X), iadd(j, PRIME_Y), iadd(k, PRIME_Z), x1, y1, z1);
+
+		const float xAFlipMask0 = (float)((xNMask | 1) << 1) * x1;
+		const float yAFlipMask0 = (float)((yNMask | 1) << 1) * y1;
+		const float zAFlipMask0 = (float)((zNMask | 1) << 1) * z1;
+		const float xAFlipMask1 = (float)(-2 - (xNMask << 2)) * x1 - 1.0f;
+		const float yAFlipMask1 = (float)(-2 - (yNMask << 2)) * y1 - 1.0f;
+		const float zAFlipMask1 = (float)(-2 - (zNMask << 2)) * z1 - 1.0f;
+
+		const int32_t PX2 = ishl(PRIME_X, 1), PY2 = ishl(PRIME_Y, 1), PZ2 = ishl(PRIME_Z, 1);
+		const float xs = (float)(xNMask | 1), ys = (float)(yNMask | 1), zs = (float)(zNMask | 1);
+
+		bool skip5 = false;
+		const float a2 = xAFlipMask0 + a0;
+		if (a2 > 0)
+		{
+			value += s2s_term(a2, seed, iadd(i, ~xNMask & PRIME_X), iadd(j, yNMask & PRIME_Y), iadd(k, zNMask & PRIME_Z), x0 - xs, y0, z0);
+		}
+		else
+		{
+			const float a3 = yAFlipMask0 + zAFlipMask0 + a0;
+			if (a3 > 0)
+				value += s2s_term(a3, seed, iadd(i, xNMask & PRIME_X), iadd(j, ~yNMask & PRIME_Y), iadd(k, ~zNMask & PRIME_Z), x0, y0 - ys, z0 - zs);
+			const float a4 = xAFlipMask1 + a1;
+			if (a4 > 0)
+			{
+				value += s2s_term(a4, seed2, iadd(i, xNMask & PX2), iadd(j, PRIME_Y), iadd(k, PRIME_Z), xs + x1, y1, z1);
+				skip5 = true;
+			}
+		}
+
+		bool skip9 = false;
+		const float a6 = yAFlipMask0 + a0;
+		if (a6 > 0)
+		{
+			value += s2s_term(a6, seed, iadd(i, xNMask & PRIME_X), iadd(j, ~yNMask & PRIME_Y), iadd(k, zNMask & PRIME_Z), x0, y0 - ys, z0);
+		}
+		else
+		{
+			const float a7 = xAFlipMask0 + zAFlipMask0 + a0;
+			if (a7 > 0)
+				value += s2s_term(a7, seed, iadd(i, ~xNMask & PRIME_X), iadd(j, yNMask & PRIME_Y), iadd(k, ~zNMask & PRIME_Z), x0 - xs, y0, z0 - zs);
+			const float a8 = yAFlipMask1 + a1;
+			if (a8 > 0)
+			{
+				value += s2s_term(a8, seed2, iadd(i, PRIME_X), iadd(j, yNMask & PY2), iadd(k, PRIME_Z), x1, ys + y1, z1);
+				skip9 = true;
+			}
+		}
+
+		bool skipD = false;
+		const float aA = zAFlipMask0 + a0;
+		if (aA > 0)
+		{
+			value += s2s_term(aA, seed, iadd(i, xNMask & PRIME_X), iadd(j, yNMask & PRIME_Y), iadd(k, ~zNMask & PRIME_Z), x0, y0, z0 - zs);
+		}
+		else
+		{
+			const float aB = xAFlipMask0 + yAFlipMask0 + a0;
+			if (aB > 0)
+				value += s2s_term(aB, seed, iadd(i, ~xNMask & PRIME_X), iadd(j, ~yNMask & PRIME_Y), iadd(k, zNMask & PRIME_Z), x0 - xs, y0 - ys, z0);
+			const float aC = zAFlipMask1 + a1;
+			if (aC > 0)
+			{
+				value += s2s_term(aC, seed2, iadd(i, PRIME_X), iadd(j, PRIME_Y), iadd(k, zNMask & PZ2), x1, y1, zs + z1);
+				skipD = true;
+			}
+		}
+
+		if (!skip5)
+		{
+			const float a5 = yAFlipMask1 + zAFlipMask1 + a1;
+			if (a5 > 0)
+				value += s2s_term(a5, seed2, iadd(i, PRIME_X), iadd(j, yNMask & PY2), iadd(k, zNMask & PZ2), x1, ys + y1, zs + z1);
+		}
+		if (!skip9)
+		{
+			const float a9 = xAFlipMask1 + zAFlipMask1 + a1;
+			if (a9 > 0)
+				value += s2s_term(a9, seed2, iadd(i, xNMask & PX2), iadd(j, PRIME_Y), iadd(k, zNMask & PZ2), xs + x1, y1, zs + z1);
+		}
+		if (!skipD)
+		{
+			const float aD = xAFlipMask1 + yAFlipMask1 + a1;
+			if (aD > 0)
+				value += s2s_term(aD, seed2, iadd(i, xNMask & PX2), iadd(j, yNMask & PY2), iadd(k, PRIME_Z), xs + x1, ys + y1, z1);
+		}
+
+		return value * 9.046026385208288f;
+	}
+
+	// Cellular: 27 neighbouring cells, one jittered feature point each.  `rv` = the 256 x float4 jitter
+	// direction table handed to the planet at creation (see upg.h: upstream's table is not
+	// reconstructible, the oracle declares a substitute and the product receives it as data).
+	template<int DIST, int OP>
+	UPG_HD float single_cellular(const float *rv, int32_t seed, float x, float y, float z)
+	{
+		const int32_t xr = fast_round(x), yr = fast_round(y), zr = fast_round(z);
+		float d0 = 1e10f, d1 = 1e10f;
+		int32_t closest = 0;
+		const float jitter = 0.39614353f * 1.0f;
+
+		int32_t xp = imul(xr - 1, PRIME_X);
+		const int32_t ypBase = imul(yr - 1, PRIME_Y);
+		const int32_t zpBase = imul(zr - 1, PRIME_Z);
+		for (int32_t xi = xr - 1; xi <= xr + 1; xi++)
+		{
+			int32_t yp = ypBase;
+			for (int32_t yi = yr - 1; yi <= yr + 1; yi++)
+			{
+				int32_t zp = zpBase;
+				for (int32_t zi = zr - 1; zi <= zr + 1; zi++)
+				{
+					const int32_t h = lattice_hash(seed, xp, yp, zp);
+					const int32_t idx = h & (255 << 2);
+					const float vx = ((float)xi - x) + rv[idx] * jitter;
+					const float vy = ((float)yi - y) + rv[idx | 1] * jitter;
+					const float vz = ((float)zi - z) + rv[idx | 2] * jitter;
+					float nd;
+					if (DIST == CD_MANHATTAN)
+						nd = abs_(vx) + abs_(vy) + abs_(vz);
+					else if (DIST == CD_HYBRID)
+						nd = (abs_(vx) + abs_(vy) + abs_(vz)) + (vx * vx + vy * vy + vz * vz);
+					else
+						nd = vx * vx + vy * vy + vz * vz;
+					d1 = fmax_(fmin_(d1, nd), d0);
+					if (nd < d0)
+					{
+						d0 = nd;
+						closest = h;
+					}
+					zp = iadd(zp, PRIME_Z);
+				}
+				yp = iadd(yp, PRIME_Y);
+			}
+			xp = iadd(xp, PRIME_X);
+		}
+
+		if (DIST == CD_EUCLIDEAN && OP >= CO_DISTANCE)
+		{
+			d0 = sqrtf(d0);
+			if (OP >= CO_DISTANCE2)
+				d1 = sqrtf(d1);
+		}
+
+		switch (OP)
+		{
+			case CO_CELL:
+				return (float)closest * (1 / 2147483648.0f);
+			case CO_DISTANCE:
+				return d0 - 1;
+			case CO_DISTANCE2:
+				return d1 - 1;
+			case CO_ADD:
+				return (d1 + d0) * 0.5f - 1;
+			case CO_SUBTRACT:
+				return d1 - d0 - 1;
+			case CO_MULTIPLY:
+				return d1 * d0 * 0.5f - 1;
+			case CO_DIVIDE:
+				return d0 / d1 - 1;
+			default:
+				return 0;
+		}
+	}
+
+	// ---- dispatch + fractal drivers -----------------------------------------------------------------
+
+	template<int TYPE>
+	UPG_HD float noise_single(int32_t seed, float x, float y, float z)
+	{
+		if (TYPE == NT_SIMPLEX)
+			return single_simplex(seed, x, y, z);
+		if (TYPE == NT_SIMPLEX_REDUCED)
+			return single_simplex_s(seed, x, y, z);
+		if (TYPE == NT_PERLIN)
+			return single_perlin(seed, x, y, z);
+		if (TYPE == NT_CUBIC)
+			return single_cubic(seed, x, y, z);
+		return single_value(seed, x, y, z);
+	}
+
+	UPG_HD float ping_pong(float t)
+	{
+		t -= (float)((int32_t)(t * 0.5f) * 2);
+		return t < 1 ? t : 2 - t;
+	}
+
+	template<int FRACTAL>
+	UPG_HD float fractal_term(float n)
+	{
+		if (FRACTAL == FT_RIDGED)
+			return abs_(n) * -2 + 1; // library: noise = |n|; (noise * -2 + 1)
+		if (FRACTAL == FT_PINGPONG)
+			return (ping_pong((n + 1) * 2.0f) - 0.5f) * 2;
+		return n;
+	}
+
+	// GetNoise(x, y, z): frequency scale, domain rotation for the two simplex kinds, fractal loop.
+	// weighted strength stays at the library default 0 (cage never sets it) => amp *= lerp(1, ., 0) == amp.
+	template<int TYPE, int FRACTAL, int OCTAVES>
+	UPG_HD float noise3(const NoiseInst &n, float x, float y, float z)
+	{
+		x *= n.frequency;
+		y *= n.frequency;
+		z *= n.frequency;
+		if (TYPE == NT_SIMPLEX || TYPE == NT_SIMPLEX_REDUCED)
+		{
+			const float R3 = (float)(2.0 / 3.0);
+			const float r = (x + y + z) * R3;
+			x = r - x;
+			y = r - y;
+			z = r - z;
+		}
+		if (FRACTAL == FT_NONE)
+			return noise_single<TYPE>(n.seed, x, y, z);
+		int32_t seed = n.seed;
+		float sum = 0;
+		float amp = n.bounding;
+#pragma unroll
+		for (int o = 0; o < OCTAVES; o++)
+		{
+			const float v = noise_single<TYPE>(seed, x, y, z);
+			seed = iadd(seed, 1);
+			sum += fractal_term<FRACTAL>(v) * amp;
+			x *= n.lacunarity;
+			y *= n.lacunarity;
+			z *= n.lacunarity;
+			amp *= n.gain;
+		}
+		return sum;
+	}
+
+	template<int TYPE, int FRACTAL, int OCTAVES>
+	UPG_HD float noise3(const NoiseInst &n, V3 p)
+	{
+		return noise3<TYPE, FRACTAL, OCTAVES>(n, p.x, p.y, p.z);
+	}
+
+	// cellular variant (needs the jitter table and the distance / return kind)
+	template<int DIST, int OP, int FRACTAL, int OCTAVES>
+	UPG_HD float noise3_cellular(const float *rv, const NoiseInst &n, float x, float y, float z)
+	{
+		x *= n.frequency;
+		y *= n.frequency;
+		z *= n.frequency;
+		if (FRACTAL == FT_NONE)
+			return single_cellular<DIST, OP>(rv, n.seed, x, y, z);
+		int32_t seed = n.seed;
+		float sum = 0;
+		float amp = n.bounding;
+		for (int o = 0; o < OCTAVES; o++)
+		{
+			const float v = single_cellular<DIST, OP>(rv, seed, x, y, z);
+			seed = iadd(seed, 1);
+			sum += fractal_term<FRACTAL>(v) * amp;
+			x *= n.lacunarity;
+			y *= n.lacunarity;
+			z *= n.lacunarity;
+			amp *= n.gain;
+		}
+		return sum;
+	}
+
+	// GetNoise(x, 0) for the Value kind, no fractal (sources/coloringModes.cpp:36-48)
+	UPG_HD float noise1_value(const NoiseInst &n, float x)
+	{
+		return single_value2(n.seed, x * n.frequency, 0.0f * n.frequency);
+	}
+}

@@ -1,0 +1,81 @@
+"""`Planet`: Python face of upg_planet (include/upg.h), mirroring how the reference is configured:
+`unnatural-planets --shape S --elevation E --colors C [--poles] [--flowers]` (sources/main.cpp:17-54) plus the
+explicit seed the reference lacks."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+# the reference's name tables, in order (sources/modesConfiguration.cpp:78-113, 176-183, 207-211)
+SHAPES = ("asteroid", "belt", "bowl", "box", "bunny", "capsule", "cube", "disk", "doubletorus", "fibers", "gear", "h2o", "h3o", "h4o", "hemispheres", "hexagon", "hexagonalprism", "insidecube", "knot", "mandelbulb", "mobiusstrip", "monkeyhead", "octahedron", "pipe", "sphere", "square", "tetrahedron", "torus", "toruscross", "triangularprism", "tube", "twistedhexagonalprism", "twistedplane", "wormhole")
+ELEVATIONS = ("none", "simple", "legacy", "lakes", "islands", "craters")
+COLORINGS = ("default", "barren", "debug")
+DEFAULT_SEED = (1346519564496, 42245614964156)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Planet:
+    def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0):
+        L = capi.load_library()
+        d = capi.PlanetDesc()
+        L.upg_planet_desc_default(C.byref(d))
+        sid, eid, cid = L.upg_shape_id(shape.encode()), L.upg_elevation_id(elevation.encode()), L.upg_coloring_id(coloring.encode())
+        if sid < 0:
+            raise ValueError("unknown shape mode configuration: %r" % shape)
+        if eid < 0:
+            raise ValueError("unknown elevation mode configuration: %r" % elevation)
+        if cid < 0:
+            raise ValueError("unknown coloring mode configuration: %r" % coloring)
+        d.shape, d.elevation, d.coloring = sid, eid, cid
+        d.poles, d.flowers = int(poles), int(flowers)
+        d.seed[0], d.seed[1] = seed
+        d.box_size = box
+        d.grid_resolution = grid
+        d.device = device
+        self.res = grid
+        self.box = box
+        self.device = device
+        self._lib = L
+        self._h = C.c_void_p()
+        capi.check(L.upg_planet_create(C.byref(d), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.upg_planet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed_log(self):
+        out = np.zeros(128, dtype=np.uint32)
+        n = self._lib.upg_planet_seed_log(self._h, _ptr(out), 128)
+        return out[:n].copy()
+
+    # K1 ------------------------------------------------------------------------------------------
+    def field_samples(self, field="land", z0=0, z1=None, out=None):
+        """terrainSdf* over z-slices [z0, z1) of the grid -> host float32 array [z][y][x]."""
+        z1 = self.res if z1 is None else z1
+        if out is None:
+            out = np.empty((z1 - z0, self.res, self.res), dtype=np.float32)
+        capi.check(self._lib.upg_field_samples(self._h, capi.FIELDS[field], z0, z1, _ptr(out)))
+        return out
+
+    def field_samples_device(self, field, z0, z1, device_ptr, stream=0):
+        """asynchronous, into device memory (an integer device pointer), on CUDA stream handle `stream`."""
+        capi.check(self._lib.upg_field_samples_device(self._h, capi.FIELDS[field], z0, z1, C.c_void_p(device_ptr), C.c_void_p(stream)))
+
+    def field_points(self, field, positions):
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(len(pos), dtype=np.float32)
+        capi.check(self._lib.upg_field_points(self._h, capi.FIELDS[field], _ptr(pos), len(pos), _ptr(out)))
+        return out
