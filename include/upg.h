@@ -114,6 +114,42 @@ int upg_field_samples_device(upg_planet *planet, int field, int z0, int z1, floa
  * mesh culling (sources/meshGeneration.cpp:62-68) and the parity probes */
 int upg_field_points(upg_planet *planet, int field, const float *host_positions, uint64_t n, float *host_out);
 
+/*
+ * The triangle mesh of one field as MarchingCubes::makeMesh builds it up to and including the vertex normals
+ * (externals/cage/sources/libcore/mesh/marchingCubes.cpp:176-227): dualmc::DualMC<float>::build(iso 0, manifold, shared
+ * vertices), grid -> world, quad split by the shorter diagonal, degenerate-triangle filter, area-weighted normals --
+ * with the reference's vertex, quad and triangle ORDER.  The remaining clean-up of makeMesh / meshGenerateGeneric
+ * (removeNonManifoldTriangles, meshClip, meshRemoveDisconnected, meshFlipNormals: marchingCubes.cpp:237-240,
+ * sources/meshGeneration.cpp:41-42) stays with the caller (cage functions over these arrays).
+ * All arrays are pinned host memory owned by the library until upg_mesh_free().
+ */
+typedef struct upg_mesh
+{
+	float *positions; /* vertex_count x 3, world units                 -> Mesh::positions(PointerRange<const Vec3>) */
+	float *normals; /* vertex_count x 3                              -> Mesh::normals(...) */
+	uint32_t *indices; /* index_count (3 per triangle)                  -> Mesh::indices(...) */
+	float *dmc_vertices; /* vertex_count x 3, dualmc::Vertex in GRID units (parity with dualmc's own output) */
+	uint32_t *dmc_quads; /* quad_count x 4, dualmc::Quad */
+	uint32_t vertex_count;
+	uint32_t index_count;
+	uint32_t quad_count;
+	uint32_t reserved;
+	uint64_t near_zero_samples; /* samples with |value| < 1e-3: where sign / topology parity with a CPU run is not promised */
+	void *owner; /* internal */
+} upg_mesh;
+
+/* K1 + K2..K4.  Replaces the body of meshGenerateGeneric<FNC>() up to makeMesh's normals (sources/meshGeneration.cpp:32-40):
+ * samples `field` over the planet's grid on the device and extracts the isosurface without the samples ever leaving HBM.
+ * UPG_ERR_EMPTY_MESH when no triangle results (the reference throws "generated empty base land mesh", :51-52). */
+int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out);
+
+/* K2..K4 alone over caller-provided samples (host memory, layout [z][y][x]): MarchingCubes::densities(values) followed by
+ * makeMesh() (include/cage-core/marchingCubes.h:16,27).  `full_resolution` / `box_size` define the grid -> world mapping
+ * (MarchingCubesCreateConfig::position); pass rx = ry = rz = full_resolution for a whole grid. */
+int upg_isosurface(const float *host_samples, int rx, int ry, int rz, float box_size, int full_resolution, int device, upg_mesh *out);
+
+void upg_mesh_free(upg_mesh *mesh);
+
 /* measurement helper for bench.py: the FP32 FMA ceiling (TFLOP/s, FMA = 2 flop) of `device`, measured live with a
  * dependent-free FFMA kernel -- the roofline denominator of the compute-bound kernels (K1 sampling, K6 texel baking);
  * MEASURED_PEAKS.json only carries HBM and tensor-core peaks */

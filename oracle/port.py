@@ -88,3 +88,28 @@ def sample_rate(shape, elevation, res, slices, threads):
     p.grid("land", res, z0=z0, z1=z0 + slices, threads=threads)
     dt = time.perf_counter() - t
     return slices * res * res / dt, dt
+
+
+def isosurface(dens, box=4000.0, full_res=None, iso=0.0, manifold=True):
+    """dualmc (shared vertices) + the triangle tail of MarchingCubes::makeMesh, serial restatement (up_oracle_mesh.cpp)"""
+    L = lib()
+    L.upo_isosurface.restype = C.c_void_p
+    L.upo_isosurface.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int]
+    L.upo_isosurface_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+    L.upo_isosurface_copy.argtypes = [C.c_void_p] * 6
+    L.upo_isosurface_free.argtypes = [C.c_void_p]
+    dens = np.ascontiguousarray(dens, dtype=np.float32)
+    rz, ry, rx = dens.shape
+    h = L.upo_isosurface(_p(dens), rx, ry, rz, iso, int(manifold), box, full_res or rx)
+    nv, nq, ni = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    L.upo_isosurface_sizes(C.c_void_p(h), C.byref(nv), C.byref(nq), C.byref(ni))
+    out = dict(
+        dmc_vertices=np.zeros((nv.value, 3), np.float32),
+        dmc_quads=np.zeros((nq.value, 4), np.int32),
+        positions=np.zeros((nv.value, 3), np.float32),
+        normals=np.zeros((nv.value, 3), np.float32),
+        indices=np.zeros(ni.value, np.uint32),
+    )
+    L.upo_isosurface_copy(C.c_void_p(h), _p(out["dmc_vertices"]), _p(out["dmc_quads"]), _p(out["positions"]), _p(out["normals"]), _p(out["indices"]))
+    L.upo_isosurface_free(C.c_void_p(h))
+    return out

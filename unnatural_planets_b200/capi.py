@@ -35,12 +35,14 @@ class Mesh(C.Structure):
         ("positions", C.POINTER(C.c_float)),
         ("normals", C.POINTER(C.c_float)),
         ("indices", C.POINTER(C.c_uint32)),
+        ("dmc_vertices", C.POINTER(C.c_float)),
+        ("dmc_quads", C.POINTER(C.c_uint32)),
         ("vertex_count", C.c_uint32),
         ("index_count", C.c_uint32),
         ("quad_count", C.c_uint32),
-        ("active_cells", C.c_uint32),
+        ("reserved", C.c_uint32),
         ("near_zero_samples", C.c_uint64),
-        ("_owner", C.c_void_p),
+        ("owner", C.c_void_p),
     ]
 
 
@@ -76,6 +78,10 @@ def load_library():
     L.upg_field_samples.argtypes = [vp, i32, i32, i32, fp]
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
+    L.upg_field_mesh.argtypes = [vp, i32, C.POINTER(Mesh)]
+    L.upg_isosurface.argtypes = [fp, i32, i32, i32, C.c_float, i32, i32, C.POINTER(Mesh)]
+    L.upg_mesh_free.argtypes = [C.POINTER(Mesh)]
+    L.upg_mesh_free.restype = None
     L.upg_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
     _lib = L
     return L

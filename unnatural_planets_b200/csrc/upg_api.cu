@@ -397,3 +397,149 @@ extern "C"
 		return rc;
 	}
 }
+
+// ---- isosurface entry points ------------------------------------------------------------------------------------
+namespace upg
+{
+	// copies a device-side DmcResult into one pinned host block and fills the ABI struct
+	static int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
+	{
+		const uint64_t nv = r.vertexCount, nq = r.quadCount, ni = (uint64_t)r.triangleCount * 3;
+		const uint64_t bytes = sizeof(float) * nv * 9 + sizeof(uint32_t) * (ni + nq * 4);
+		char *block = nullptr;
+		cudaError_t e = cudaMallocHost((void **)&block, bytes ? bytes : 16);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaMallocHost(mesh)");
+		char *p = block;
+		out->positions = (float *)p;
+		p += sizeof(float) * nv * 3;
+		out->normals = (float *)p;
+		p += sizeof(float) * nv * 3;
+		out->dmc_vertices = (float *)p;
+		p += sizeof(float) * nv * 3;
+		out->indices = (uint32_t *)p;
+		p += sizeof(uint32_t) * ni;
+		out->dmc_quads = (uint32_t *)p;
+		if (nv)
+		{
+			e = cudaMemcpyAsync(out->positions, r.positions, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(out->normals, r.normals, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(out->dmc_vertices, r.rawVertices, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
+		}
+		if (e == cudaSuccess && ni)
+			e = cudaMemcpyAsync(out->indices, r.indices, sizeof(uint32_t) * ni, cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess && nq)
+			e = cudaMemcpyAsync(out->dmc_quads, r.quads, sizeof(uint32_t) * nq * 4, cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess)
+		{
+			cudaFreeHost(block);
+			std::memset(out, 0, sizeof(*out));
+			return cuda_fail(e, "mesh download");
+		}
+		out->vertex_count = (uint32_t)nv;
+		out->index_count = (uint32_t)ni;
+		out->quad_count = (uint32_t)nq;
+		out->reserved = 0;
+		out->near_zero_samples = r.nearZeroSamples;
+		out->owner = block;
+		return UPG_OK;
+	}
+}
+
+extern "C"
+{
+	int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		std::memset(out, 0, sizeof(*out));
+		if (!valid_field(field))
+			return fail(UPG_ERR_ARGUMENT, "bad field %d", field);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		const int res = p->params.grid.res;
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		float *dens = nullptr;
+		e = cudaMallocAsync(&dens, sizeof(float) * (uint64_t)res * res * res, cs.compute);
+		if (e != cudaSuccess)
+			rc = cuda_fail(e, "cudaMallocAsync(field)");
+		if (rc == UPG_OK)
+		{
+			FieldLaunch L;
+			L.out = dens;
+			L.positions = nullptr;
+			L.count = (uint64_t)res * res * res;
+			L.z0 = 0;
+			L.field = field;
+			L.status = p->status;
+			rc = launch_field(p, L, cs.compute);
+		}
+		DmcResult r;
+		if (rc == UPG_OK)
+			rc = dmc_extract(dens, res, res, res, p->boxSize, res, cs.compute, r);
+		if (rc == UPG_OK)
+			rc = check_status(p, cs.compute, "upg_field_mesh");
+		if (rc == UPG_OK && r.triangleCount == 0)
+			rc = fail(UPG_ERR_EMPTY_MESH, "generated empty mesh");
+		if (rc == UPG_OK)
+			rc = mesh_to_host(r, cs.compute, out);
+		dmc_release(r, cs.compute);
+		if (dens)
+			cudaFreeAsync(dens, cs.compute);
+		cudaStreamSynchronize(cs.compute);
+		cs.close();
+		return rc;
+	}
+
+	int upg_isosurface(const float *host_samples, int rx, int ry, int rz, float box_size, int full_resolution, int device, upg_mesh *out)
+	{
+		if (!host_samples || !out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		std::memset(out, 0, sizeof(*out));
+		if (rx <= 2 || ry <= 2 || rz <= 2 || full_resolution <= 5)
+			return fail(UPG_ERR_ARGUMENT, "bad volume size %d x %d x %d (resolution %d)", rx, ry, rz, full_resolution);
+		cudaError_t e = cudaSetDevice(device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		const uint64_t n = (uint64_t)rx * ry * rz;
+		float *dens = nullptr;
+		e = cudaMallocAsync(&dens, sizeof(float) * n, cs.compute);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dens, host_samples, sizeof(float) * n, cudaMemcpyHostToDevice, cs.compute);
+		if (e != cudaSuccess)
+			rc = cuda_fail(e, "upload samples");
+		DmcResult r;
+		if (rc == UPG_OK)
+			rc = dmc_extract(dens, rx, ry, rz, box_size, full_resolution, cs.compute, r);
+		if (rc == UPG_OK)
+			rc = mesh_to_host(r, cs.compute, out);
+		dmc_release(r, cs.compute);
+		if (dens)
+			cudaFreeAsync(dens, cs.compute);
+		cudaStreamSynchronize(cs.compute);
+		cs.close();
+		return rc;
+	}
+
+	void upg_mesh_free(upg_mesh *mesh)
+	{
+		if (!mesh)
+			return;
+		if (mesh->owner)
+			cudaFreeHost(mesh->owner);
+		std::memset(mesh, 0, sizeof(*mesh));
+	}
+}

@@ -49,6 +49,20 @@ namespace upg
 		}
 	};
 
+	// device-side result of the isosurface stage (upg_dmc.cu); arrays live in the stream-ordered pool
+	struct DmcResult
+	{
+		float *rawVertices = nullptr; // dualmc vertices in grid units (x, y, z)
+		float *positions = nullptr; // world positions
+		float *normals = nullptr; // area-weighted, normalised
+		uint32_t *indices = nullptr; // 3 per triangle
+		uint32_t *quads = nullptr; // 4 per quad: dualmc's own output, before the triangle split
+		uint32_t vertexCount = 0, quadCount = 0, triangleCount = 0;
+		uint64_t nearZeroSamples = 0; // samples with |value| < 1e-3: where topology parity is not promised
+	};
+	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out);
+	void dmc_release(DmcResult &r, cudaStream_t s);
+
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
 	int check_status(Planet *planet, cudaStream_t stream, const char *what);
 }

@@ -20,6 +20,36 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _mesh_to_numpy(lib, m):
+    nv, ni, nq = m.vertex_count, m.index_count, m.quad_count
+
+    def take(ptr, count, dtype):
+        if count == 0:
+            return np.zeros(0, dtype=dtype)
+        return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+    out = dict(
+        positions=take(m.positions, nv * 3, np.float32).reshape(-1, 3),
+        normals=take(m.normals, nv * 3, np.float32).reshape(-1, 3),
+        indices=take(m.indices, ni, np.uint32),
+        dmc_vertices=take(m.dmc_vertices, nv * 3, np.float32).reshape(-1, 3),
+        dmc_quads=take(m.dmc_quads, nq * 4, np.uint32).reshape(-1, 4),
+        near_zero_samples=int(m.near_zero_samples),
+    )
+    lib.upg_mesh_free(C.byref(m))
+    return out
+
+
+def isosurface(samples, box=4000.0, full_res=None, device=0):
+    """K2..K4 over caller-provided samples [z][y][x] (upg_isosurface): dualmc + makeMesh's triangle tail on the GPU."""
+    L = capi.load_library()
+    s = np.ascontiguousarray(samples, dtype=np.float32)
+    rz, ry, rx = s.shape
+    m = capi.Mesh()
+    capi.check(L.upg_isosurface(_ptr(s), rx, ry, rz, box, full_res or rx, device, C.byref(m)))
+    return _mesh_to_numpy(L, m)
+
+
 class Planet:
     def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0):
         L = capi.load_library()
@@ -73,6 +103,13 @@ class Planet:
     def field_samples_device(self, field, z0, z1, device_ptr, stream=0):
         """asynchronous, into device memory (an integer device pointer), on CUDA stream handle `stream`."""
         capi.check(self._lib.upg_field_samples_device(self._h, capi.FIELDS[field], z0, z1, C.c_void_p(device_ptr), C.c_void_p(stream)))
+
+    # K1 + K2..K4 ---------------------------------------------------------------------------------
+    def field_mesh(self, field="land"):
+        """meshGenerateGeneric up to makeMesh's normals (upg_field_mesh) -> dict of numpy arrays."""
+        m = capi.Mesh()
+        capi.check(self._lib.upg_field_mesh(self._h, capi.FIELDS[field], C.byref(m)))
+        return _mesh_to_numpy(self._lib, m)
 
     def field_points(self, field, positions):
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
