@@ -112,6 +112,22 @@ namespace
 		return nullptr;
 	}
 
+	// position-keyed RNG state for the colorDeviation() draws (see upref_tiles_seeded)
+	uint64_t splitmix64(uint64_t z)
+	{
+		z += 0x9e3779b97f4a7c15ull;
+		z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+		z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+		return z ^ (z >> 31);
+	}
+	void texelRngState(const float *p, uint64_t *s)
+	{
+		uint32_t b[3];
+		std::memcpy(b, p, 12);
+		s[0] = splitmix64((uint64_t)b[0] | ((uint64_t)b[1] << 32)) | 1ull;
+		s[1] = splitmix64(s[0] ^ (uint64_t)b[2]) | 1ull;
+	}
+
 	MarchingCubesCreateConfig gridConfig(float boxSize, int res)
 	{
 		// sources/meshGeneration.cpp:34-37
@@ -356,6 +372,24 @@ extern "C"
 					o[12] = (float)(int)t.type;
 				}
 			});
+	}
+
+	// As upref_tiles, but the calling thread's random generator -- which colorDeviation() in generateSand draws from
+	// (sources/coloringModes.cpp:456, sources/math.cpp:40-45), making the reference's sand texels differ from run to
+	// run -- is re-seeded before every tile from a hash of the tile position.  The product uses the same
+	// position-keyed state (unnatural_planets_b200/csrc/upg_coloring.cuh texel_rng_state); the reference code itself
+	// runs unmodified, only its RNG *input* is pinned.
+	int upref_tiles_seeded(int purpose, const float *pos, const float *nrm, int n, float *out)
+	{
+		int rc = 0;
+		for (int i = 0; i < n && rc == 0; i++)
+		{
+			uint64_t s[2];
+			texelRngState(pos + (size_t)i * 3, s);
+			detail::randomGenerator() = RandomGenerator(s[0], s[1]);
+			rc = upref_tiles(purpose, pos + (size_t)i * 3, nrm + (size_t)i * 3, 1, out + (size_t)i * 13);
+		}
+		return rc;
 	}
 
 	// generateTexturesLand / Water (sources/textures.cpp:86-96): rasterise + colour + 7 dilations + u8

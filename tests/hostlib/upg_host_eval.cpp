@@ -68,6 +68,8 @@ extern "C"
 	struct upgh_planet
 	{
 		PlanetParams params;
+		ColoringConsts coloring;
+		float cellular[1024];
 		SeedLog log;
 	};
 
@@ -86,6 +88,8 @@ extern "C"
 		b.thread.s[1] = s1;
 		b.shapeStatics(p->params);
 		b.elevationStatics(p->params);
+		coloring_statics(b, p->params, p->coloring);
+		default_cellular_table(p->cellular);
 		p->log = b.log;
 		return p;
 	}
@@ -134,5 +138,78 @@ extern "C"
 		UPGH_TYPE(NT_CUBIC)
 		UPGH_TYPE(NT_VALUE)
 		return NAN;
+	}
+
+	// terrainTile on explicit position / normal pairs, same 13 output columns as oracle/ref_harness.cpp upref_tiles
+	void upgh_tiles(const upgh_planet *p, int purpose, const float *pos, const float *nrm, uint64_t n, float *out)
+	{
+		const PlanetParams &P = p->params;
+		for (uint64_t i = 0; i < n; i++)
+		{
+			const V3 position = v3(pos[i * 3 + 0], pos[i * 3 + 1], pos[i * 3 + 2]);
+			const V3 normal = v3(nrm[i * 3 + 0], nrm[i * 3 + 1], nrm[i * 3 + 2]);
+			Tile t = tile_init(position, normal, purpose);
+			t.elevation = eval_field(P, purpose == MP_LAND ? FD_ELEVATION : FD_ELEVATION_RAW, position);
+			float elevs[8];
+			for (int k = 0; k < 8; k++)
+				elevs[k] = eval_field(P, FD_ELEVATION, slope_probe(position, normal, k));
+			t.slope = slope_from_probes(elevs);
+			switch (P.coloring)
+			{
+				case CL_DEFAULT:
+					coloring_run<CL_DEFAULT>(p->coloring, p->cellular, t);
+					break;
+				case CL_BARREN:
+					coloring_run<CL_BARREN>(p->coloring, p->cellular, t);
+					break;
+				default:
+					coloring_run<CL_DEBUG>(p->coloring, p->cellular, t);
+					break;
+			}
+			float *o = out + i * 13;
+			o[0] = t.albedo.x;
+			o[1] = t.albedo.y;
+			o[2] = t.albedo.z;
+			o[3] = t.roughness;
+			o[4] = t.metallic;
+			o[5] = t.height;
+			o[6] = t.elevation;
+			o[7] = t.slope;
+			o[8] = t.temperature;
+			o[9] = t.precipitation;
+			o[10] = t.opacity;
+			o[11] = (float)t.biome;
+			o[12] = (float)t.type;
+		}
+	}
+	void upgh_color(int what, const float *in3, float *out3)
+	{
+		const V3 v = v3(in3[0], in3[1], in3[2]);
+		V3 r = v;
+		switch (what)
+		{
+			case 0:
+				r = rgb_to_hsv(v);
+				break;
+			case 1:
+				r = hsv_to_rgb(v);
+				break;
+			case 2:
+				r = rgb_to_hsluv(v);
+				break;
+			case 3:
+				r = hsluv_to_rgb(v);
+				break;
+		}
+		out3[0] = r.x;
+		out3[1] = r.y;
+		out3[2] = r.z;
+	}
+	void upgh_color_interpolate(const float *a3, const float *b3, float f, float *out3)
+	{
+		const V3 r = interpolate_color(v3(a3[0], a3[1], a3[2]), v3(b3[0], b3[1], b3[2]), f);
+		out3[0] = r.x;
+		out3[1] = r.y;
+		out3[2] = r.z;
 	}
 }

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "upg_coloring.cuh"
 #include "upg_terrain.cuh"
 
 namespace upg
@@ -197,6 +198,167 @@ namespace upg
 			}
 		}
 	};
+
+	// cellular-noise variants keep their distance / return kind in the template arguments of the call site; the
+	// instance only carries seed / frequency / fractal parameters
+	inline NoiseInst make_cellular(uint32_t seed, float frequency, int octaves = 3) { return make_noise(seed, frequency, octaves); }
+
+	// The colouring statics, in the order terrainPreseed() first passes their declarations (sources/modesConfiguration.cpp:
+	// 288-306 -> sources/coloringModes.cpp:905-966): a LAND tile through the chosen colouring function, then a WATER tile.
+	// Every generate* function declares its statics before any early return, so the order only depends on the colouring mode.
+	inline void coloring_statics(PlanetBuilder &b, const PlanetParams &P, ColoringConsts &C)
+	{
+		std::memset(&C, 0, sizeof(C));
+		C.poles = P.poles;
+		C.flowers = P.flowers;
+		const NoiseInst none = make_noise(0);
+		NoiseInst *all = &C.beach;
+		for (NoiseInst *n = all; n <= &C.waterHueShift; n++)
+			*n = none;
+		C.boulderCenters = C.flowerCluster = C.flowerCenter = make_voronoi(0, 1, 10);
+
+		auto precipitation = [&]() { C.precp = make_noise(b.noiseSeed(), 0.001f, 2); };
+		auto temperature = [&]()
+		{
+			C.temp = make_noise(b.noiseSeed(), 0.0003f, 2, 0.4f);
+			C.polar = make_noise(b.noiseSeed(), 0.007f, 3);
+		};
+		auto bedrock = [&]()
+		{
+			const uint32_t seed = b.noiseSeed();
+			C.bedrockDepth = make_noise(b.noiseSeed(), 0.0031f);
+			C.bedrockFreq = make_noise(b.noiseSeed(), 0.013f);
+			C.bedrockCracks = make_cellular(seed, 0.017f);
+			C.bedrockValue = make_cellular(seed, 0.017f);
+			C.bedrockSaturation = make_noise(b.noiseSeed(), 0.0022f, 2);
+		};
+		auto cliffs = [&]() { C.cliffsCracks = make_noise(b.noiseSeed(), 0.047f, 2); };
+		auto mica = [&]()
+		{
+			C.micaMask = make_cellular(b.noiseSeed(), 0.02f);
+			C.micaCracks = make_cellular(b.noiseSeed(), 0.05f);
+		};
+		auto dirt = [&]()
+		{
+			C.dirtHeight = make_noise(b.noiseSeed(), 0.05f, 3, 0.4f, 2.3f);
+			C.dirtCracks = make_noise(b.noiseSeed(), 0.07f, 2);
+			C.dirtCracksMask = make_noise(b.noiseSeed(), 0.02f, 4);
+		};
+		auto sand = [&]()
+		{
+			C.sandHeightScale = make_noise(b.noiseSeed(), 0.001f, 3);
+			C.sandHeight = make_noise(b.noiseSeed(), 0.01f, 3, 0.7f);
+			C.sandColor = make_noise(b.noiseSeed(), 0.0008f);
+			C.sandHue = make_noise(b.noiseSeed(), 0.02f, 2);
+		};
+		auto grass = [&]()
+		{
+			const uint32_t seed = b.noiseSeed();
+			C.grassHue = make_noise(b.noiseSeed(), 0.01f, 2);
+			C.grassPatchesCells = make_cellular(seed, 0.1f);
+			C.grassPatchesDist = make_cellular(seed, 0.1f);
+			C.grassScratches = make_cellular(b.noiseSeed(), 0.3f);
+			C.beach = make_noise(b.noiseSeed(), 0.035f); // beachMask's static, first reached from the grass mask (:511)
+		};
+		auto boulders = [&]()
+		{
+			C.boulderThreshold = make_noise(b.noiseSeed(), 0.01f);
+			C.boulderCenters = make_voronoi(b.noiseSeed(), 2, 200);
+			C.boulderSize = make_noise(b.noiseSeed(), 0.09f);
+			C.boulderHue = make_noise(b.noiseSeed(), 0.3f);
+			C.boulderValue = make_noise(b.noiseSeed(), 0.5f);
+			C.boulderScratches = make_noise(b.noiseSeed(), 0.5f);
+		};
+		auto flowers = [&]()
+		{
+			C.flowerCluster = make_voronoi(b.noiseSeed(), 1, 200);
+			C.flowerCenter = make_voronoi(b.noiseSeed(), 1, 35);
+			C.flowerSize = make_noise(b.noiseSeed(), 0.35f);
+			C.flowerColor = make_noise(b.noiseSeed(), 0.02f);
+			C.flowerHue1 = make_noise(b.noiseSeed(), 0.005f);
+			C.flowerHue2 = make_noise(b.noiseSeed(), 0.4f);
+		};
+		auto ice = [&]()
+		{
+			const uint32_t seed = b.noiseSeed();
+			C.iceTempOffset = make_noise(b.noiseSeed(), 0.035f);
+			C.iceFreq = make_noise(b.noiseSeed(), 0.01f, 3);
+			C.iceThickness = make_cellular(seed, 0.05f, 2);
+			C.iceCracks = make_cellular(seed, 0.05f, 2);
+		};
+		auto snow = [&]()
+		{
+			C.snowElevOffset = make_noise(b.noiseSeed(), 0.055f);
+			C.snowThickness = make_noise(b.noiseSeed(), 0.05f, 3);
+		};
+		auto water = [&]()
+		{
+			C.waterColorSwitch = make_noise(b.noiseSeed(), 0.0015f, 2);
+			C.waterHueShift = make_noise(b.noiseSeed(), 0.004f, 3);
+		};
+
+		switch (P.coloring)
+		{
+			case CL_DEFAULT:
+				precipitation();
+				temperature();
+				bedrock();
+				cliffs();
+				mica();
+				dirt();
+				sand();
+				grass();
+				boulders();
+				flowers();
+				ice();
+				snow();
+				water();
+				break;
+			case CL_BARREN:
+				bedrock();
+				cliffs();
+				mica();
+				boulders();
+				water();
+				break;
+			case CL_DEBUG:
+				precipitation();
+				temperature();
+				break;
+		}
+
+		C.hsluvSandTarget = rgb_to_hsluv(v3(187, 104, 50) / 255);
+		C.hsluvWaterDeep = rgb_to_hsluv(v3(40, 63, 168) / 255);
+		C.hsluvWaterShallow = rgb_to_hsluv(v3(39, 154, 186) / 255);
+		C.hsluvFlowerA = rgb_to_hsluv(v3(0.5f, 0, 0.35f));
+		C.hsluvFlowerB = rgb_to_hsluv(v3(0.5f, 0.4f, 0));
+	}
+
+	// the declared substitute for FastNoiseLite's RandVecs3D constant table (same construction as
+	// oracle/up_noise.h upo_randvecs3d): 256 unit vectors from a splitmix64 stream, w = 0
+	inline void default_cellular_table(float *table /* 1024 */)
+	{
+		for (int e = 0; e < 256; e++)
+		{
+			uint64_t s = 0x5eedc0de00000000ull + (uint64_t)e;
+			auto next = [&]()
+			{
+				uint64_t z = (s += 0x9e3779b97f4a7c15ull);
+				z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+				z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+				return z ^ (z >> 31);
+			};
+			const double u = (double)(next() >> 11) * (1.0 / 9007199254740992.0);
+			const double v = (double)(next() >> 11) * (1.0 / 9007199254740992.0);
+			const double zz = 2.0 * u - 1.0;
+			const double rr = std::sqrt(1.0 - zz * zz);
+			const double ph = 6.283185307179586476925286766559 * v;
+			table[e * 4 + 0] = (float)(rr * std::cos(ph));
+			table[e * 4 + 1] = (float)(rr * std::sin(ph));
+			table[e * 4 + 2] = (float)zz;
+			table[e * 4 + 3] = 0.0f;
+		}
+	}
 
 	inline void set_grid(PlanetParams &P, float boxSize, int res)
 	{
