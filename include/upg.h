@@ -150,6 +150,70 @@ int upg_isosurface(const float *host_samples, int rx, int ry, int rz, float box_
 
 void upg_mesh_free(upg_mesh *mesh);
 
+/*
+ * ---- texel baking (K5..K7) ------------------------------------------------------------------------------------
+ */
+
+/* MeshPurposeEnum (sources/planets.h:49-55): which terrainSdf* feeds tile.elevation and which layers run */
+enum
+{
+	UPG_PURPOSE_LAND = 1,
+	UPG_PURPOSE_WATER = 2,
+	UPG_PURPOSE_NAVIGATION = 3
+};
+
+/* what terrainTile() leaves in a Tile (sources/planets.h:63-83), the fields the generator reads afterwards */
+typedef struct upg_tile
+{
+	float albedo[3];
+	float roughness;
+	float metallic;
+	float height;
+	float elevation;
+	float slope; /* radians */
+	float temperature;
+	float precipitation;
+	float opacity;
+	float biome; /* TerrainBiomeEnum as a number */
+	float type; /* TerrainTypeEnum as a number */
+} upg_tile;
+
+/*
+ * The Cellular generator of FastNoiseLite indexes a 256 x 4 float constant table (RandVecs3D).  The library source is an
+ * un-vendored submodule of the reference (externals/cage/externals/fastnoise), so the table is DATA here: a planet starts
+ * with the declared substitute (unit vectors from a fixed splitmix64 stream, identical to oracle/up_noise.h) and an
+ * integration that has the real header passes upstream's table once per planet.  1024 floats, entry e at [4e .. 4e+2].
+ */
+int upg_planet_set_cellular_table(upg_planet *planet, const float *table1024);
+
+/* terrainTile() (sources/modesConfiguration.cpp:281-286) for n explicit position / unit-normal pairs: the per-vertex loop of
+ * generateTileProperties (sources/tileProperties.cpp:258-265, purpose NAVIGATION) and the parity probe of the colouring. */
+int upg_tiles(upg_planet *planet, int purpose, const float *host_positions, const float *host_normals, uint64_t n, upg_tile *host_out);
+
+/*
+ * K5 + K6 + K7.  Replaces Generator<Water>::generate (sources/textures.cpp:45-82) behind generateTexturesLand / Water
+ * (:86-96): meshGenerateTexture's scan-line coverage with "the last triangle wins" (externals/cage/sources/libcore/mesh/
+ * meshAlgorithms.cpp:1676-1729), one terrainTile per covered texel (Generator::pixel, textures.cpp:24-43), seven NaN-aware
+ * dilation rounds per image (imageDilation(img, 7, true), libcore/image/imageAlgorithms.cpp:349-527) and the truncating
+ * 8-bit quantisation of imageConvert(U8) (image.cpp:244-262).
+ * Mesh arrays are what Mesh::positions() / normals() / uvs() / indices() expose (include/cage-core/mesh.h:34-43,86-88).
+ * Outputs are tightly packed rows, top row first as cage stores them: albedo w*h*3 (land) or w*h*4 (water: rgb + opacity),
+ * special w*h*2 (roughness, metallic), height w*h*1.  Uncovered texels that no dilation round reaches are 0.
+ */
+int upg_bake(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint8_t *albedo, uint8_t *special, uint8_t *height_map);
+
+/* coverage statistics of the last upg_bake on this thread: texels written by the rasteriser (= terrainTile evaluations;
+ * the reference evaluates every (triangle, texel) visit, this library only the winning one) */
+uint64_t upg_bake_last_covered_texels(void);
+
+/* K5 alone, for parity: owner[y*w+x] = index of the LAST triangle whose scan covers the texel (0xffffffff = none) and the
+ * barycentric weights of that visit (meshAlgorithms.cpp:1719-1724); `callbacks` = number of (triangle, texel) visits */
+int upg_raster(int device, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t *owner, float *weights /* w*h*3 */, uint64_t *callbacks);
+
+/* K7 alone: imageDilation(img, rounds, use_nan) on a float image (in place) and, when u8_out != NULL, imageConvert(U8)
+ * of the result (imageAlgorithms.cpp:504-527, 100-113).  channels 1..4. */
+int upg_dilate(int device, float *image, uint32_t width, uint32_t height, uint32_t channels, uint32_t rounds, int use_nan, uint8_t *u8_out);
+
 /* measurement helper for bench.py: the FP32 FMA ceiling (TFLOP/s, FMA = 2 flop) of `device`, measured live with a
  * dependent-free FFMA kernel -- the roofline denominator of the compute-bound kernels (K1 sampling, K6 texel baking);
  * MEASURED_PEAKS.json only carries HBM and tensor-core peaks */

@@ -174,6 +174,30 @@ class RefPlanet:
         self._check(self.lib.upref_tiles(C.c_int(code), _fp(pos), _fp(nrm), C.c_int(len(pos)), _fp(out)))
         return out
 
+    def tiles_seeded(self, purpose, pos, nrm):
+        """as tiles(), with the thread RNG re-seeded from each tile position (pins generateSand's colorDeviation)"""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((len(pos), 13), dtype=np.float32)
+        code = {"land": 1, "water": 2, "navigation": 3}[purpose]
+        self._check(self.lib.upref_tiles_seeded(C.c_int(code), _fp(pos), _fp(nrm), C.c_int(len(pos)), _fp(out)))
+        return out
+
+    def bake_seeded(self, water, pos, nrm, uv, idx, w, h):
+        """generateTextures* re-assembled from the reference's building blocks with the position-keyed RNG (ref_harness.cpp)"""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
+        ch = 4 if water else 3
+        albedo = np.zeros((h, w, ch), dtype=np.uint8)
+        special = np.zeros((h, w, 2), dtype=np.uint8)
+        height = np.zeros((h, w, 1), dtype=np.uint8)
+        covered = C.c_uint64(0)
+        self._check(self.lib.upref_bake_seeded(C.c_int(int(water)), _fp(pos), _fp(nrm), _fp(uv), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), C.c_uint32(w), C.c_uint32(h), _fp(albedo), _fp(special), _fp(height), C.byref(covered)))
+        self.last_covered_texels = int(covered.value)
+        return albedo, special, height
+
     def bake(self, water, pos, nrm, uv, idx, w, h):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
         nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)

@@ -414,6 +414,82 @@ extern "C"
 			});
 	}
 
+	// Generator<Water>::generate (sources/textures.cpp:45-82) re-assembled from the reference's own building blocks
+	// (imageFill, meshGenerateTexture, terrainTile, imageDilation, imageConvert) with ONE difference: the thread RNG is
+	// re-seeded from the tile position before every terrainTile call (see upref_tiles_seeded), which makes generateSand's
+	// colorDeviation reproducible.  tests/ check that without sand (barren / debug colouring) this equals upref_bake bit for bit.
+	int upref_bake_seeded(int water, const float *pos, const float *nrm, const float *uv, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *special, uint8_t *height, uint64_t *covered)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> msh = newMesh();
+				msh->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nverts));
+				msh->normals(PointerRange<const Vec3>((const Vec3 *)nrm, (const Vec3 *)nrm + nverts));
+				msh->uvs(PointerRange<const Vec2>((const Vec2 *)uv, (const Vec2 *)uv + nverts));
+				msh->indices(PointerRange<const uint32>(idx, idx + nidx));
+				struct Gen
+				{
+					Mesh *mesh;
+					Holder<Image> a, s, hm;
+					bool water;
+					void pixel(const Vec2i &xy, const Vec3i &indices, const Vec3 &weights)
+					{
+						Tile tile;
+						tile.position = mesh->positionAt(indices, weights);
+						tile.normal = mesh->normalAt(indices, weights);
+						uint64_t st[2];
+						texelRngState((const float *)&tile.position, st);
+						detail::randomGenerator() = RandomGenerator(st[0], st[1]);
+						tile.meshPurpose = water ? MeshPurposeEnum::Water : MeshPurposeEnum::Land;
+						terrainTile(tile);
+						if (water)
+							a->set(xy, Vec4(tile.albedo, tile.opacity));
+						else
+							a->set(xy, tile.albedo);
+						s->set(xy, Vec2(tile.roughness, tile.metallic));
+						hm->set(xy, tile.height);
+					}
+				} gen;
+				gen.mesh = +msh;
+				gen.water = !!water;
+				gen.a = newImage();
+				gen.a->initialize(w, h, water ? 4 : 3, ImageFormatEnum::Float);
+				if (water)
+					imageFill(+gen.a, Vec4::Nan());
+				else
+					imageFill(+gen.a, Vec3::Nan());
+				gen.s = newImage();
+				gen.s->initialize(w, h, 2, ImageFormatEnum::Float);
+				imageFill(+gen.s, Vec2::Nan());
+				gen.hm = newImage();
+				gen.hm->initialize(w, h, 1, ImageFormatEnum::Float);
+				imageFill(+gen.hm, Real::Nan());
+				MeshGenerateTextureConfig cfg;
+				cfg.width = w;
+				cfg.height = h;
+				cfg.generator.bind<Gen, &Gen::pixel>(&gen);
+				meshGenerateTexture(+msh, cfg);
+				if (covered)
+				{
+					uint64_t c = 0;
+					const float *hv = (const float *)gen.hm->rawViewFloat().data();
+					for (size_t i = 0; i < (size_t)w * h; i++)
+						c += hv[i] == hv[i];
+					*covered = c;
+				}
+				imageDilation(+gen.a, 7, true);
+				imageDilation(+gen.s, 7, true);
+				imageDilation(+gen.hm, 7, true);
+				imageConvert(+gen.a, ImageFormatEnum::U8);
+				imageConvert(+gen.s, ImageFormatEnum::U8);
+				imageConvert(+gen.hm, ImageFormatEnum::U8);
+				std::memcpy(albedo, gen.a->rawViewU8().data(), gen.a->rawViewU8().size());
+				std::memcpy(special, gen.s->rawViewU8().data(), gen.s->rawViewU8().size());
+				std::memcpy(height, gen.hm->rawViewU8().data(), gen.hm->rawViewU8().size());
+			});
+	}
+
 	// meshGenerateTexture coverage only (externals/cage/sources/libcore/mesh/meshAlgorithms.cpp:1676-1729):
 	// owner[y*w+x] = index of the LAST triangle whose scan covers the texel (0xffffffff if none), weights of that visit
 	int upref_raster(const float *pos, const float *uv, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t *owner, float *weights /* w*h*3 */, uint64_t *callbacks)

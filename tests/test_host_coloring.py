@@ -1,0 +1,74 @@
+"""CPU tests of the colouring stage: the product's device headers compiled for the host (tests/hostlib -- test-only) against
+golden vectors the reference itself produced (tests/golden/make_golden_bake.py).  Host arithmetic is the reference's own
+(same libm, no FMA), so everything here is asserted BIT-EXACT, including the seed -> noise-instance assignment order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import bake_common as bc
+from conftest import golden, same_bits
+from unnatural_planets_b200.planet import COLORINGS, ELEVATIONS, SHAPES
+
+
+@pytest.fixture(scope="module")
+def H(hostlib):
+    hostlib.upgh_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    hostlib.upgh_color.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    hostlib.upgh_color_interpolate.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    return hostlib
+
+
+def host_tiles(H, cfg, purpose, pos, nrm):
+    s, e, c, p, f = cfg
+    h = H.upgh_create(SHAPES.index(s), ELEVATIONS.index(e), COLORINGS.index(c), int(p), int(f), 1346519564496, 42245614964156, 4000.0, 500)
+    out = np.zeros((len(pos), 13), dtype=np.float32)
+    H.upgh_tiles(C.c_void_p(h), {"land": 1, "water": 2, "navigation": 3}[purpose], pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), len(pos), out.ctypes.data_as(C.c_void_p))
+    H.upgh_destroy(C.c_void_p(h))
+    return out
+
+
+@pytest.mark.parametrize("cfg", bc.TILE_CONFIGS, ids=bc.config_name)
+@pytest.mark.parametrize("purpose", bc.PURPOSES)
+def test_tiles_bit_exact(H, cfg, purpose):
+    g = golden("tiles_%s.npz" % bc.config_name(cfg))
+    pos, nrm = bc.tile_probes(cfg[0])
+    assert (pos == g["positions"]).all() and (nrm == g["normals"]).all()  # the probe generator is deterministic
+    got = host_tiles(H, cfg, purpose, pos, nrm)
+    ok = same_bits(got, g[purpose])
+    assert ok.all(), (int((~ok).sum()), np.argwhere(~ok)[:5])
+
+
+def test_fixture_reaches_every_layer():
+    # the fixtures are only worth something if they exercise the layers: every biome but one, all terrain types, sand,
+    # snow, ice, flowers / boulders / mica (flowers enabled) show up in the reference's own outputs
+    g = golden("tiles_sphere_lakes_default_p1_f1.npz")["land"]
+    assert len(np.unique(g[:, 11])) >= 9
+    assert set(np.unique(g[:, 12]).astype(int)) >= {1, 2, 3, 4}
+    assert (g[:, 4] > 0.5).sum() > 0  # metallic: mica
+    w = golden("tiles_sphere_lakes_default_p1_f1.npz")["water"]
+    assert (w[:, 10] < 1).sum() > 100  # opacity only changes on the water path
+
+
+def test_color_conversions(H):
+    g = golden("colors.npz")
+    cols = g["input"]
+    for code, what in enumerate(("rgb2hsv", "hsv2rgb", "rgb2hsluv", "hsluv2rgb")):
+        out = np.zeros(3, dtype=np.float32)
+        for i, c in enumerate(cols):
+            H.upgh_color(code, c.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            assert same_bits(out, g[what][i]).all(), (what, i, out, g[what][i])
+    out = np.zeros(3, dtype=np.float32)
+    for i in range(len(cols) - 1):
+        a, b = np.ascontiguousarray(cols[i]), np.ascontiguousarray(cols[i + 1])
+        H.upgh_color_interpolate(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), float(g["interp_f"][i]), out.ctypes.data_as(C.c_void_p))
+        assert same_bits(out, g["interp"][i]).all(), (i, out, g["interp"][i])
+
+
+def test_hsv_known_answers_of_the_reference_tests(H):
+    # externals/cage/sources/test-core/color.cpp:53-62
+    out = np.zeros(3, dtype=np.float32)
+    for hsv, rgb in (((0, 0.5, 1), (1, 0.5, 0.5)), ((0, 1, 1), (1, 0, 0)), ((0, 0, 0.5), (0.5, 0.5, 0.5))):
+        v = np.array(hsv, dtype=np.float32)
+        H.upgh_color(1, v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert np.allclose(out, rgb, atol=1e-6)

@@ -46,6 +46,26 @@ class Mesh(C.Structure):
     ]
 
 
+class Tile(C.Structure):
+    _fields_ = [
+        ("albedo", C.c_float * 3),
+        ("roughness", C.c_float),
+        ("metallic", C.c_float),
+        ("height", C.c_float),
+        ("elevation", C.c_float),
+        ("slope", C.c_float),
+        ("temperature", C.c_float),
+        ("precipitation", C.c_float),
+        ("opacity", C.c_float),
+        ("biome", C.c_float),
+        ("type", C.c_float),
+    ]
+
+
+PURPOSES = {"land": 1, "water": 2, "navigation": 3}
+TILE_COLUMNS = ("albedo_r", "albedo_g", "albedo_b", "roughness", "metallic", "height", "elevation", "slope", "temperature", "precipitation", "opacity", "biome", "type")
+
+
 def library_path() -> str:
     return os.path.join(HERE, "libupg.so")
 
@@ -83,6 +103,13 @@ def load_library():
     L.upg_mesh_free.argtypes = [C.POINTER(Mesh)]
     L.upg_mesh_free.restype = None
     L.upg_measure_fp32_peak.argtypes = [i32, C.POINTER(C.c_float)]
+    u32 = C.c_uint32
+    L.upg_planet_set_cellular_table.argtypes = [vp, fp]
+    L.upg_tiles.argtypes = [vp, i32, fp, fp, u64, fp]
+    L.upg_bake.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, fp, fp, fp]
+    L.upg_bake_last_covered_texels.restype = u64
+    L.upg_raster.argtypes = [i32, fp, u32, fp, u32, u32, u32, fp, fp, C.POINTER(u64)]
+    L.upg_dilate.argtypes = [i32, fp, u32, u32, u32, u32, i32, fp]
     _lib = L
     return L
 

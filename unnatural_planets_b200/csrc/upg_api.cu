@@ -201,6 +201,7 @@ extern "C"
 		b.thread.s[1] = d->seed[1];
 		b.shapeStatics(p->params);
 		b.elevationStatics(p->params);
+		coloring_statics(b, p->params, p->coloring);
 		p->seedLog = b.log;
 
 		// the device side: fails loudly when there is no GPU (no CPU fallback exists)
@@ -220,8 +221,20 @@ extern "C"
 			e = cudaMalloc(&p->status, sizeof(uint32_t) * 4);
 		if (e == cudaSuccess)
 			e = cudaMemset(p->status, 0, sizeof(uint32_t) * 4);
+		if (e == cudaSuccess)
+			e = cudaMalloc(&p->cellularTable, sizeof(float) * 1024);
+		if (e == cudaSuccess)
+		{
+			float table[1024];
+			default_cellular_table(table);
+			e = cudaMemcpy(p->cellularTable, table, sizeof(table), cudaMemcpyHostToDevice);
+		}
 		if (e != cudaSuccess)
 		{
+			if (p->status)
+				cudaFree(p->status);
+			if (p->cellularTable)
+				cudaFree(p->cellularTable);
 			delete p;
 			return cuda_fail(e, "upg_planet_create");
 		}
@@ -237,7 +250,22 @@ extern "C"
 		cudaSetDevice(p->device);
 		if (p->status)
 			cudaFree(p->status);
+		if (p->cellularTable)
+			cudaFree(p->cellularTable);
 		delete p;
+	}
+
+	int upg_planet_set_cellular_table(upg_planet *planet, const float *table1024)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !table1024)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e == cudaSuccess)
+			e = cudaMemcpy(p->cellularTable, table1024, sizeof(float) * 1024, cudaMemcpyHostToDevice);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "upg_planet_set_cellular_table");
+		return UPG_OK;
 	}
 
 	int upg_planet_seed_log(const upg_planet *planet, uint32_t *out, int capacity)

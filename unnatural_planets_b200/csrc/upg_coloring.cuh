@@ -23,9 +23,13 @@
 #include "upg_terrain.cuh"
 
 #if defined(__CUDACC__)
-#define UPG_LAYER __device__ __noinline__
+// the layers are real (non-inlined) device functions: the colouring kernel stays a few thousand instructions per layer
+// instead of one giant inlined body; they only exist in the translation unit that launches the kernel
+#define UPG_LAYER static __device__ __noinline__
+#define UPG_COLORING __device__ __forceinline__
 #else
 #define UPG_LAYER inline
+#define UPG_COLORING inline
 #endif
 
 namespace upg
@@ -645,7 +649,7 @@ namespace upg
 
 	// coloringDefault / coloringBarren / coloringDebug (:905-966).  t.elevation and t.slope are already set.
 	template<int COLORING>
-	UPG_HD void coloring_run(const ColoringConsts &C, const float *rv, Tile &t)
+	UPG_COLORING void coloring_run(const ColoringConsts &C, const float *rv, Tile &t)
 	{
 		if (COLORING == CL_DEFAULT)
 		{

@@ -15,7 +15,9 @@ namespace upg
 	struct Planet
 	{
 		PlanetParams params;
+		ColoringConsts coloring;
 		SeedLog seedLog;
+		float *cellularTable = nullptr; // device: 1024 floats (FastNoiseLite RandVecs3D or its declared substitute)
 		float boxSize = 4000;
 		int device = 0;
 		uint32_t *status = nullptr; // device: bit 0 = NaN sample seen

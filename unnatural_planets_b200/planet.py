@@ -50,6 +50,28 @@ def isosurface(samples, box=4000.0, full_res=None, device=0):
     return _mesh_to_numpy(L, m)
 
 
+def raster(uv, idx, w, h, device=0):
+    """K5 alone (upg_raster): owner image (0xffffffff = uncovered), barycentric weights of the winning visit, visit count."""
+    L = capi.load_library()
+    uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32).reshape(-1)
+    owner = np.zeros((h, w), dtype=np.uint32)
+    weights = np.zeros((h, w, 3), dtype=np.float32)
+    calls = C.c_uint64(0)
+    capi.check(L.upg_raster(device, _ptr(uv), len(uv), _ptr(idx), len(idx), w, h, _ptr(owner), _ptr(weights), C.byref(calls)))
+    return owner, weights, int(calls.value)
+
+
+def dilate(img, rounds, use_nan=True, to_u8=False, device=0):
+    """K7 alone (upg_dilate): imageDilation(img, rounds, use_nan) [+ imageConvert(U8)] on an (h, w, ch) float image."""
+    L = capi.load_library()
+    img = np.array(img, dtype=np.float32, order="C", copy=True)
+    h, w, ch = img.shape
+    u8 = np.zeros((h, w, ch), dtype=np.uint8) if to_u8 else None
+    capi.check(L.upg_dilate(device, _ptr(img), w, h, ch, rounds, int(use_nan), _ptr(u8) if to_u8 else None))
+    return (img, u8) if to_u8 else img
+
+
 class Planet:
     def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0):
         L = capi.load_library()
@@ -116,3 +138,30 @@ class Planet:
         out = np.empty(len(pos), dtype=np.float32)
         capi.check(self._lib.upg_field_points(self._h, capi.FIELDS[field], _ptr(pos), len(pos), _ptr(out)))
         return out
+
+    # K5..K7 --------------------------------------------------------------------------------------
+    def set_cellular_table(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float32).reshape(-1)
+        assert t.size == 1024
+        capi.check(self._lib.upg_planet_set_cellular_table(self._h, _ptr(t)))
+
+    def tiles(self, purpose, positions, normals):
+        """terrainTile on explicit (position, unit normal) pairs -> (n, 13) float32, columns capi.TILE_COLUMNS."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((len(pos), 13), dtype=np.float32)
+        capi.check(self._lib.upg_tiles(self._h, capi.PURPOSES[purpose], _ptr(pos), _ptr(nrm), len(pos), _ptr(out)))
+        return out
+
+    def bake(self, water, positions, normals, uvs, indices, w, h):
+        """generateTexturesLand / Water (upg_bake) -> (albedo u8 (h,w,3|4), special u8 (h,w,2), height u8 (h,w,1))."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        albedo = np.zeros((h, w, 4 if water else 3), dtype=np.uint8)
+        special = np.zeros((h, w, 2), dtype=np.uint8)
+        height = np.zeros((h, w, 1), dtype=np.uint8)
+        capi.check(self._lib.upg_bake(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, _ptr(albedo), _ptr(special), _ptr(height)))
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
+        return albedo, special, height
