@@ -202,6 +202,15 @@ int upg_tiles(upg_planet *planet, int purpose, const float *host_positions, cons
  */
 int upg_bake(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint8_t *albedo, uint8_t *special, uint8_t *height_map);
 
+/* Rows [row0, row1) of the same textures: the unit of multi-GPU sharding ("texture baking shards by texel-row tiles").  Texels
+ * are independent; the seven dilation rounds reach 7 rows, so the call bakes a band with a 7-row apron internally and returns
+ * exactly the rows a whole-image upg_bake would.  Outputs hold (row1 - row0) rows. */
+int upg_bake_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *height_map);
+
+/* same with the mesh and the outputs in DEVICE memory, on `cuda_stream` (synchronises that stream before returning): for callers
+ * that keep the mesh on the GPU (bench.py's device-resident metric) */
+int upg_bake_device(upg_planet *planet, int water, const float *device_positions, const float *device_normals, const float *device_uvs, uint32_t vertex_count, const uint32_t *device_indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint8_t *device_albedo, uint8_t *device_special, uint8_t *device_height_map, void *cuda_stream);
+
 /* coverage statistics of the last upg_bake on this thread: texels written by the rasteriser (= terrainTile evaluations;
  * the reference evaluates every (triangle, texel) visit, this library only the winning one) */
 uint64_t upg_bake_last_covered_texels(void);

@@ -219,6 +219,25 @@ def test_bake_live_reference_1024():
         check_bake(got, want, ("live", water))
 
 
+@pytest.mark.parametrize("water", [0, 1])
+def test_bake_rows_equal_whole_image(water):
+    # texel-row sharding (BASELINE north_star: "texture baking shards by texel-row tiles"): ragged bands, including bands
+    # thinner than the 7-row dilation apron, reassemble to the whole-image result bit for bit
+    cfg = ("sphere", "lakes", "default", True, True)
+    pos, nrm, uv, idx = bc.atlas_mesh()
+    p = make_planet(cfg)
+    whole = p.bake(water, pos, nrm, uv, idx, 192, 192)
+    total = p.last_covered_texels
+    cuts = [0, 5, 64, 67, 131, 192]
+    parts, covered = [], 0
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        parts.append(p.bake_rows(water, pos, nrm, uv, idx, 192, 192, r0, r1))
+        covered += p.last_covered_texels
+    assert covered == total
+    for k in range(3):
+        assert (np.concatenate([q[k] for q in parts], axis=0) == whole[k]).all()
+
+
 def test_bake_empty_mesh_and_errors():
     p = make_planet(("sphere", "lakes", "default", False, False))
     a, s, h = p.bake(0, np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), np.zeros((3, 2), np.float32), np.zeros(0, np.uint32), 32, 32)

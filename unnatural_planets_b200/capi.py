@@ -108,6 +108,8 @@ def load_library():
     L.upg_tiles.argtypes = [vp, i32, fp, fp, u64, fp]
     L.upg_bake.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, fp, fp, fp]
     L.upg_bake_last_covered_texels.restype = u64
+    L.upg_bake_rows.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp]
+    L.upg_bake_device.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp, vp]
     L.upg_raster.argtypes = [i32, fp, u32, fp, u32, u32, u32, fp, fp, C.POINTER(u64)]
     L.upg_dilate.argtypes = [i32, fp, u32, u32, u32, u32, i32, fp]
     _lib = L

@@ -40,6 +40,7 @@ namespace upg
 			const uint32_t *indices; // 3 per triangle
 			uint32_t triangles;
 			uint32_t width, height;
+			uint32_t bandBegin, bandEnd; // rows [bandBegin, bandEnd) are kept (row-tile sharding); the owner image is band sized
 		};
 
 		// Vec2i * Real (meshAlgorithms.cpp:52-55): per component sint32(int * float)
@@ -81,7 +82,12 @@ namespace upg
 			const int2 d20 = make_int2(t2.x - t0.x, t2.y - t0.y);
 			const int2 d21 = make_int2(t2.x - t1.x, t2.y - t1.y);
 			const int2 d10 = make_int2(t1.x - t0.x, t1.y - t0.y);
-			for (int i = 0; i <= totalHeight; i++)
+			// scan lines are independent of each other: rows outside the band are skipped, not walked
+			if (t2.y < (int)M.bandBegin || t0.y >= (int)M.bandEnd)
+				return;
+			const int iBegin = t0.y < (int)M.bandBegin ? (int)M.bandBegin - t0.y : 0;
+			const int iEnd = t2.y >= (int)M.bandEnd ? (int)M.bandEnd - 1 - t0.y : totalHeight;
+			for (int i = iBegin; i <= iEnd; i++)
 			{
 				const bool secondHalf = i > t1.y - t0.y || t1.y == t0.y;
 				const uint32_t segmentHeight = secondHalf ? (uint32_t)(t2.y - t1.y) : (uint32_t)(t1.y - t0.y);
@@ -124,8 +130,8 @@ namespace upg
 					{
 						mine++;
 						// the reference asserts the texel is inside the image and otherwise writes out of bounds; skip instead
-						if (x >= 0 && y >= 0 && (uint32_t)x < M.width && (uint32_t)y < M.height)
-							atomicMax(&owner[(size_t)y * M.width + x], tri + 1);
+						if (x >= 0 && (uint32_t)x < M.width && y >= (int)M.bandBegin && y < (int)M.bandEnd)
+							atomicMax(&owner[(size_t)(y - (int)M.bandBegin) * M.width + x], tri + 1);
 					});
 			}
 			// one atomic per warp
@@ -187,6 +193,16 @@ namespace upg
 			weights[i * 3 + 2] = w.z;
 		}
 
+		// covered texels of the band that fall into the caller's rows (the band adds a 7-row apron for the dilation)
+		__global__ void __launch_bounds__(256) count_in_range_kernel(const uint32_t *__restrict__ list, uint32_t n, uint32_t lo, uint32_t hi, unsigned long long *__restrict__ out)
+		{
+			const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+			const bool in = i < n && list[i] >= lo && list[i] < hi;
+			const unsigned m = __ballot_sync(0xffffffffu, in);
+			if ((threadIdx.x & 31) == 0 && m)
+				atomicAdd(out, (unsigned long long)__popc(m));
+		}
+
 		struct IsCovered
 		{
 			const uint32_t *owner;
@@ -228,7 +244,7 @@ namespace upg
 				return;
 			const uint32_t texel = A.texels[i];
 			const uint32_t tri = A.owner[texel] - 1;
-			const V3 w = texel_weights(A.mesh, tri, texel % A.mesh.width, texel / A.mesh.width);
+			const V3 w = texel_weights(A.mesh, tri, texel % A.mesh.width, texel / A.mesh.width + A.mesh.bandBegin);
 			const uint32_t i0 = A.mesh.indices[tri * 3 + 0], i1 = A.mesh.indices[tri * 3 + 1], i2 = A.mesh.indices[tri * 3 + 2];
 			// attrAt: at(ids[0]) * w[0] + at(ids[1]) * w[1] + at(ids[2]) * w[2]; normals additionally normalised
 			const V3 position = (load3(A.positions, i0) * w.x + load3(A.positions, i1) * w.y) + load3(A.positions, i2) * w.z;
@@ -781,7 +797,7 @@ extern "C"
 				e = cudaMemsetAsync(downer, 0, sizeof(uint32_t) * texels, cs.compute);
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(dvisits, 0, sizeof(unsigned long long), cs.compute);
-			RasterMesh M{ duv, didx, nidx / 3, w, h };
+			RasterMesh M{ duv, didx, nidx / 3, w, h, 0, h };
 			if (e == cudaSuccess && M.triangles)
 			{
 				raster_owner_kernel<<<blocks_for(M.triangles, BAKE_BLOCK), BAKE_BLOCK, 0, cs.compute>>>(M, downer, dvisits);
@@ -870,53 +886,45 @@ extern "C"
 		return rc;
 	}
 
-	int upg_bake(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)
+	int upg_bake_device(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, void *cuda_stream)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
-		if (!p || !positions || !normals || !albedo || !special || !heightMap)
+		if (!p || !dpos || !dnrm || !duv || !didx || !dAlbedo || !dSpecial || !dHeight)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
-		int rc = check_mesh(uvs, nverts, idx, nidx, w, h);
-		if (rc)
-			return rc;
+		if (nidx % 3 != 0)
+			return fail(UPG_ERR_ARGUMENT, "generating texture requires triangles mesh");
+		if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull || row0 > row1 || row1 > h)
+			return fail(UPG_ERR_ARGUMENT, "bad texture resolution %u x %u or rows [%u, %u)", w, h, row0, row1);
 		cudaError_t e = cudaSetDevice(p->device);
 		if (e != cudaSuccess)
 			return cuda_fail(e, "cudaSetDevice");
-		CallStreams cs;
-		rc = cs.open();
-		if (rc)
-			return rc;
+		cudaStream_t s = (cudaStream_t)cuda_stream;
 		t_lastCovered = 0;
+		if (row0 == row1)
+			return UPG_OK;
+		int rc = UPG_OK;
 		{
-			cudaStream_t s = cs.compute;
 			Scratch mem(s);
-			const size_t texels = (size_t)w * h;
 			const int ach = water ? 4 : 3;
 			const int purpose = water ? MP_WATER : MP_LAND;
-			float *dpos = mem.alloc<float>((size_t)nverts * 3);
-			float *dnrm = mem.alloc<float>((size_t)nverts * 3);
-			float *duv = mem.alloc<float>((size_t)nverts * 2);
-			uint32_t *didx = mem.alloc<uint32_t>(nidx);
+			// the band: the caller's rows plus what seven dilation rounds can reach (imageDilation(img, 7), textures.cpp:73-77)
+			const uint32_t bandBegin = row0 > 7 ? row0 - 7 : 0;
+			const uint32_t bandEnd = row1 + 7 < h ? row1 + 7 : h;
+			const uint32_t bandH = bandEnd - bandBegin;
+			const size_t texels = (size_t)w * bandH;
 			uint32_t *owner = mem.alloc<uint32_t>(texels);
 			uint32_t *list = mem.alloc<uint32_t>(texels);
 			uint32_t *dcount = mem.alloc<uint32_t>(1);
-			unsigned long long *dvisits = mem.alloc<unsigned long long>(1);
+			unsigned long long *dvisits = mem.alloc<unsigned long long>(2);
 			float *imgAlbedo = mem.alloc<float>(texels * ach);
 			float *imgSpecial = mem.alloc<float>(texels * 2);
 			float *imgHeight = mem.alloc<float>(texels);
 			uint8_t *q = mem.alloc<uint8_t>(texels * (ach + 3));
 			e = mem.err;
 			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(dpos, positions, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(dnrm, normals, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(duv, uvs, sizeof(float) * 2 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(didx, idx, sizeof(uint32_t) * nidx, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
 				e = cudaMemsetAsync(owner, 0, sizeof(uint32_t) * texels, s);
 			if (e == cudaSuccess)
-				e = cudaMemsetAsync(dvisits, 0, sizeof(unsigned long long), s);
+				e = cudaMemsetAsync(dvisits, 0, sizeof(unsigned long long) * 2, s);
 			// imageFill(NaN) (sources/textures.cpp:47-63): all-ones is a quiet NaN
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(imgAlbedo, 0xff, sizeof(float) * texels * ach, s);
@@ -925,7 +933,7 @@ extern "C"
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(imgHeight, 0xff, sizeof(float) * texels, s);
 
-			RasterMesh M{ duv, didx, nidx / 3, w, h };
+			RasterMesh M{ duv, didx, nidx / 3, w, h, bandBegin, bandEnd };
 			if (e == cudaSuccess && M.triangles)
 			{
 				raster_owner_kernel<<<blocks_for(M.triangles, BAKE_BLOCK), BAKE_BLOCK, 0, s>>>(M, owner, dvisits);
@@ -933,6 +941,7 @@ extern "C"
 			}
 			// covered texels in raster order
 			uint32_t covered = 0;
+			unsigned long long coveredRows = 0;
 			if (e == cudaSuccess)
 			{
 				size_t tmpBytes = 0;
@@ -950,8 +959,14 @@ extern "C"
 					e = cudaMemcpyAsync(&covered, dcount, sizeof(covered), cudaMemcpyDeviceToHost, s);
 				if (e == cudaSuccess)
 					e = cudaStreamSynchronize(s);
+				if (e == cudaSuccess && covered)
+				{
+					count_in_range_kernel<<<blocks_for(covered, 256), 256, 0, s>>>(list, covered, (row0 - bandBegin) * w, (row1 - bandBegin) * w, dvisits + 1);
+					e = cudaGetLastError();
+					if (e == cudaSuccess)
+						e = cudaMemcpyAsync(&coveredRows, dvisits + 1, sizeof(coveredRows), cudaMemcpyDeviceToHost, s);
+				}
 			}
-			t_lastCovered = covered;
 
 			// K6 in chunks of the list: bounds the scratch (9 probes x 16 B per texel) whatever the texture size
 			const uint32_t chunk = 1u << 22;
@@ -991,28 +1006,75 @@ extern "C"
 				}
 			}
 
-			// K7 + download
+			// K7 over the band (its outer 7 rows are apron unless they are the image border), then the caller's rows
 			uint8_t *qAlbedo = q, *qSpecial = q + texels * ach, *qHeight = qSpecial + texels * 2;
+			const size_t skip = (size_t)(row0 - bandBegin) * w, keep = (size_t)(row1 - row0) * w;
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = dilate7(imgAlbedo, w, h, ach, qAlbedo, s);
+				e = dilate7(imgAlbedo, w, bandH, ach, qAlbedo, s);
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = dilate7(imgSpecial, w, h, 2, qSpecial, s);
+				e = dilate7(imgSpecial, w, bandH, 2, qSpecial, s);
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = dilate7(imgHeight, w, h, 1, qHeight, s);
+				e = dilate7(imgHeight, w, bandH, 1, qHeight, s);
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = cudaMemcpyAsync(albedo, qAlbedo, texels * ach, cudaMemcpyDeviceToHost, s);
+				e = cudaMemcpyAsync(dAlbedo, qAlbedo + skip * ach, keep * ach, cudaMemcpyDefault, s);
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = cudaMemcpyAsync(special, qSpecial, texels * 2, cudaMemcpyDeviceToHost, s);
+				e = cudaMemcpyAsync(dSpecial, qSpecial + skip * 2, keep * 2, cudaMemcpyDefault, s);
 			if (e == cudaSuccess && rc == UPG_OK)
-				e = cudaMemcpyAsync(heightMap, qHeight, texels, cudaMemcpyDeviceToHost, s);
+				e = cudaMemcpyAsync(dHeight, qHeight + skip, keep, cudaMemcpyDefault, s);
 			if (e == cudaSuccess)
 				e = cudaStreamSynchronize(s);
+			t_lastCovered = coveredRows;
 			if (rc == UPG_OK && e != cudaSuccess)
 				rc = cuda_fail(e, "upg_bake");
 			if (rc == UPG_OK)
 				rc = check_status(p, s, "upg_bake");
 		}
+		return rc;
+	}
+
+	int upg_bake_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !positions || !normals || !albedo || !special || !heightMap)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		int rc = check_mesh(uvs, nverts, idx, nidx, w, h);
+		if (rc)
+			return rc;
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		rc = cs.open();
+		if (rc)
+			return rc;
+		{
+			cudaStream_t s = cs.compute;
+			Scratch mem(s);
+			float *dpos = mem.alloc<float>((size_t)nverts * 3);
+			float *dnrm = mem.alloc<float>((size_t)nverts * 3);
+			float *duv = mem.alloc<float>((size_t)nverts * 2);
+			uint32_t *didx = mem.alloc<uint32_t>(nidx);
+			e = mem.err;
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(dpos, positions, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(dnrm, normals, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(duv, uvs, sizeof(float) * 2 * nverts, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess)
+				e = cudaMemcpyAsync(didx, idx, sizeof(uint32_t) * nidx, cudaMemcpyHostToDevice, s);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "upload mesh");
+			// the outputs are host memory: the core's final copies are cudaMemcpyDefault, so they land there directly
+			if (rc == UPG_OK)
+				rc = upg_bake_device(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, albedo, special, heightMap, s);
+		}
 		cs.close();
 		return rc;
+	}
+
+	int upg_bake(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)
+	{
+		return upg_bake_rows(planet, water, positions, normals, uvs, nverts, idx, nidx, w, h, 0, h, albedo, special, heightMap);
 	}
 }

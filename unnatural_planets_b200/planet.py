@@ -165,3 +165,23 @@ class Planet:
         capi.check(self._lib.upg_bake(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, _ptr(albedo), _ptr(special), _ptr(height)))
         self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
         return albedo, special, height
+
+    def bake_rows(self, water, positions, normals, uvs, indices, w, h, row0, row1):
+        """rows [row0, row1) of the textures bake() returns (upg_bake_rows): the unit of texel-row sharding across GPUs."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        rows = row1 - row0
+        albedo = np.zeros((rows, w, 4 if water else 3), dtype=np.uint8)
+        special = np.zeros((rows, w, 2), dtype=np.uint8)
+        height = np.zeros((rows, w, 1), dtype=np.uint8)
+        capi.check(self._lib.upg_bake_rows(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, row0, row1, _ptr(albedo), _ptr(special), _ptr(height)))
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
+        return albedo, special, height
+
+    def bake_device(self, water, d_pos, d_nrm, d_uv, nverts, d_idx, nidx, w, h, row0, row1, d_albedo, d_special, d_height, stream=0):
+        """upg_bake_device: every pointer is an integer DEVICE address; synchronises `stream` before returning."""
+        vp = C.c_void_p
+        capi.check(self._lib.upg_bake_device(self._h, int(bool(water)), vp(d_pos), vp(d_nrm), vp(d_uv), nverts, vp(d_idx), nidx, w, h, row0, row1, vp(d_albedo), vp(d_special), vp(d_height), vp(stream)))
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
