@@ -1,20 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the generation hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid R] [--texture T]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
-One "step" = the dense SDF sampling of one planet: the three terrain fields the generator meshes (land, water,
-navigation; sources/generator.cpp:432-439) over the 500^3 meshing grid (sources/meshGeneration.cpp:19-28) of the
-reference's default configuration (`--shape sphere`, elevation lakes; BASELINE.json configs[0]) = 3.75e8 samples.
-Weak scaling: every rank samples one such planet per step (planet i of the batch gets the seed stream advanced by
-i draws), there is no data-path collective; `value` = samples of all ranks / max-over-ranks device time.
+Workload = BASELINE.json configs[2], the largest single-GPU configuration: `--shape sphere` (elevation lakes, colouring
+default, default seed) at 2x the meshing grid resolution (1000^3 samples per field, 3 fields: land, water, navigation;
+sources/generator.cpp:432-439) with a 4096 x 4096 albedo / special / height bake of the land and the water surface.
 
-Prints ONE JSON line (rank 0).  `value`: inputs (a ~1 KB parameter block) and outputs resident in HBM.
-`e2e`: the same samples through the host-buffer C-ABI call upg_field_samples (device->host copies inside the timed
-region).  `roofline`: K1 against the FP32 FMA ceiling measured in this run.  `cpu_baseline`: the reference's own
-sampling loop (oracle/_ref, the reference sources compiled verbatim) on a bounded z-slab sample, all host threads.
+The metric is two-part (BASELINE.json: "SDF samples/s and baked texels/s ... + planet gen time vs host CPU"):
+  * `value` (metric sdf_samples_per_s): one step = the dense SDF sampling of one planet's three fields, samples resident in
+    HBM, timed with CUDA events over exactly K steps after W warm-up steps, max over ranks;  `e2e` = the same samples
+    through the host-buffer C-ABI call upg_field_samples into pinned host memory (device->host copies inside the timing).
+  * `texel_bake` (baked_texels_per_s): one step = upg_bake_device of the land + water textures (K5 raster, K6 colouring,
+    K7 dilation + quantisation) with mesh and outputs resident in HBM;  its `e2e` = upg_bake with host mesh and host images.
+  * `planet`: wall-clock of the whole hot path of one planet through the C ABI with host buffers (3 x upg_field_mesh =
+    sampling + isosurface + mesh download, 2 x upg_bake), next to the CPU reference's extrapolated time for the same work.
+Weak scaling: every rank generates its own planet (planet i uses the default seed stream advanced by i draws); there is no
+data-path collective; whole-job value = units of all ranks / max-over-ranks device time.
+`roofline`: the dominant kernel of each leg against the FP32 FMA ceiling measured in this run (both legs are FP32 / INT32
+issue bound, nothing on this path is a contraction; DESIGN.md "Rooflines").  `cpu_baseline`: the reference's own loops
+(oracle/_ref = the reference sources compiled verbatim) on a bounded sample, all host threads, rank 0 only.
 """
 import argparse
 import json
@@ -30,13 +37,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sdf_samples_per_s"
 UNIT = "samples/s"
-RES = 500
 FIELDS = ("land", "water", "navigation")
-SHAPE, ELEVATION = "sphere", "lakes"
-WORKLOAD = "BASELINE configs[0]: --shape sphere (elevation lakes, default seed), 3 fields (land, water, navigation) x 500^3 grid per planet"
-# algorithmic FP32 work of one sample (FMA = 2), per field, for sphere+lakes: see DESIGN.md "K1 work per sample"
-# (instruction counts of the un-contracted arithmetic, cross-checked with ncu smsp__sass_thread_inst_executed_op_f*)
-FLOPS_PER_SAMPLE = {"land": 640.0, "navigation": 640.0, "water": 9.0}
+SHAPE, ELEVATION, COLORING = "sphere", "lakes", "default"
+# algorithmic FP32 work (FMA = 2) per unit, counted from the un-contracted arithmetic; DESIGN.md "Work per unit"
+FLOPS_PER_SAMPLE_LAND = 640.0
+FLOPS_PER_TEXEL_LAND = 7200.0
+
+
+def workload(args):
+    return "BASELINE configs[2]: --shape sphere (elevation lakes, colouring default, default seed), 3 fields (land, water, navigation) x %d^3 grid, %d x %d land + water bake" % (args.grid, args.texture, args.texture)
 
 
 def seed_for(index):
@@ -55,7 +64,7 @@ def seed_for(index):
 
 
 class ClockSampler:
-    """polls SM clock / throttle reasons during the timed region (B200_PROFILING.md 'clocks line')"""
+    """polls SM clock / throttle reasons during the timed regions (B200_PROFILING.md 'clocks line')"""
 
     QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -82,7 +91,7 @@ class ClockSampler:
     def _run(self):
         while not self._stop.is_set():
             self._poll()
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -96,39 +105,73 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_reference_rate(slices, threads):
-    """the reference's sampling loop (oracle/_ref) on `slices` z-slices around the equator of the land field"""
+# ---- CPU reference legs (oracle/_ref; oracle/ is only ever the checker or the timed baseline, never the product) ----
+def cpu_sampling_rate(res, slices, threads):
+    """the reference's sampling loop (MarchingCubes::updateByPosition x terrainSdfLand) on `slices` z-slices around the equator"""
     from oracle import ref as oref
 
     if not oref.available():
         from oracle import port as oport  # the standalone restatement
 
-        return oport.sample_rate(SHAPE, ELEVATION, RES, slices, threads) + ("port",)
+        return oport.sample_rate(SHAPE, ELEVATION, res, slices, threads) + ("port",)
     planet = oref.RefPlanet(shape=SHAPE, elevation=ELEVATION)
-    z0 = RES // 2 - slices // 2
+    z0 = res // 2 - slices // 2
     t = time.perf_counter()
-    planet.grid("land", RES, z0=z0, z1=z0 + slices, threads=threads)
+    planet.grid("land", res, z0=z0, z1=z0 + slices, threads=threads)
     dt = time.perf_counter() - t
-    return slices * RES * RES / dt, dt, "reference"
+    return slices * res * res / dt, dt, "reference"
+
+
+def cpu_bake_rate(mesh, texture, window, threads):
+    """generateTexturesLand (rasterise + terrainTile per visit + 7 dilations + u8) of `threads` UV windows of the full bake,
+    one window per host thread -- the reference bakes one chunk per pool thread (sources/generator.cpp:159)"""
+    from oracle import ref as oref
+    from unnatural_planets_b200 import synth
+
+    if not oref.available():
+        return None
+    planet = oref.RefPlanet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING)
+    pos, nrm, uv, idx = mesh
+    size = window / texture
+    jobs = []
+    for k in range(threads):
+        # windows spread over the upper-hemisphere part of the octahedral map (no folds there)
+        u0 = 0.27 + (k % 4) * size * 1.01
+        v0 = 0.27 + (k // 4) * size * 1.01
+        jobs.append(synth.uv_window_submesh(pos, nrm, uv, idx, u0, v0, size))
+    covered = [0] * threads
+
+    def work(k):
+        p, n, u, i = jobs[k]
+        a, s, h = planet.bake(0, p, n, u, i, window, window)
+        covered[k] = int((a != 0).any(axis=2).sum())
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    t = time.perf_counter()
+    [x.start() for x in ts]
+    [x.join() for x in ts]
+    dt = time.perf_counter() - t
+    return sum(covered) / dt, dt, sum(covered)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    slices = 12 * threads  # ~12 x 250k samples per thread: a few seconds of CPU work per step
+    res = args.grid
+    slices = max(1, (12 * threads * 250000) // (res * res))  # ~3e6 samples per thread and step: seconds of CPU work
     rates = []
     for i in range(args.warmup + args.steps):
-        r, dt, kind = cpu_reference_rate(slices, threads)
+        r, dt, kind = cpu_sampling_rate(res, slices, threads)
         if i >= args.warmup:
             rates.append((r, dt))
     value = statistics.mean(r for r, _ in rates)
     ms = statistics.mean(dt for _, dt in rates) * 1e3
-    sample = "%d z-slices x %d^2 of the land field per step (%.3g of one planet's 3.75e8 samples), %d threads" % (slices, RES, slices * RES * RES / (3.0 * RES**3), threads)
+    sample = "%d z-slices x %d^2 of the land field per step (%.3g of one planet's %.3g samples), %d threads" % (slices, res, slices / (3.0 * res), 3.0 * res**3, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "host CPU, no GPU involved"},
+        "config": {"workload": workload(args), "note": "host CPU, no GPU involved"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -136,7 +179,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_mesh(planet, texture):
+    """the land and water surfaces of the planet with synthetic texture coordinates (see unnatural_planets_b200/synth.py)"""
+    import numpy as np
+
+    from unnatural_planets_b200 import synth
+
+    out = {}
+    for name in ("land", "water"):
+        m = planet.field_mesh(name)
+        uv = synth.octahedral_uv(m["positions"])
+        idx = synth.drop_folded_triangles(uv, m["indices"])
+        # meshFlipNormals (sources/meshGeneration.cpp:42): the generator bakes the flipped mesh
+        out[name] = (m["positions"], np.ascontiguousarray(-m["normals"]), uv, idx)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -144,50 +204,54 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    planet = Planet(shape=SHAPE, elevation=ELEVATION, grid=RES, device=local_rank, seed=seed_for(rank))
-    n = RES**3
+    res, tex = args.grid, args.texture
+    planet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank))
+    n = res**3
     bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in FIELDS]
     stream = torch.cuda.current_stream()
-
-    def step():
-        for f, b in zip(FIELDS, bufs):
-            planet.field_samples_device(f, 0, RES, b.data_ptr(), stream.cuda_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- leg 1: SDF sampling (the contract's timed region) ---------------------------------------------------------
+    def step():
+        for f, b in zip(FIELDS, bufs):
+            planet.field_samples_device(f, 0, res, b.data_ptr(), stream.cuda_stream)
+
     for _ in range(args.warmup):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
     ms_total = e0.elapsed_time(e1)
 
-    # per-kernel timing of the dominant kernel (land field) with CUDA events on the launching stream
+    # the dominant kernel alone (land field), CUDA events on the launching stream
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     for _ in range(max(3, args.steps)):
         k0.record(stream)
-        planet.field_samples_device("land", 0, RES, bufs[0].data_ptr(), stream.cuda_stream)
+        planet.field_samples_device("land", 0, res, bufs[0].data_ptr(), stream.cuda_stream)
         k1.record(stream)
         k1.synchronize()
         kernel_ms.append(k0.elapsed_time(k1))
     land_ms = statistics.mean(kernel_ms)
 
     # end to end through the host-buffer C-ABI call: device->host copies inside the timed region
-    host = [torch.empty(n, dtype=torch.float32, pin_memory=True) for _ in FIELDS]
-    e2e_steps = max(1, min(args.steps, 3))
+    host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    host_np = host.numpy().reshape(res, res, res)
+    e2e_steps = max(1, min(args.steps, 2))
 
     def e2e_step():
-        for f, h in zip(FIELDS, host):
-            planet.field_samples(f, 0, RES, h.numpy().reshape(RES, RES, RES))
+        for f in FIELDS:
+            planet.field_samples(f, 0, res, host_np)
 
     e2e_step()
     barrier()
@@ -196,11 +260,86 @@ def run_ours(args, rank, world, local_rank):
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t) / e2e_steps
+    del host, host_np
+    del bufs
+    torch.cuda.empty_cache()
 
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- leg 2: isosurface (sampling + K2..K4 + download, through the C ABI) -------------------------------------------
+    t = time.perf_counter()
+    meshes = bench_mesh(planet, tex)  # land + water; also the input of the bake
+    mesh_s_two = time.perf_counter() - t
+    t = time.perf_counter()
+    nav = planet.field_mesh("navigation")
+    mesh_s = mesh_s_two + (time.perf_counter() - t)  # includes the host-side synthetic UVs of two meshes (numpy, ~0.1 s)
+    t = time.perf_counter()
+    m2 = planet.field_mesh("land")
+    field_mesh_land_s = time.perf_counter() - t
+    mesh_stats = {"land_vertices": int(len(m2["positions"])), "land_triangles": int(len(m2["indices"]) // 3), "navigation_triangles": int(len(nav["indices"]) // 3), "near_zero_samples": m2["near_zero_samples"]}
+    del nav, m2
+
+    # ---- leg 3: texel baking -------------------------------------------------------------------------------------------
+    dmesh = {}
+    for name, (pos, nrm, uv, idx) in meshes.items():
+        dmesh[name] = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (pos, nrm, uv, idx.view(np.int32)))
+    outs = {"land": [torch.empty(tex * tex * c, dtype=torch.uint8, device=dev) for c in (3, 2, 1)], "water": [torch.empty(tex * tex * c, dtype=torch.uint8, device=dev) for c in (4, 2, 1)]}
+    covered = {}
+
+    def bake_step():
+        for name, water in (("land", 0), ("water", 1)):
+            p, nm, u, i = dmesh[name]
+            o = outs[name]
+            planet.bake_device(water, p.data_ptr(), nm.data_ptr(), u.data_ptr(), p.shape[0], i.data_ptr(), i.shape[0], tex, tex, 0, tex, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream.cuda_stream)
+            covered[name] = planet.last_covered_texels
+
+    bake_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 3)):
+        bake_step()
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for _ in range(bake_steps):
+        bake_step()
+    b1.record(stream)
+    barrier()
+    bake_ms = b0.elapsed_time(b1) / bake_steps
+    # land alone, for the roofline of the colouring kernel
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record(stream)
+    p, nm, u, i = dmesh["land"]
+    o = outs["land"]
+    planet.bake_device(0, p.data_ptr(), nm.data_ptr(), u.data_ptr(), p.shape[0], i.data_ptr(), i.shape[0], tex, tex, 0, tex, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream.cuda_stream)
+    l1.record(stream)
+    l1.synchronize()
+    bake_land_ms = l0.elapsed_time(l1)
+    clocks.__exit__()
+
+    # end to end: host mesh in, host images out (pinned)
+    himg = {"land": [torch.empty(tex * tex * c, dtype=torch.uint8, pin_memory=True) for c in (3, 2, 1)], "water": [torch.empty(tex * tex * c, dtype=torch.uint8, pin_memory=True) for c in (4, 2, 1)]}
+    L = capi.load_library()
+    import ctypes as C
+
+    def bake_e2e():
+        for name, water in (("land", 0), ("water", 1)):
+            pos, nrm, uv, idx = meshes[name]
+            o = himg[name]
+            capi.check(L.upg_bake(planet._h, water, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), tex, tex, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr())))
+
+    bake_e2e()
+    barrier()
+    t = time.perf_counter()
+    bake_e2e()
+    bake_e2e_s = time.perf_counter() - t
+    h2d_bake = sum(a.nbytes for m in meshes.values() for a in m)
+    d2h_bake = tex * tex * (3 + 2 + 1 + 4 + 2 + 1)
+
+    texels = covered["land"] + covered["water"]
+    times = torch.tensor([ms_total, e2e_s * 1e3, bake_ms, bake_e2e_s * 1e3, mesh_s * 1e3], dtype=torch.float64, device=dev)
+    counts = torch.tensor([float(texels)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(times[0]), float(times[1])
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, bake_ms_max, bake_e2e_ms, mesh_ms = (float(x) for x in times)
+    texels_all = float(counts[0])
     if rank != 0:
         return
 
@@ -208,41 +347,63 @@ def run_ours(args, rank, world, local_rank):
     value = samples_per_step * args.steps / (ms_total * 1e-3)
     e2e_value = samples_per_step / (e2e_ms * 1e-3)
 
-    peak = C_float_peak(capi, local_rank)
-    flops_land = FLOPS_PER_SAMPLE["land"] * n
-    achieved = flops_land / (land_ms * 1e-3) / 1e12
+    peak = fp32_peak(capi, local_rank)
+    achieved = FLOPS_PER_SAMPLE_LAND * n / (land_ms * 1e-3) / 1e12
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    peak_source = "FP32 FMA ceiling measured in this run by upg_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 SIMT figure)"
     roofline = {
         "bound": "fp32", "kernel": "sdf_sample_kernel<sphere,lakes> (land field)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": None,
-        "peak_source": "FP32 FMA ceiling measured in this run by upg_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 SIMT figure)",
-        "kernel_ms": land_ms, "flops_per_sample": FLOPS_PER_SAMPLE["land"],
+        "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_source,
+        "kernel_ms": land_ms, "flops_per_sample": FLOPS_PER_SAMPLE_LAND,
         "hbm": {"achieved_gbs": 4.0 * n / (land_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "4 B/sample written; the kernel is compute bound"},
+    }
+    bake_achieved = FLOPS_PER_TEXEL_LAND * covered["land"] / (bake_land_ms * 1e-3) / 1e12
+    texel_bake = {
+        "metric": "baked_texels_per_s", "value": texels_all / (bake_ms_max * 1e-3), "unit": "texels/s", "steps": bake_steps, "ms_per_step": bake_ms_max,
+        "texels_per_step": int(texels_all), "covered": {k: int(v) for k, v in covered.items()}, "texture": [tex, tex],
+        "note": "texels = covered texels (one terrainTile each; the reference evaluates every (triangle, texel) visit) of the land (3+2+1 ch) and water (4+2+1 ch) surfaces; UVs: synthetic octahedral chart",
+        "e2e": {"value": texels_all / world / (bake_e2e_ms * 1e-3) * world, "unit": "texels/s", "h2d_bytes_per_step": int(h2d_bake), "d2h_bytes_per_step": int(d2h_bake), "path": "upg_bake: host mesh -> device, pinned host images <- device, wall clock"},
+        "roofline": {"bound": "fp32", "kernel": "tile_color_kernel<default> + its K1 probes (land bake, whole upg_bake_device call)", "achieved": bake_achieved, "peak": peak, "unit": "TFLOP/s", "frac": bake_achieved / peak if peak else None, "traffic": None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": FLOPS_PER_TEXEL_LAND},
+    }
+    planet_ms = mesh_ms + bake_e2e_ms
+    planet_line = {
+        "ms": planet_ms, "isosurface_ms": mesh_ms, "bake_ms": bake_e2e_ms, "field_mesh_land_ms": field_mesh_land_s * 1e3,
+        "what": "3 x upg_field_mesh (sampling + Dual Marching Cubes + mesh download; incl. ~0.1 s of host numpy for the synthetic UVs) + 2 x upg_bake, host buffers, wall clock", "mesh": mesh_stats,
     }
 
     threads = os.cpu_count() or 1
-    slices = min(RES, 30 * threads)  # 10-30 s of CPU work in total, spread over every host thread
+    cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable", "sample": ""}
     try:
-        cpu_rate, cpu_dt, kind = cpu_reference_rate(slices, threads)
-        cpu = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": "%d z-slices x %d^2 of the land field (%.1f s of CPU work on %d threads)" % (slices, RES, cpu_dt, threads)}
+        slices = max(1, min(res, (30 * threads * 250000) // (res * res)))  # ~10 s of CPU work in total, spread over every host thread
+        cpu_rate, cpu_dt, kind = cpu_sampling_rate(res, slices, threads)
+        cpu = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": "%d z-slices x %d^2 of the land field (%.1f s on %d threads)" % (slices, res, cpu_dt, threads)}
+        planet_line["cpu_sampling_ms_extrapolated"] = 3.0 * n / cpu_rate * 1e3
+        window = 256
+        r = cpu_bake_rate(meshes["land"], tex, window, threads)
+        if r:
+            cpu["texel_bake"] = {"value": r[0], "unit": "texels/s", "sample": "%d windows of %d^2 texels of the %d^2 land bake, one per thread (%.1f s, %d covered texels)" % (threads, window, tex, r[1], r[2])}
+            planet_line["cpu_bake_ms_extrapolated"] = texels_all / world / r[0] * 1e3
     except Exception as ex:  # the baseline is reported, never required for the GPU number
-        cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable", "sample": str(ex)}
+        cpu["sample"] = "failed: %r" % (ex,)
 
+    launches_sampling = len(FIELDS) * args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "grid": RES, "fields": list(FIELDS), "planets_per_step": world, "l2": "each step writes 1.5 GB of samples per GPU (>> 126 MB L2); inputs are a ~1 KB parameter block"},
+        "config": {"workload": workload(args), "grid": res, "fields": list(FIELDS), "texture": tex, "planets_per_step": world, "l2": "each sampling step writes %.1f GB per GPU and each bake step touches > 1 GB of float images (>> 126 MB L2); inputs are a ~2 KB parameter block and a mesh" % (12e-9 * n)},
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n * len(FIELDS), "path": "upg_field_samples -> pinned host buffers, wall clock incl. D2H"},
-        "gpu_launches": len(FIELDS) * args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n * len(FIELDS), "path": "upg_field_samples -> pinned host buffer, wall clock incl. D2H"},
+        "gpu_launches": launches_sampling,
         "roofline": roofline,
+        "texel_bake": texel_bake,
+        "planet": planet_line,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
 
 
-def C_float_peak(capi, device):
+def fp32_peak(capi, device):
     import ctypes as C
 
     v = C.c_float(0)
@@ -256,6 +417,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=1000, help="samples per axis of the meshing grid (BASELINE configs[2]: 1000)")
+    ap.add_argument("--texture", type=int, default=4096, help="bake resolution (BASELINE configs[2]: 4096)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -59,15 +59,24 @@ def test_seed_order_matches_reference_registry(hostlib, shape, elev):
     log = HostPlanet(hostlib, shape, elev).seed_log()
     n_shape = 1 if shape == "asteroid" else 0
     n_elev = {"none": 0, "simple": 1, "legacy": 2, "lakes": 4, "islands": 4, "craters": 2}[elev]
-    assert len(log) == n_shape + n_elev
+    # ... followed by the 40 draws of coloringDefault (sources/coloringModes.cpp:905-930 through terrainPreseed)
+    assert len(log) == n_shape + n_elev + 40
     ref_seeds = [np.uint32(r["seed"] & 0xFFFFFFFF) for r in reg]
+    b = n_shape + n_elev
     if elev == "craters":
         # the first elevation seed goes to the Voronoi object (not a NoiseFunction): registry holds only the second
         assert log[n_shape + 1] == ref_seeds[n_shape]
         if n_shape:
             assert log[0] == ref_seeds[0]
+        rb = b - 1
     else:
-        assert list(log) == ref_seeds[: len(log)]
+        assert list(log[:b]) == ref_seeds[:b]
+        rb = b
+    # colouring: draws that are not NoiseFunctions (three Voronoi seeds) are absent from the registry, the three `static
+    # const uint32 seed` draws (bedrock, grass, ice) show up later, twice each, on the Cellular objects that share them
+    c = [int(x) for x in log[b:]]
+    expect = c[0:3] + [c[4], c[5], c[3], c[3], c[6]] + c[7:17] + [c[18], c[17], c[17], c[19], c[20], c[21]] + c[23:27] + c[29:33] + [c[34], c[35], c[33], c[33]] + c[36:40]
+    assert [int(x) for x in ref_seeds[rb:]] == expect
     # the thread generator itself is only advanced by the fibers (3 draws) and asteroid (1 draw) statics
     assert tuple(int(x) for x in g["rng_state_after_preseed"]) != (0, 0)
 
@@ -97,6 +106,6 @@ def test_rng_known_answers(hostlib):
         s1 ^= s0
         s = [rotl(s0, 24) ^ s1 ^ ((s1 << 16) & mask), rotl(s1, 37)]
     assert out == [int(x) for x in m["rng_raw"]]
-    # and the product's own stream (seed log of a lakes planet) is the low 32 bits of the first four outputs
+    # and the product's own stream (seed log of a lakes planet with the default colouring: 4 + 40 draws) is the low 32 bits
     log = HostPlanet(hostlib, "sphere", "lakes").seed_log()
-    assert [int(x) for x in log] == [x & 0xFFFFFFFF for x in out[:4]]
+    assert [int(x) for x in log] == [x & 0xFFFFFFFF for x in out[:44]]

@@ -67,7 +67,8 @@ TILE_COLUMNS = ("albedo_r", "albedo_g", "albedo_b", "roughness", "metallic", "he
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libupg.so")
+    # UPG_LIBRARY: an alternative build of the same library (A/B measurements of kernel variants); never a fallback
+    return os.environ.get("UPG_LIBRARY") or os.path.join(HERE, "libupg.so")
 
 
 _lib = None

@@ -11,6 +11,13 @@
 
 #include "upg_common.cuh"
 
+// the two double-precision HSLuv conversions are real functions on the device (four call sites, ~1 k instructions each)
+#if defined(__CUDACC__)
+#define UPG_COLOR_OUTLINED static __host__ __device__ __noinline__
+#else
+#define UPG_COLOR_OUTLINED inline
+#endif
+
 namespace upg
 {
 	// Real wrap(Real) (include/cage-core/math.h:810-816)
@@ -171,7 +178,7 @@ namespace upg
 			return c / 12.92;
 		}
 
-		UPG_HD D3 rgb2hsluv(double r, double g, double b)
+		UPG_COLOR_OUTLINED D3 rgb2hsluv(double r, double g, double b)
 		{
 			const double kappa = 903.29629629629629629630;
 			const double epsilon = 0.00885645167903563082;
@@ -214,7 +221,7 @@ namespace upg
 			return D3{ H, S, L };
 		}
 
-		UPG_HD D3 hsluv2rgb(double h, double s, double l)
+		UPG_COLOR_OUTLINED D3 hsluv2rgb(double h, double s, double l)
 		{
 			const double kappa = 903.29629629629629629630;
 			const double refU = 0.19783000664283680764, refV = 0.46831999493879100370;

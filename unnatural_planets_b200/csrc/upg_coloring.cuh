@@ -229,6 +229,18 @@ namespace upg
 		return (float)((double)(result >> 11) * 0x1.0p-53);
 	}
 
+	// nearest projected feature point, as a real function (three call sites)
+#if defined(__CUDACC__)
+	static __device__ __noinline__ V3 voronoi_nearest1(const VoronoiInst &v, V3 position, V3 normal)
+#else
+	inline V3 voronoi_nearest1(const VoronoiInst &v, V3 position, V3 normal)
+#endif
+	{
+		V3 r;
+		voronoi_nearest<1, true>(v, position, normal, &r);
+		return r;
+	}
+
 	// ---- layers -------------------------------------------------------------------------------------------------
 	// beachMask (:34-49)
 	UPG_HD float beach_mask(const ColoringConsts &C, const Tile &t)
@@ -241,7 +253,7 @@ namespace upg
 	// generatePrecipitation (:59-80)
 	UPG_LAYER void generate_precipitation(const ColoringConsts &C, Tile &t)
 	{
-		float p = noise3<NT_CUBIC, FT_FBM, 2>(C.precp, t.position) * 0.5f + 0.5f;
+		float p = noise3<NT_CUBIC, FT_FBM, 2, true>(C.precp, t.position) * 0.5f + 0.5f;
 		p = saturate_(p);
 		p = smootherstep_(p);
 		p = smootherstep_(p);
@@ -255,7 +267,7 @@ namespace upg
 	// generateTemperature (:82-120)
 	UPG_LAYER void generate_temperature(const ColoringConsts &C, Tile &t)
 	{
-		float v = noise3<NT_SIMPLEX, FT_FBM, 2>(C.temp, t.position) * 0.5f + 0.5f;
+		float v = noise3<NT_SIMPLEX, FT_FBM, 2, true>(C.temp, t.position) * 0.5f + 0.5f;
 		v = saturate_(v);
 		v = smoothstep_(v);
 		v = v * 2 - 1;
@@ -263,7 +275,7 @@ namespace upg
 		{
 			float polar = abs_(atanf(t.position.y / length(v2(t.position.x, t.position.z)))) / 3.14159274101257324f * 2;
 			polar = powf(polar, 1.7f);
-			polar += noise3<NT_VALUE, FT_FBM, 3>(C.polar, t.position) * 0.1f;
+			polar += noise3<NT_VALUE, FT_FBM, 3, true>(C.polar, t.position) * 0.1f;
 			v += 0.6f - polar * 3.2f;
 		}
 		t.temperature = 15 + v * 30 - fmax_(t.elevation, 0) * 0.02f;
@@ -323,12 +335,12 @@ namespace upg
 	// generateBedrock (:202-261)
 	UPG_LAYER void generate_bedrock(const ColoringConsts &C, const float *rv, Tile &t)
 	{
-		const float depth = sqr_(noise3<NT_CUBIC, FT_NONE, 3>(C.bedrockDepth, t.position) * 0.5f + 0.501f) * 2;
-		const float freq = noise3<NT_CUBIC, FT_NONE, 3>(C.bedrockFreq, t.position) * 0.15f + 1;
+		const float depth = sqr_(noise3<NT_CUBIC, FT_NONE, 3, true>(C.bedrockDepth, t.position) * 0.5f + 0.501f) * 2;
+		const float freq = noise3<NT_CUBIC, FT_NONE, 3, true>(C.bedrockFreq, t.position) * 0.15f + 1;
 		const V3 pf = t.position * freq;
 		const float cracks = saturate_(powf(noise3_cellular<CD_HYBRID, CO_SUBTRACT, FT_NONE, 3>(rv, C.bedrockCracks, pf.x, pf.y, pf.z) * 0.5f + 0.5f, 0.7f));
 		const float value = noise3_cellular<CD_HYBRID, CO_CELL, FT_NONE, 3>(rv, C.bedrockValue, pf.x, pf.y, pf.z);
-		const float saturation = saturate_(noise3<NT_CUBIC, FT_FBM, 2>(C.bedrockSaturation, t.position) * 0.35f + 0.3f);
+		const float saturation = saturate_(noise3<NT_CUBIC, FT_FBM, 2, true>(C.bedrockSaturation, t.position) * 0.35f + 0.3f);
 		const V3 hsv = v3(0.07f, saturation, saturate_(value * 0.1f + 0.7f) * (cracks * 0.4f + 0.6f));
 		t.albedo = hsv_to_rgb(hsv);
 		t.roughness = lerp_(0.9f, value * -0.15f + 0.65f, cracks);
@@ -348,7 +360,7 @@ namespace upg
 		t.albedo = hsv_to_rgb(hsv);
 		t.roughness *= bf * 0.2f + 0.8f;
 		{
-			const float cracks = sharp_edge(saturate_(noise3<NT_SIMPLEX_REDUCED, FT_RIDGED, 2>(C.cliffsCracks, t.position) * 2 - 1.1f), 0.2f);
+			const float cracks = sharp_edge(saturate_(noise3<NT_SIMPLEX_REDUCED, FT_RIDGED, 2, true>(C.cliffsCracks, t.position) * 2 - 1.1f), 0.2f);
 			t.height *= lerp_double(1.0, 0.8, cracks);
 			t.albedo = t.albedo * lerp_double(1.0, 0.9, cracks);
 			t.roughness = lerp_(t.roughness, 0.9f, cracks);
@@ -377,7 +389,7 @@ namespace upg
 	// generateDirt (:338-402)
 	UPG_LAYER void generate_dirt(const ColoringConsts &C, Tile &t)
 	{
-		float height = noise3<NT_PERLIN, FT_FBM, 3>(C.dirtHeight, t.position) * 0.2f + 0.5f;
+		float height = noise3<NT_PERLIN, FT_FBM, 3, true>(C.dirtHeight, t.position) * 0.2f + 0.5f;
 		const float bf = sharp_edge(saturate_(height - t.height + 0.4f)) * steepness_mask(t.slope, 20, 5);
 		if (bf < 1e-7f)
 			return;
@@ -392,8 +404,8 @@ namespace upg
 		float roughness = 0.8f;
 		const float metallic = 0;
 		{
-			float cracks = sharp_edge(saturate_(noise3<NT_SIMPLEX_REDUCED, FT_RIDGED, 2>(C.dirtCracks, t.position) * 2 - 1.2f), 0.15f);
-			cracks *= sqr_(smoothstep_(saturate_(noise3<NT_CUBIC, FT_FBM, 4>(C.dirtCracksMask, t.position) * 0.5f + 0.5f))) * 0.9f + 0.1f;
+			float cracks = sharp_edge(saturate_(noise3<NT_SIMPLEX_REDUCED, FT_RIDGED, 2, true>(C.dirtCracks, t.position) * 2 - 1.2f), 0.15f);
+			cracks *= sqr_(smoothstep_(saturate_(noise3<NT_CUBIC, FT_FBM, 4, true>(C.dirtCracksMask, t.position) * 0.5f + 0.5f))) * 0.9f + 0.1f;
 			cracks *= range_mask(t.precipitation, 70, 20) * 0.9f + 0.1f;
 			height = lerp_(height, height * 0.5f, cracks);
 			color = lerp3(color, v3(0.1f, 0.1f, 0.1f), cracks);
@@ -411,10 +423,10 @@ namespace upg
 		const float bf = range_mask(t.temperature, 24, 28) * steepness_mask(t.slope, 19, 10);
 		if (bf < 1e-7f)
 			return;
-		const float heightScale = noise3<NT_SIMPLEX, FT_FBM, 3>(C.sandHeightScale, t.position) * 0.3f + 1;
-		const float height = (noise3<NT_SIMPLEX, FT_RIDGED, 3>(C.sandHeight, t.position * heightScale) * 0.2f) * (range_mask(t.precipitation, 100, 50) * 0.4f + 0.6f) + 0.5f;
-		const float colorShift = smootherstep_(smootherstep_(noise3<NT_PERLIN, FT_NONE, 3>(C.sandColor, t.position) * 0.5f + 0.5f));
-		const float hueShift = noise3<NT_CUBIC, FT_FBM, 2>(C.sandHue, t.position) * 0.1f;
+		const float heightScale = noise3<NT_SIMPLEX, FT_FBM, 3, true>(C.sandHeightScale, t.position) * 0.3f + 1;
+		const float height = (noise3<NT_SIMPLEX, FT_RIDGED, 3, true>(C.sandHeight, t.position * heightScale) * 0.2f) * (range_mask(t.precipitation, 100, 50) * 0.4f + 0.6f) + 0.5f;
+		const float colorShift = smootherstep_(smootherstep_(noise3<NT_PERLIN, FT_NONE, 3, true>(C.sandColor, t.position) * 0.5f + 0.5f));
+		const float hueShift = noise3<NT_CUBIC, FT_FBM, 2, true>(C.sandHue, t.position) * 0.1f;
 		V3 color = color_hue_shift(v3(189, 174, 152) / 255, hueShift);
 		color = interpolate_hsluv(rgb_to_hsluv(color), C.hsluvSandTarget, colorShift);
 		{
@@ -439,7 +451,7 @@ namespace upg
 		if (bf < 1e-7f)
 			return;
 		const float dryness = clamp_(t.temperature - (t.precipitation + 100) * 30 / 400, 0, 5) / 5;
-		const float hueShiftBase = noise3<NT_PERLIN, FT_FBM, 2>(C.grassHue, t.position);
+		const float hueShiftBase = noise3<NT_PERLIN, FT_FBM, 2, true>(C.grassHue, t.position);
 		const float hueShift = hueShiftBase * 0.09f - dryness * 0.1f;
 		V3 color = v3(114, 187, 77) / 255;
 		color = color_hue_shift(color, hueShift);
@@ -463,22 +475,21 @@ namespace upg
 	{
 		if (!C.flowers)
 			return;
-		if (noise3<NT_PERLIN, FT_NONE, 3>(C.boulderThreshold, t.position) < 0.15f)
+		if (noise3<NT_PERLIN, FT_NONE, 3, true>(C.boulderThreshold, t.position) < 0.15f)
 			return;
-		V3 center;
-		voronoi_nearest<1, true>(C.boulderCenters, t.position, t.normal, &center);
+		const V3 center = voronoi_nearest1(C.boulderCenters, t.position, t.normal);
 		const float dist = distance(center, t.position);
-		const float size = smootherstep_(smootherstep_(saturate_(noise3<NT_PERLIN, FT_NONE, 3>(C.boulderSize, t.position) * 0.5f + 0.5f))) * 3 + 3;
+		const float size = smootherstep_(smootherstep_(saturate_(noise3<NT_PERLIN, FT_NONE, 3, true>(C.boulderSize, t.position) * 0.5f + 0.5f))) * 3 + 3;
 		const float bf = range_mask(size - dist, 0, 0.5f);
 		if (bf < 1e-7f)
 			return;
-		const float hueShift = noise3<NT_PERLIN, FT_NONE, 3>(C.boulderHue, t.position) * 0.12f;
-		const float valueShift = noise3<NT_PERLIN, FT_NONE, 3>(C.boulderValue, t.position) * 0.18f;
+		const float hueShift = noise3<NT_PERLIN, FT_NONE, 3, true>(C.boulderHue, t.position) * 0.12f;
+		const float valueShift = noise3<NT_PERLIN, FT_NONE, 3, true>(C.boulderValue, t.position) * 0.18f;
 		V3 color = rgb_to_hsv(v3(154, 154, 154) / 255);
 		color.x = fmod_(color.x + hueShift + 1, 1.0f);
 		color.z = saturate_(color.z + valueShift);
 		color = hsv_to_rgb(color);
-		const float roughness = noise3<NT_PERLIN, FT_NONE, 3>(C.boulderScratches, t.position) * 0.1f + 0.4f;
+		const float roughness = noise3<NT_PERLIN, FT_NONE, 3, true>(C.boulderScratches, t.position) * 0.1f + 0.4f;
 		const float metallic = 0;
 		const float height = 1 - sqr_(dist / size) * 0.5f;
 		t.albedo = lerp3(t.albedo, color, bf);
@@ -491,8 +502,8 @@ namespace upg
 	UPG_LAYER void generate_water(const ColoringConsts &C, Tile &t)
 	{
 		{
-			const float colorSwitch = noise3<NT_PERLIN, FT_FBM, 2>(C.waterColorSwitch, t.position) * 0.5f + 0.5f;
-			const float hueShift = noise3<NT_CUBIC, FT_FBM, 3>(C.waterHueShift, t.position) * 0.09f;
+			const float colorSwitch = noise3<NT_PERLIN, FT_FBM, 2, true>(C.waterColorSwitch, t.position) * 0.5f + 0.5f;
+			const float hueShift = noise3<NT_CUBIC, FT_FBM, 3, true>(C.waterHueShift, t.position) * 0.09f;
 			t.albedo = color_hue_shift(interpolate_hsluv(C.hsluvWaterDeep, C.hsluvWaterShallow, colorSwitch), hueShift);
 		}
 		{
@@ -518,21 +529,19 @@ namespace upg
 			return;
 		if (!waterlily && range_mask(abs_(t.precipitation - 200), 100, 70) < 1e-5f)
 			return;
-		V3 center;
-		voronoi_nearest<1, true>(C.flowerCenter, t.position, t.normal, &center);
+		const V3 center = voronoi_nearest1(C.flowerCenter, t.position, t.normal);
 		if (distance_squared(center, t.position) > sqr_(4.0f))
 			return;
-		V3 cluster;
-		voronoi_nearest<1, true>(C.flowerCluster, t.position, t.normal, &cluster);
+		const V3 cluster = voronoi_nearest1(C.flowerCluster, t.position, t.normal);
 		if (distance_squared(center, cluster) > sqr_(20.0f))
 			return;
 		const float dist = distance(center, t.position);
-		const float size = smootherstep_(smootherstep_(saturate_(noise3<NT_PERLIN, FT_NONE, 3>(C.flowerSize, t.position) * 0.5f + 0.5f))) * 2 + 1.5f;
+		const float size = smootherstep_(smootherstep_(saturate_(noise3<NT_PERLIN, FT_NONE, 3, true>(C.flowerSize, t.position) * 0.5f + 0.5f))) * 2 + 1.5f;
 		const float bf = range_mask(size - dist, 0, 0.1f);
 		if (bf < 1e-7f)
 			return;
-		const V3 baseColor = waterlily ? v3(0.2f, 0.14f, 0) : interpolate_hsluv(C.hsluvFlowerA, C.hsluvFlowerB, sharp_edge(noise3<NT_PERLIN, FT_NONE, 3>(C.flowerColor, cluster) + 0.4f, 0.2f));
-		const V3 color = color_hue_shift(baseColor, noise3<NT_PERLIN, FT_NONE, 3>(C.flowerHue1, t.position) * 0.1f + noise3<NT_PERLIN, FT_NONE, 3>(C.flowerHue2, t.position) * 0.1f);
+		const V3 baseColor = waterlily ? v3(0.2f, 0.14f, 0) : interpolate_hsluv(C.hsluvFlowerA, C.hsluvFlowerB, sharp_edge(noise3<NT_PERLIN, FT_NONE, 3, true>(C.flowerColor, cluster) + 0.4f, 0.2f));
+		const V3 color = color_hue_shift(baseColor, noise3<NT_PERLIN, FT_NONE, 3, true>(C.flowerHue1, t.position) * 0.1f + noise3<NT_PERLIN, FT_NONE, 3, true>(C.flowerHue2, t.position) * 0.1f);
 		const float roughness = 0.8f;
 		const float metallic = waterlily ? 0.85f : 0;
 		const float height = 0.7f + sqr_(dist / size) * 0.2f;
@@ -546,7 +555,7 @@ namespace upg
 	// generateIce (:746-817)
 	UPG_LAYER void generate_ice(const ColoringConsts &C, const float *rv, Tile &t)
 	{
-		const float tempOff = noise3<NT_VALUE, FT_NONE, 3>(C.iceTempOffset, t.position) * 1.5f;
+		const float tempOff = noise3<NT_VALUE, FT_NONE, 3, true>(C.iceTempOffset, t.position) * 1.5f;
 		const float bf = sharp_edge(range_mask(t.temperature + tempOff, 0, -3)) * (1 - beach_mask(C, t));
 		if (bf < 1e-7f)
 			return;
@@ -555,7 +564,7 @@ namespace upg
 			if (t.type != TT_CLIFFS)
 				t.type = TT_ROUGH;
 		}
-		const float freq = noise3<NT_VALUE, FT_FBM, 3>(C.iceFreq, t.position) * 0.08f + 1;
+		const float freq = noise3<NT_VALUE, FT_FBM, 3, true>(C.iceFreq, t.position) * 0.08f + 1;
 		const V3 pf = t.position * freq;
 		const float thickness = sharp_edge(saturate_(noise3_cellular<CD_HYBRID, CO_CELL, FT_FBM, 2>(rv, C.iceThickness, pf.x, pf.y, pf.z) * 0.5f + 0.8f), 0.1f) * 0.6f + 0.4f;
 		const float crack = 1 - powf(noise3_cellular<CD_HYBRID, CO_SUBTRACT, FT_FBM, 2>(rv, C.iceCracks, pf.x, pf.y, pf.z) * 0.5f + 0.5f, 0.3f);
@@ -574,8 +583,8 @@ namespace upg
 	// generateSnow (:819-855)
 	UPG_LAYER void generate_snow(const ColoringConsts &C, Tile &t)
 	{
-		float bf = sharp_edge(range_mask(t.elevation + noise3<NT_VALUE, FT_NONE, 3>(C.snowElevOffset, t.position) * 20, 220, 240) * steepness_mask(t.slope, 25, 5));
-		const float thickness = noise3<NT_CUBIC, FT_FBM, 3>(C.snowThickness, t.position) * 0.5f + 0.5f;
+		float bf = sharp_edge(range_mask(t.elevation + noise3<NT_VALUE, FT_NONE, 3, true>(C.snowElevOffset, t.position) * 20, 220, 240) * steepness_mask(t.slope, 25, 5));
+		const float thickness = noise3<NT_CUBIC, FT_FBM, 3, true>(C.snowThickness, t.position) * 0.5f + 0.5f;
 		bf *= saturate_(thickness * 0.5f + 0.7f);
 		if (bf < 1e-7f)
 			return;

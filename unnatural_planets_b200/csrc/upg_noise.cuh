@@ -15,6 +15,15 @@
 
 #include "upg_common.cuh"
 
+// The octave loop of the fractal drivers is kept ROLLED by default: the bodies are hundreds of instructions each and the
+// unrolled kernels (130 KB of SASS for sphere+lakes) overflow the 32 KB L1.5 instruction cache, which shows up as
+// "no_instruction" issue stalls (profiles/).  -DUPG_UNROLL_OCTAVES restores full unrolling for A/B measurements.
+#if defined(UPG_UNROLL_OCTAVES)
+#define UPG_OCTAVE_LOOP _Pragma("unroll")
+#else
+#define UPG_OCTAVE_LOOP _Pragma("unroll 1")
+#endif
+
 namespace upg
 {
 	// values follow cage's enums (include/cage-core/noiseFunction.h:8-43)
@@ -415,9 +424,11 @@ namespace upg
 		int32_t xp = imul(xr - 1, PRIME_X);
 		const int32_t ypBase = imul(yr - 1, PRIME_Y);
 		const int32_t zpBase = imul(zr - 1, PRIME_Z);
+#pragma unroll 1
 		for (int32_t xi = xr - 1; xi <= xr + 1; xi++)
 		{
 			int32_t yp = ypBase;
+#pragma unroll 1
 			for (int32_t yi = yr - 1; yi <= yr + 1; yi++)
 			{
 				int32_t zp = zpBase;
@@ -492,6 +503,26 @@ namespace upg
 		return single_value(seed, x, y, z);
 	}
 
+	// The same generators as real (non-inlined) functions.  The colouring kernel calls ~40 noise instances from 13 layers;
+	// inlining every octave of every call site made it 49 k SASS instructions (784 KB), 25x the L1.5 instruction cache, and
+	// ncu showed the warps waiting for instruction fetch ("no_instruction") most of the time.  One body per generator keeps the
+	// hot code resident.  Templates have vague linkage, so there is one copy per library, and none where unused.
+#if defined(__CUDACC__)
+#define UPG_OUTLINED __host__ __device__ __noinline__
+#else
+#define UPG_OUTLINED inline
+#endif
+	template<int TYPE>
+	UPG_OUTLINED float noise_single_outlined(int32_t seed, float x, float y, float z)
+	{
+		return noise_single<TYPE>(seed, x, y, z);
+	}
+	template<int DIST, int OP>
+	UPG_OUTLINED float single_cellular_outlined(const float *rv, int32_t seed, float x, float y, float z)
+	{
+		return single_cellular<DIST, OP>(rv, seed, x, y, z);
+	}
+
 	UPG_HD float ping_pong(float t)
 	{
 		t -= (float)((int32_t)(t * 0.5f) * 2);
@@ -510,7 +541,7 @@ namespace upg
 
 	// GetNoise(x, y, z): frequency scale, domain rotation for the two simplex kinds, fractal loop.
 	// weighted strength stays at the library default 0 (cage never sets it) => amp *= lerp(1, ., 0) == amp.
-	template<int TYPE, int FRACTAL, int OCTAVES>
+	template<int TYPE, int FRACTAL, int OCTAVES, bool OUTLINED = false>
 	UPG_HD float noise3(const NoiseInst &n, float x, float y, float z)
 	{
 		x *= n.frequency;
@@ -525,14 +556,14 @@ namespace upg
 			z = r - z;
 		}
 		if (FRACTAL == FT_NONE)
-			return noise_single<TYPE>(n.seed, x, y, z);
+			return OUTLINED ? noise_single_outlined<TYPE>(n.seed, x, y, z) : noise_single<TYPE>(n.seed, x, y, z);
 		int32_t seed = n.seed;
 		float sum = 0;
 		float amp = n.bounding;
-#pragma unroll
+		UPG_OCTAVE_LOOP
 		for (int o = 0; o < OCTAVES; o++)
 		{
-			const float v = noise_single<TYPE>(seed, x, y, z);
+			const float v = OUTLINED ? noise_single_outlined<TYPE>(seed, x, y, z) : noise_single<TYPE>(seed, x, y, z);
 			seed = iadd(seed, 1);
 			sum += fractal_term<FRACTAL>(v) * amp;
 			x *= n.lacunarity;
@@ -543,10 +574,10 @@ namespace upg
 		return sum;
 	}
 
-	template<int TYPE, int FRACTAL, int OCTAVES>
+	template<int TYPE, int FRACTAL, int OCTAVES, bool OUTLINED = false>
 	UPG_HD float noise3(const NoiseInst &n, V3 p)
 	{
-		return noise3<TYPE, FRACTAL, OCTAVES>(n, p.x, p.y, p.z);
+		return noise3<TYPE, FRACTAL, OCTAVES, OUTLINED>(n, p.x, p.y, p.z);
 	}
 
 	// cellular variant (needs the jitter table and the distance / return kind)
@@ -557,13 +588,14 @@ namespace upg
 		y *= n.frequency;
 		z *= n.frequency;
 		if (FRACTAL == FT_NONE)
-			return single_cellular<DIST, OP>(rv, n.seed, x, y, z);
+			return single_cellular_outlined<DIST, OP>(rv, n.seed, x, y, z);
 		int32_t seed = n.seed;
 		float sum = 0;
 		float amp = n.bounding;
+#pragma unroll 1
 		for (int o = 0; o < OCTAVES; o++)
 		{
-			const float v = single_cellular<DIST, OP>(rv, seed, x, y, z);
+			const float v = single_cellular_outlined<DIST, OP>(rv, seed, x, y, z);
 			seed = iadd(seed, 1);
 			sum += fractal_term<FRACTAL>(v) * amp;
 			x *= n.lacunarity;
