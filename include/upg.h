@@ -143,6 +143,18 @@ typedef struct upg_mesh
  * UPG_ERR_EMPTY_MESH when no triangle results (the reference throws "generated empty base land mesh", :51-52). */
 int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out);
 
+/*
+ * Multi-GPU sharding of K1 + K2..K4 by z-slab ("grid sampling shards naturally by z-slab").  dualmc's scan over z in [0, res-2)
+ * (dualmc.tpp:401) is split into `slab_count` contiguous ranges (upg_slab_range); slab k samples its slices plus a 3-slice halo on
+ * each side ON ITS OWN DEVICE (recomputed, not exchanged) and returns the quads / triangles its scan iterations emit and the
+ * vertices they create.  Vertex ids in `indices` / `dmc_quads` are RELATIVE to the slab's first vertex, as two's-complement
+ * uint32 (ids below zero refer to the last vertices of slab k-1): add the total vertex_count of slabs 0..k-1 (mod 2^32) and
+ * concatenate the arrays of all slabs in order -- the result is bit-identical to upg_field_mesh on one device, with the
+ * reference's vertex / quad / triangle order.  The only exchange a multi-GPU caller needs is that count and the final gather.
+ */
+void upg_slab_range(int grid_resolution, int slab, int slab_count, int *z0, int *z1);
+int upg_field_mesh_slab(upg_planet *planet, int field, int slab, int slab_count, upg_mesh *out);
+
 /* K2..K4 alone over caller-provided samples (host memory, layout [z][y][x]): MarchingCubes::densities(values) followed by
  * makeMesh() (include/cage-core/marchingCubes.h:16,27).  `full_resolution` / `box_size` define the grid -> world mapping
  * (MarchingCubesCreateConfig::position); pass rx = ry = rz = full_resolution for a whole grid. */

@@ -84,3 +84,25 @@ def test_default_size_sphere_properties():
     assert cosang.min() > 0.95
     # every quad index is valid and every vertex is used
     assert np.array_equal(np.unique(m["dmc_quads"]), np.arange(nv))
+
+
+# ---- z-slab sharding (BASELINE north_star: "grid sampling shards naturally by z-slab across the GPUs") -------------------------
+@pytest.mark.parametrize("shape,elev,res", [("sphere", "lakes", 64), ("torus", "craters", 48), ("mandelbulb", "none", 40), ("gear", "simple", 37)])
+@pytest.mark.parametrize("slabs", [1, 2, 3, 8, 64])
+def test_slab_extraction_stitches_to_the_whole_mesh(shape, elev, res, slabs):
+    # every slab samples its own slices (+3 halo) and extracts its own share; concatenated with the vertex bases added, the
+    # result is the single-device mesh BIT FOR BIT, in the reference's vertex / quad / triangle order
+    from unnatural_planets_b200 import slab_range, stitch_slabs
+
+    p = Planet(shape=shape, elevation=elev, grid=res)
+    whole = p.field_mesh("land")
+    parts = [p.field_mesh_slab("land", k, slabs) for k in range(slabs)]
+    ranges = [slab_range(res, k, slabs) for k in range(slabs)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == res - 2 and all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:]))
+    got = stitch_slabs(parts)
+    for k in ("positions", "normals", "dmc_vertices", "indices", "dmc_quads"):
+        assert got[k].shape == whole[k].shape, (k, got[k].shape, whole[k].shape)
+        assert (got[k].view(np.uint32) == whole[k].view(np.uint32)).all(), k
+    if shape == "sphere" and 1 < slabs < res:
+        # interior slabs do reference vertices of their lower neighbour (negative relative ids)
+        assert any((s["indices"].view(np.int32) < 0).any() for s in parts[1:] if len(s["indices"]))

@@ -100,6 +100,9 @@ def load_library():
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
     L.upg_field_mesh.argtypes = [vp, i32, C.POINTER(Mesh)]
+    L.upg_field_mesh_slab.argtypes = [vp, i32, i32, i32, C.POINTER(Mesh)]
+    L.upg_slab_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.upg_slab_range.restype = None
     L.upg_isosurface.argtypes = [fp, i32, i32, i32, C.c_float, i32, i32, C.POINTER(Mesh)]
     L.upg_mesh_free.argtypes = [C.POINTER(Mesh)]
     L.upg_mesh_free.restype = None

@@ -44,6 +44,7 @@ namespace upg
 		struct Dims
 		{
 			int32_t rx, ry, rz; // samples per axis
+			int32_t z0; // global z index of local slice 0 (slab extraction; 0 for a whole volume)
 			__host__ __device__ int32_t cx() const { return rx - 1; } // cells per axis
 			__host__ __device__ int32_t cy() const { return ry - 1; }
 			__host__ __device__ int32_t cz() const { return rz - 1; }
@@ -383,7 +384,7 @@ namespace upg
 			px *= inv;
 			py *= inv;
 			pz *= inv;
-			return v3((float)cx + px, (float)cy + py, (float)cz + pz);
+			return v3((float)cx + px, (float)cy + py, (float)(cz + d.z0) + pz); // the GLOBAL cell origin enters the sum (slabs)
 		}
 
 		struct WorldMap
@@ -569,6 +570,41 @@ namespace upg
 			normals[v * 3 + 2] = acc.z;
 		}
 
+		// slab extraction: the quads anchored at local z in [lo, hi) form one contiguous block of the ordered quad list; vertices
+		// are numbered in creation (= scan) order and triangles follow their quads, so the same holds for both.
+		// out = { firstQuad, endQuad, firstVertex, endVertex, firstTriangle, endTriangle }
+		__global__ void dmc_owned_ranges(Dims d, const uint32_t *__restrict__ quadCell, uint32_t nQuads, const uint32_t *__restrict__ vids, uint32_t nVerts, const uint32_t *__restrict__ triOffset, uint32_t nTris, int32_t lo, int32_t hi, uint32_t *__restrict__ out)
+		{
+			if (threadIdx.x != 0 || blockIdx.x != 0)
+				return;
+			const uint64_t perSlice = (uint64_t)d.cx() * d.cy();
+			for (int k = 0; k < 2; k++)
+			{
+				const int32_t z = k == 0 ? lo : hi;
+				const uint64_t key = z <= 0 ? 0 : (uint64_t)z * perSlice; // first cell index of slice z
+				uint32_t a = 0, b = nQuads;
+				while (a < b)
+				{
+					const uint32_t m = a + (b - a) / 2;
+					if ((uint64_t)quadCell[m] < key)
+						a = m + 1;
+					else
+						b = m;
+				}
+				out[k] = a;
+				out[2 + k] = a < nQuads ? vids[a * 4] : nVerts;
+				out[4 + k] = a < nQuads ? triOffset[a] : nTris;
+			}
+		}
+
+		// vertex ids relative to the first owned vertex (two's complement: ids below it belong to the previous slab)
+		__global__ void __launch_bounds__(DMC_BLOCK) dmc_rebase(uint32_t *__restrict__ ids, uint64_t n, uint32_t first)
+		{
+			const uint64_t i = (uint64_t)blockIdx.x * DMC_BLOCK + threadIdx.x;
+			if (i < n)
+				ids[i] -= first;
+		}
+
 		template<class T>
 		cudaError_t dalloc(T **p, uint64_t count, cudaStream_t s)
 		{
@@ -610,10 +646,10 @@ namespace upg
 
 	// Everything on `s`; the caller owns `dens` (rx*ry*rz floats on the device).  Outputs are device arrays allocated
 	// with cudaMallocAsync on `s` (released by dmc_release).
-	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out)
+	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset, int ownZ0, int ownZ1)
 	{
 		out = DmcResult();
-		const Dims d{ rx, ry, rz };
+		const Dims d{ rx, ry, rz, zOffset };
 		if (rx <= 2 || ry <= 2 || rz <= 2)
 			return fail(UPG_ERR_ARGUMENT, "volume too small for dual marching cubes");
 		const uint64_t cells = d.cells();
@@ -738,6 +774,42 @@ namespace upg
 				out.quads = quadFinal; // dualmc's quads, in emitted order
 				quadFinal = nullptr;
 			}
+			// slab: keep the blocks owned by scan iterations [ownZ0, ownZ1) (global z), ids relative to the first owned vertex
+			if (e == cudaSuccess && (ownZ0 > zOffset || ownZ1 < zOffset + rz))
+			{
+				uint32_t *ranges = nullptr;
+				uint32_t h[6] = { 0, 0, 0, 0, 0, 0 };
+				UPG_TRY(dalloc(&ranges, 6, s));
+				if (e == cudaSuccess)
+				{
+					dmc_owned_ranges<<<1, 1, 0, s>>>(d, quadCell, nQuads, vids, nVerts, triOffset, nTris, ownZ0 - zOffset, ownZ1 - zOffset, ranges);
+					UPG_LAUNCHED();
+				}
+				UPG_TRY(cudaMemcpyAsync(h, ranges, sizeof(h), cudaMemcpyDeviceToHost, s));
+				UPG_TRY(cudaStreamSynchronize(s));
+				if (ranges)
+					cudaFreeAsync(ranges, s);
+				if (e == cudaSuccess)
+				{
+					out.firstQuad = h[0];
+					out.ownedQuads = h[1] - h[0];
+					out.firstVertex = h[2];
+					out.ownedVertices = h[3] - h[2];
+					out.firstTriangle = h[4];
+					out.ownedTriangles = h[5] - h[4];
+					out.slab = true;
+					if (out.ownedQuads)
+					{
+						dmc_rebase<<<(out.ownedQuads * 4 + DMC_BLOCK - 1) / DMC_BLOCK, DMC_BLOCK, 0, s>>>(out.quads + (uint64_t)out.firstQuad * 4, (uint64_t)out.ownedQuads * 4, out.firstVertex);
+						UPG_LAUNCHED();
+					}
+					if (out.ownedTriangles)
+					{
+						dmc_rebase<<<(out.ownedTriangles * 3 + DMC_BLOCK - 1) / DMC_BLOCK, DMC_BLOCK, 0, s>>>(out.indices + (uint64_t)out.firstTriangle * 3, (uint64_t)out.ownedTriangles * 3, out.firstVertex);
+						UPG_LAUNCHED();
+					}
+				}
+			}
 		}
 #undef UPG_TRY
 #undef UPG_LAUNCHED
@@ -745,6 +817,12 @@ namespace upg
 		out.vertexCount = nVerts;
 		out.quadCount = nQuads;
 		out.triangleCount = nTris;
+		if (!out.slab)
+		{
+			out.ownedVertices = nVerts;
+			out.ownedQuads = nQuads;
+			out.ownedTriangles = nTris;
+		}
 
 		void *scratch[] = { codes, blockQuads, blockOffsets, quadBase, nearZero, quadCell, quadInfo, flags, vids, vertCell, vertCode, quadFinal, triInfo, faceN, triCount, triOffset };
 		for (void *p : scratch)

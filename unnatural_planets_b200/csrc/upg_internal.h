@@ -60,9 +60,15 @@ namespace upg
 		uint32_t *indices = nullptr; // 3 per triangle
 		uint32_t *quads = nullptr; // 4 per quad: dualmc's own output, before the triangle split
 		uint32_t vertexCount = 0, quadCount = 0, triangleCount = 0;
+		// slab extraction (dmc_extract with an owned z range): the blocks of the arrays above that belong to the slab; `quads`
+		// and `indices` of those blocks hold vertex ids relative to firstVertex (two's complement)
+		bool slab = false;
+		uint32_t firstVertex = 0, ownedVertices = 0, firstQuad = 0, ownedQuads = 0, firstTriangle = 0, ownedTriangles = 0;
 		uint64_t nearZeroSamples = 0; // samples with |value| < 1e-3: where topology parity is not promised
 	};
-	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out);
+	// zOffset: global z of local slice 0; [ownZ0, ownZ1): global scan iterations (dualmc's z loop) whose quads / created vertices /
+	// triangles are reported (defaults = the whole volume)
+	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset = 0, int ownZ0 = 0, int ownZ1 = 0x7fffffff);
 	void dmc_release(DmcResult &r, cudaStream_t s);
 
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);

@@ -50,6 +50,22 @@ def isosurface(samples, box=4000.0, full_res=None, device=0):
     return _mesh_to_numpy(L, m)
 
 
+def slab_range(res, slab, slab_count):
+    z0, z1 = C.c_int(0), C.c_int(0)
+    capi.load_library().upg_slab_range(res, slab, slab_count, C.byref(z0), C.byref(z1))
+    return z0.value, z1.value
+
+
+def stitch_slabs(slabs):
+    """concatenates field_mesh_slab() results of slabs 0..n-1: adds each slab's vertex base to its relative ids (mod 2^32)"""
+    base = np.cumsum([0] + [len(s["positions"]) for s in slabs])
+    out = {k: np.concatenate([s[k] for s in slabs]) for k in ("positions", "normals", "dmc_vertices")}
+    out["indices"] = np.concatenate([s["indices"] + np.uint32(b) for s, b in zip(slabs, base)])
+    out["dmc_quads"] = np.concatenate([s["dmc_quads"] + np.uint32(b) for s, b in zip(slabs, base)])
+    out["near_zero_samples"] = sum(s["near_zero_samples"] for s in slabs)
+    return out
+
+
 def raster(uv, idx, w, h, device=0):
     """K5 alone (upg_raster): owner image (0xffffffff = uncovered), barycentric weights of the winning visit, visit count."""
     L = capi.load_library()
@@ -131,6 +147,13 @@ class Planet:
         """meshGenerateGeneric up to makeMesh's normals (upg_field_mesh) -> dict of numpy arrays."""
         m = capi.Mesh()
         capi.check(self._lib.upg_field_mesh(self._h, capi.FIELDS[field], C.byref(m)))
+        return _mesh_to_numpy(self._lib, m)
+
+    def field_mesh_slab(self, field, slab, slab_count):
+        """slab `slab` of `slab_count` of field_mesh() (upg_field_mesh_slab): indices / dmc_quads are relative to the slab's
+        first vertex (uint32, two's complement); see stitch_slabs()."""
+        m = capi.Mesh()
+        capi.check(self._lib.upg_field_mesh_slab(self._h, capi.FIELDS[field], slab, slab_count, C.byref(m)))
         return _mesh_to_numpy(self._lib, m)
 
     def field_points(self, field, positions):
