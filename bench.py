@@ -35,6 +35,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_STDOUT = sys.stdout
 METRIC = "sdf_samples_per_s"
 UNIT = "samples/s"
 FIELDS = ("land", "water", "navigation")
@@ -176,10 +177,10 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
-def bench_mesh(planet, texture):
+def bench_mesh(raw):
     """the land and water surfaces of the planet with synthetic texture coordinates (see unnatural_planets_b200/synth.py)"""
     import numpy as np
 
@@ -187,7 +188,7 @@ def bench_mesh(planet, texture):
 
     out = {}
     for name in ("land", "water"):
-        m = planet.field_mesh(name)
+        m = raw[name]
         uv = synth.octahedral_uv(m["positions"])
         idx = synth.drop_folded_triangles(uv, m["indices"])
         # meshFlipNormals (sources/meshGeneration.cpp:42): the generator bakes the flipped mesh
@@ -265,17 +266,17 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.empty_cache()
 
     # ---- leg 2: isosurface (sampling + K2..K4 + download, through the C ABI) -------------------------------------------
+    planet.field_mesh("land")  # warm the memory pool like a second planet of a batch would find it
+    barrier()
     t = time.perf_counter()
-    meshes = bench_mesh(planet, tex)  # land + water; also the input of the bake
-    mesh_s_two = time.perf_counter() - t
-    t = time.perf_counter()
-    nav = planet.field_mesh("navigation")
-    mesh_s = mesh_s_two + (time.perf_counter() - t)  # includes the host-side synthetic UVs of two meshes (numpy, ~0.1 s)
+    raw = {f: planet.field_mesh(f) for f in FIELDS}
+    mesh_s = time.perf_counter() - t
     t = time.perf_counter()
     m2 = planet.field_mesh("land")
     field_mesh_land_s = time.perf_counter() - t
-    mesh_stats = {"land_vertices": int(len(m2["positions"])), "land_triangles": int(len(m2["indices"]) // 3), "navigation_triangles": int(len(nav["indices"]) // 3), "near_zero_samples": m2["near_zero_samples"]}
-    del nav, m2
+    mesh_stats = {"land_vertices": int(len(m2["positions"])), "land_triangles": int(len(m2["indices"]) // 3), "navigation_triangles": int(len(raw["navigation"]["indices"]) // 3), "near_zero_samples": m2["near_zero_samples"]}
+    meshes = bench_mesh(raw)  # synthetic UVs (host numpy, outside every timing); the input of the bake
+    del raw, m2
 
     # ---- leg 3: texel baking -------------------------------------------------------------------------------------------
     dmesh = {}
@@ -332,6 +333,62 @@ def run_ours(args, rank, world, local_rank):
     h2d_bake = sum(a.nbytes for m in meshes.values() for a in m)
     d2h_bake = tex * tex * (3 + 2 + 1 + 4 + 2 + 1)
 
+    # ---- leg 4: ONE planet sharded over all ranks (BASELINE configs[4] shape: z-slab sampling + extraction, row-tile bake) ----
+    sharded_line = None
+    if args.sharded_grid > 0:
+        from unnatural_planets_b200 import sharded as sh
+
+        del dmesh, outs
+        torch.cuda.empty_cache()
+        sp = sh.ShardedPlanet(device=local_rank, shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=args.sharded_grid)
+        stex = args.sharded_texture
+        sh.gather_varlen(np.zeros(4, dtype=np.float32), dst=0)  # opens NCCL's point-to-point channels outside the timing
+        barrier()
+        t = time.perf_counter()
+        smeshes, phases = {}, {}
+        for f in FIELDS:
+            smeshes[f] = sp.field_mesh(f, dst=0)
+            phases["mesh_" + f] = sp.timing
+        barrier()
+        t_mesh = time.perf_counter() - t
+        # the bake input lives on rank 0 after the gather: broadcast it (a few tens of MB) like the generator would hand every
+        # device the chunk mesh; the synthetic UVs are host work outside the timing
+        src = None
+        if rank == 0:
+            from unnatural_planets_b200 import synth
+
+            src = {}
+            for name in ("land", "water"):
+                m = smeshes[name]
+                uv = synth.octahedral_uv(m["positions"])
+                src[name] = [m["positions"], np.ascontiguousarray(-m["normals"]), uv, synth.drop_folded_triangles(uv, m["indices"])]
+        if world > 1:
+            box = [src]
+            dist.broadcast_object_list(box, src=0)
+            src = box[0]
+        barrier()
+        t = time.perf_counter()
+        stexels = 0
+        for name, water in (("land", 0), ("water", 1)):
+            sp.bake(water, *src[name], stex, stex, dst=0)
+            phases["bake_" + name] = sp.timing
+            stexels += sp.last_covered_texels
+        barrier()
+        t_bake = time.perf_counter() - t
+        st = torch.tensor([t_mesh, t_bake], dtype=torch.float64, device=dev)
+        sc = torch.tensor([float(stexels)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            sharded_line = {
+                "what": "ONE planet over %d GPU(s), strong scaling: 3 x upg_field_mesh_slab (own z-slab + 3-slice recomputed halo, extraction, download) + count all_gather + gather of the mesh chunks to rank 0; then 2 x upg_bake_rows (own rows + 7-row apron) + gather of the row tiles; wall clock, max over ranks" % world,
+                "grid": args.sharded_grid, "texture": stex, "isosurface_ms": float(st[0]) * 1e3, "bake_ms": float(st[1]) * 1e3,
+                "samples_per_s": 3.0 * args.sharded_grid**3 / float(st[0]), "texels_per_s": float(sc[0]) / float(st[1]),
+                "land_triangles": int(len(smeshes["land"]["indices"]) // 3), "covered_texels": int(sc[0]), "rank0_phases_ms": phases,
+            }
+        del smeshes, src
+
     texels = covered["land"] + covered["water"]
     times = torch.tensor([ms_total, e2e_s * 1e3, bake_ms, bake_e2e_s * 1e3, mesh_s * 1e3], dtype=torch.float64, device=dev)
     counts = torch.tensor([float(texels)], dtype=torch.float64, device=dev)
@@ -363,13 +420,13 @@ def run_ours(args, rank, world, local_rank):
         "metric": "baked_texels_per_s", "value": texels_all / (bake_ms_max * 1e-3), "unit": "texels/s", "steps": bake_steps, "ms_per_step": bake_ms_max,
         "texels_per_step": int(texels_all), "covered": {k: int(v) for k, v in covered.items()}, "texture": [tex, tex],
         "note": "texels = covered texels (one terrainTile each; the reference evaluates every (triangle, texel) visit) of the land (3+2+1 ch) and water (4+2+1 ch) surfaces; UVs: synthetic octahedral chart",
-        "e2e": {"value": texels_all / world / (bake_e2e_ms * 1e-3) * world, "unit": "texels/s", "h2d_bytes_per_step": int(h2d_bake), "d2h_bytes_per_step": int(d2h_bake), "path": "upg_bake: host mesh -> device, pinned host images <- device, wall clock"},
+        "e2e": {"value": texels_all / (bake_e2e_ms * 1e-3), "unit": "texels/s", "h2d_bytes_per_step": int(h2d_bake), "d2h_bytes_per_step": int(d2h_bake), "path": "upg_bake: host mesh -> device, pinned host images <- device, wall clock"},
         "roofline": {"bound": "fp32", "kernel": "tile_color_kernel<default> + its K1 probes (land bake, whole upg_bake_device call)", "achieved": bake_achieved, "peak": peak, "unit": "TFLOP/s", "frac": bake_achieved / peak if peak else None, "traffic": None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": FLOPS_PER_TEXEL_LAND},
     }
     planet_ms = mesh_ms + bake_e2e_ms
     planet_line = {
         "ms": planet_ms, "isosurface_ms": mesh_ms, "bake_ms": bake_e2e_ms, "field_mesh_land_ms": field_mesh_land_s * 1e3,
-        "what": "3 x upg_field_mesh (sampling + Dual Marching Cubes + mesh download; incl. ~0.1 s of host numpy for the synthetic UVs) + 2 x upg_bake, host buffers, wall clock", "mesh": mesh_stats,
+        "what": "3 x upg_field_mesh (sampling + Dual Marching Cubes + mesh download) + 2 x upg_bake, host buffers, wall clock", "mesh": mesh_stats,
     }
 
     threads = os.cpu_count() or 1
@@ -398,9 +455,10 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "texel_bake": texel_bake,
         "planet": planet_line,
+        "sharded_planet": sharded_line,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 def fp32_peak(capi, device):
@@ -419,10 +477,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=1000, help="samples per axis of the meshing grid (BASELINE configs[2]: 1000)")
     ap.add_argument("--texture", type=int, default=4096, help="bake resolution (BASELINE configs[2]: 4096)")
+    ap.add_argument("--sharded-grid", type=int, default=1024, help="grid of the one-planet-over-all-ranks leg (BASELINE configs[4]: 1024; 0 = skip)")
+    ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner does) are sent to stderr
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -430,6 +495,7 @@ def main():
         import torch
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:

@@ -136,6 +136,7 @@ typedef struct upg_mesh
 	uint32_t reserved;
 	uint64_t near_zero_samples; /* samples with |value| < 1e-3: where sign / topology parity with a CPU run is not promised */
 	void *owner; /* internal */
+	uint64_t owner_bytes; /* internal */
 } upg_mesh;
 
 /* K1 + K2..K4.  Replaces the body of meshGenerateGeneric<FNC>() up to makeMesh's normals (sources/meshGeneration.cpp:32-40):

@@ -264,3 +264,21 @@ def test_bake_is_deterministic_and_reentrant():
     [t.join() for t in ts]
     for a, b in zip(serial, out):
         assert all((x == y).all() for x, y in zip(a, b))
+
+
+def test_sharded_planet_single_rank_equals_planet():
+    # unnatural_planets_b200/sharded.py with a group of one (no process group): the collective wrappers reduce to the plain calls;
+    # the bake goes through upg_bake_device (device mesh, device images)
+    from unnatural_planets_b200.sharded import ShardedPlanet
+
+    cfg = ("sphere", "lakes", "default", True, True)
+    s, e, c, po, f = cfg
+    sp = ShardedPlanet(device=0, shape=s, elevation=e, coloring=c, poles=po, flowers=f, grid=48)
+    p = make_planet(cfg, grid=48)
+    a, b = sp.field_mesh("land"), p.field_mesh("land")
+    for k in ("positions", "normals", "indices", "dmc_quads"):
+        assert (a[k].view(np.uint32) == b[k].view(np.uint32)).all(), k
+    pos, nrm, uv, idx = bc.atlas_mesh()
+    got = sp.bake(0, pos, nrm, uv, idx, 192, 192)
+    want = p.bake(0, pos, nrm, uv, idx, 192, 192)
+    assert all((g.cpu().numpy() == w).all() for g, w in zip(got, want))

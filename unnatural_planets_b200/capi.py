@@ -43,6 +43,7 @@ class Mesh(C.Structure):
         ("reserved", C.c_uint32),
         ("near_zero_samples", C.c_uint64),
         ("owner", C.c_void_p),
+        ("owner_bytes", C.c_uint64),
     ]
 
 

@@ -4,6 +4,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -429,6 +431,70 @@ extern "C"
 // ---- isosurface entry points ------------------------------------------------------------------------------------
 namespace upg
 {
+	// Pinned host blocks are expensive to create (cudaMallocHost of ~100 MB costs tens of milliseconds, more than the sampling
+	// of a 500^3 field), and the generator asks for one mesh after another: blocks handed back by upg_mesh_free are kept
+	// (up to 1 GiB in total) and reused for the next mesh of a similar size.
+	namespace
+	{
+		struct PinnedBlock
+		{
+			void *ptr;
+			size_t bytes;
+		};
+		std::mutex g_pinnedMutex;
+		PinnedBlock g_pinnedFree[16];
+		int g_pinnedCount = 0;
+		size_t g_pinnedBytes = 0;
+
+		cudaError_t pinned_acquire(size_t bytes, void **out, size_t *capacity)
+		{
+			{
+				std::lock_guard<std::mutex> lock(g_pinnedMutex);
+				int best = -1;
+				for (int i = 0; i < g_pinnedCount; i++)
+					if (g_pinnedFree[i].bytes >= bytes && g_pinnedFree[i].bytes <= bytes * 2 + (1u << 20) && (best < 0 || g_pinnedFree[i].bytes < g_pinnedFree[best].bytes))
+						best = i;
+				if (best >= 0)
+				{
+					*out = g_pinnedFree[best].ptr;
+					*capacity = g_pinnedFree[best].bytes;
+					g_pinnedBytes -= g_pinnedFree[best].bytes;
+					g_pinnedFree[best] = g_pinnedFree[--g_pinnedCount];
+					return cudaSuccess;
+				}
+			}
+			*capacity = bytes;
+			return cudaMallocHost(out, bytes);
+		}
+
+		void pinned_release(void *ptr, size_t bytes)
+		{
+			{
+				std::lock_guard<std::mutex> lock(g_pinnedMutex);
+				if (g_pinnedCount < 16 && g_pinnedBytes + bytes <= ((size_t)1 << 30))
+				{
+					g_pinnedFree[g_pinnedCount++] = PinnedBlock{ ptr, bytes };
+					g_pinnedBytes += bytes;
+					return;
+				}
+			}
+			cudaFreeHost(ptr);
+		}
+
+		// UPG_TRACE=1: wall-clock phases of the host-buffer entry points on stderr (profiling aid)
+		bool trace_enabled()
+		{
+			static const bool on = std::getenv("UPG_TRACE") != nullptr;
+			return on;
+		}
+		double now_ms()
+		{
+			timespec ts;
+			clock_gettime(CLOCK_MONOTONIC, &ts);
+			return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+		}
+	}
+
 	// copies a device-side DmcResult into one pinned host block and fills the ABI struct
 	static int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
 	{
@@ -437,7 +503,8 @@ namespace upg
 		const uint64_t v0 = (uint64_t)r.firstVertex * 3, q0 = (uint64_t)r.firstQuad * 4, i0 = (uint64_t)r.firstTriangle * 3;
 		const uint64_t bytes = sizeof(float) * nv * 9 + sizeof(uint32_t) * (ni + nq * 4);
 		char *block = nullptr;
-		cudaError_t e = cudaMallocHost((void **)&block, bytes ? bytes : 16);
+		size_t capacity = 0;
+		cudaError_t e = pinned_acquire(bytes ? bytes : 16, (void **)&block, &capacity);
 		if (e != cudaSuccess)
 			return cuda_fail(e, "cudaMallocHost(mesh)");
 		char *p = block;
@@ -466,7 +533,7 @@ namespace upg
 			e = cudaStreamSynchronize(s);
 		if (e != cudaSuccess)
 		{
-			cudaFreeHost(block);
+			pinned_release(block, capacity);
 			std::memset(out, 0, sizeof(*out));
 			return cuda_fail(e, "mesh download");
 		}
@@ -476,6 +543,7 @@ namespace upg
 		out->reserved = 0;
 		out->near_zero_samples = r.nearZeroSamples;
 		out->owner = block;
+		out->owner_bytes = capacity;
 		return UPG_OK;
 	}
 }
@@ -498,6 +566,9 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		const bool trace = trace_enabled();
+		const double t0 = trace ? now_ms() : 0;
+		double t1 = 0, t2 = 0;
 		float *dens = nullptr;
 		e = cudaMallocAsync(&dens, sizeof(float) * (uint64_t)res * res * res, cs.compute);
 		if (e != cudaSuccess)
@@ -513,6 +584,11 @@ extern "C"
 			L.status = p->status;
 			rc = launch_field(p, L, cs.compute);
 		}
+		if (trace)
+		{
+			cudaStreamSynchronize(cs.compute);
+			t1 = now_ms();
+		}
 		DmcResult r;
 		if (rc == UPG_OK)
 			rc = dmc_extract(dens, res, res, res, p->boxSize, res, cs.compute, r);
@@ -520,8 +596,15 @@ extern "C"
 			rc = check_status(p, cs.compute, "upg_field_mesh");
 		if (rc == UPG_OK && r.triangleCount == 0)
 			rc = fail(UPG_ERR_EMPTY_MESH, "generated empty mesh");
+		if (trace)
+		{
+			cudaStreamSynchronize(cs.compute);
+			t2 = now_ms();
+		}
 		if (rc == UPG_OK)
 			rc = mesh_to_host(r, cs.compute, out);
+		if (trace)
+			std::fprintf(stderr, "[upg] field_mesh(%d) res %d: sample %.2f ms, extract %.2f ms, download %.2f ms (%u vertices, %u triangles)\n", field, res, t1 - t0, t2 - t1, now_ms() - t2, r.vertexCount, r.triangleCount);
 		dmc_release(r, cs.compute);
 		if (dens)
 			cudaFreeAsync(dens, cs.compute);
@@ -638,7 +721,7 @@ extern "C"
 		if (!mesh)
 			return;
 		if (mesh->owner)
-			cudaFreeHost(mesh->owner);
+			pinned_release(mesh->owner, (size_t)mesh->owner_bytes);
 		std::memset(mesh, 0, sizeof(*mesh));
 	}
 }
