@@ -283,17 +283,26 @@ namespace upg
 			uint32_t *status;
 		};
 
+#ifndef UPG_COLOR_BLOCK
+#define UPG_COLOR_BLOCK 768
+#endif
+#ifndef UPG_COLOR_BLOCKS_PER_SM
+#define UPG_COLOR_BLOCKS_PER_SM 1
+#endif
+		constexpr int COLOR_BLOCK = UPG_COLOR_BLOCK;
+
 		template<int COLORING>
-		__global__ void __launch_bounds__(BAKE_BLOCK) tile_color_kernel(const __grid_constant__ ColoringConsts C, const __grid_constant__ ColorArgs A)
+		__global__ void __launch_bounds__(COLOR_BLOCK, UPG_COLOR_BLOCKS_PER_SM) tile_color_kernel(const __grid_constant__ ColoringConsts C, const __grid_constant__ ColorArgs A)
 		{
 			// the jitter table is looked up with divergent indices: keep it in shared memory
 			__shared__ float rv[1024];
-			for (int k = threadIdx.x; k < 1024; k += BAKE_BLOCK)
+			for (int k = threadIdx.x; k < 1024; k += COLOR_BLOCK)
 				rv[k] = A.cellular[k];
 			__syncthreads();
-			const uint32_t i = blockIdx.x * BAKE_BLOCK + threadIdx.x;
-			if (i >= A.n)
-				return;
+			// threads past the end keep running (on the last tile) so that every thread reaches the barriers between layers
+			const uint32_t self = blockIdx.x * COLOR_BLOCK + threadIdx.x;
+			const bool live = self < A.n;
+			const uint32_t i = live ? self : A.n - 1;
 			const size_t n = A.n;
 			Tile t = tile_init(load3(A.probes, 8 * n + i), load3(A.normals, i), A.purpose);
 			// generateElevation (coloringModes.cpp:51-57)
@@ -306,6 +315,8 @@ namespace upg
 			if (isnan_(t.elevation) || isnan_(t.slope))
 				atomicOr(A.status, 1u); // "invalid elevation sdf value" (sources/modesConfiguration.cpp:233-234)
 			coloring_run<COLORING>(C, rv, t);
+			if (!live)
+				return;
 			if (A.tiles)
 			{
 				upg_tile &o = A.tiles[i];
@@ -661,17 +672,17 @@ namespace upg
 			A.n = n;
 			A.purpose = purpose;
 			A.status = p->status;
-			const unsigned blocks = blocks_for(n, BAKE_BLOCK);
+			const unsigned blocks = blocks_for(n, COLOR_BLOCK);
 			switch (p->params.coloring)
 			{
 				case CL_DEFAULT:
-					tile_color_kernel<CL_DEFAULT><<<blocks, BAKE_BLOCK, 0, s>>>(p->coloring, A);
+					tile_color_kernel<CL_DEFAULT><<<blocks, COLOR_BLOCK, 0, s>>>(p->coloring, A);
 					break;
 				case CL_BARREN:
-					tile_color_kernel<CL_BARREN><<<blocks, BAKE_BLOCK, 0, s>>>(p->coloring, A);
+					tile_color_kernel<CL_BARREN><<<blocks, COLOR_BLOCK, 0, s>>>(p->coloring, A);
 					break;
 				default:
-					tile_color_kernel<CL_DEBUG><<<blocks, BAKE_BLOCK, 0, s>>>(p->coloring, A);
+					tile_color_kernel<CL_DEBUG><<<blocks, COLOR_BLOCK, 0, s>>>(p->coloring, A);
 					break;
 			}
 			const cudaError_t e = cudaGetLastError();

@@ -22,6 +22,15 @@
 #include "upg_planet.h"
 #include "upg_terrain.cuh"
 
+// All warps of a colouring block run the same layer at the same time (a barrier between layers): the instruction stream of a
+// tile walks through ~180 KB of code, 6x the L1.5 instruction cache, and warps that drift apart each pay their own fetches
+// from L2 (ncu: `no_instruction` was the dominant stall, profiles/r01_d).  In step, one fetch feeds every warp of the SM.
+#if defined(__CUDA_ARCH__)
+#define UPG_LAYER_SYNC() __syncthreads()
+#else
+#define UPG_LAYER_SYNC() ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 // the layers are real (non-inlined) device functions: the colouring kernel stays a few thousand instructions per layer
 // instead of one giant inlined body; they only exist in the translation unit that launches the kernel
@@ -660,26 +669,40 @@ namespace upg
 	template<int COLORING>
 	UPG_COLORING void coloring_run(const ColoringConsts &C, const float *rv, Tile &t)
 	{
+		// t.purpose is uniform over a launch, so every thread of a block meets the same sequence of barriers
 		if (COLORING == CL_DEFAULT)
 		{
 			generate_precipitation(C, t);
+			UPG_LAYER_SYNC();
 			generate_temperature(C, t);
 			generate_biome(t);
 			generate_type(t);
+			UPG_LAYER_SYNC();
 			if (t.purpose == MP_WATER)
+			{
 				generate_water(C, t);
+			}
 			else
 			{
 				generate_bedrock(C, rv, t);
+				UPG_LAYER_SYNC();
 				generate_cliffs(C, t);
+				UPG_LAYER_SYNC();
 				generate_mica(C, rv, t);
+				UPG_LAYER_SYNC();
 				generate_dirt(C, t);
+				UPG_LAYER_SYNC();
 				generate_sand(C, t);
+				UPG_LAYER_SYNC();
 				generate_grass(C, rv, t);
+				UPG_LAYER_SYNC();
 				generate_boulders(C, t);
 			}
+			UPG_LAYER_SYNC();
 			generate_flowers(C, t);
+			UPG_LAYER_SYNC();
 			generate_ice(C, rv, t);
+			UPG_LAYER_SYNC();
 			if (t.purpose != MP_WATER)
 				generate_snow(C, t);
 			generate_finalization(t);
@@ -697,8 +720,11 @@ namespace upg
 				t.biome = BI_BARE;
 				t.type = TT_FLAT;
 				generate_bedrock(C, rv, t);
+				UPG_LAYER_SYNC();
 				generate_cliffs(C, t);
+				UPG_LAYER_SYNC();
 				generate_mica(C, rv, t);
+				UPG_LAYER_SYNC();
 				generate_boulders(C, t);
 			}
 			generate_finalization(t);
@@ -706,6 +732,7 @@ namespace upg
 		else
 		{
 			generate_precipitation(C, t);
+			UPG_LAYER_SYNC();
 			generate_temperature(C, t);
 			generate_biome(t);
 			generate_type(t);
