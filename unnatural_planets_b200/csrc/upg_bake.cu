@@ -298,6 +298,7 @@ namespace upg
 			__shared__ float rv[1024];
 			for (int k = threadIdx.x; k < 1024; k += COLOR_BLOCK)
 				rv[k] = A.cellular[k];
+			grad_table_init<COLOR_BLOCK>(); // gradient table of the Perlin / OpenSimplex generators (upg_noise.cuh)
 			__syncthreads();
 			// threads past the end keep running (on the last tile) so that every thread reaches the barriers between layers
 			const uint32_t self = blockIdx.x * COLOR_BLOCK + threadIdx.x;

@@ -53,6 +53,8 @@ namespace upg
 	template<int SHAPE, int ELEV>
 	__global__ void __launch_bounds__(FIELD_BLOCK) sdf_sample_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
 	{
+		grad_table_init<FIELD_BLOCK>(); // shared-memory gradient table of the Perlin / OpenSimplex generators (upg_noise.cuh)
+		__syncthreads();
 		const uint64_t idx = (uint64_t)blockIdx.x * FIELD_BLOCK + threadIdx.x;
 		if (idx >= L.count)
 			return;

@@ -83,34 +83,86 @@ namespace upg
 	UPG_HD int32_t lattice_hash(int32_t seed, int32_t xp, int32_t yp, int32_t zp) { return imul(seed ^ xp ^ yp ^ zp, 0x27d4eb2d); }
 	UPG_HD int32_t lattice_hash(int32_t seed, int32_t xp, int32_t yp) { return imul(seed ^ xp ^ yp, 0x27d4eb2d); }
 
-	UPG_HD float value_from_hash(int32_t h)
+	// Lattice value BEFORE the library's final scale by 2^-31.  The scale is a power of two, so it commutes exactly with every
+	// rounding of the interpolation that follows (no intermediate comes near the subnormal range: the unscaled corner values
+	// are integers): the generators below interpolate the unscaled values and apply VALUE_SCALE once at the end, which is
+	// bit-identical to scaling all 8 (Value) or 64 (ValueCubic) corners first and saves that many multiplies.
+	constexpr float VALUE_SCALE = 1.0f / 2147483648.0f;
+	UPG_HD float value_bits_from_hash(int32_t h)
 	{
 		h = imul(h, h);
 		h ^= ishl(h, 19);
-		return (float)h * (1.0f / 2147483648.0f);
+		return (float)h;
 	}
+	UPG_HD float value_from_hash(int32_t h) { return value_bits_from_hash(h) * VALUE_SCALE; }
 	UPG_HD float val_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp) { return value_from_hash(lattice_hash(seed, xp, yp, zp)); }
 	UPG_HD float val_coord(int32_t seed, int32_t xp, int32_t yp) { return value_from_hash(lattice_hash(seed, xp, yp)); }
 
 	// Gradient dot product.  The library indexes a 64-entry table of directions (the 12 cube-edge
-	// vectors five times over, then (1,1,0) (0,-1,1) (-1,1,0) (0,-1,-1)).  Every entry has one zero
-	// component and two +-1 components, so x*gx + y*gy + z*gz (evaluated left to right) is exactly
-	// (+-a) + (+-b) for two of the three offsets: selecting and sign-flipping reproduces the table
-	// result bit for bit without a divergent memory lookup.
+	// vectors five times over, then (1,1,0) (0,-1,1) (-1,1,0) (0,-1,-1)) with bits 2..7 of h ^ (h >> 15)
+	// and evaluates xd*gx + yd*gy + zd*gz left to right.
+	//
+	// Entry e: c = e % 12 (fillers 60..63 -> entries 8, 1, 9, 3); group c >> 2 says which component is
+	// zero, bits 0 and 1 of c are the signs of the two others.
+	UPG_HD void grad_entry(uint32_t e, float &gx, float &gy, float &gz)
+	{
+		const uint32_t c = e < 60u ? e % 12u : ((0x3918u >> ((e - 60u) * 4u)) & 15u);
+		const uint32_t grp = c >> 2; // 0: (0,s0,s1)  1: (s0,0,s1)  2: (s0,s1,0)
+		const float s0 = (c & 1u) ? -1.0f : 1.0f, s1 = (c & 2u) ? -1.0f : 1.0f;
+		gx = grp == 0u ? 0.0f : s0;
+		gy = grp == 0u ? s0 : grp == 1u ? 0.0f : s1;
+		gz = grp == 2u ? 0.0f : s1;
+	}
+
+	// Device form: decoding (group, signs, fillers) from the hash costs ~20 ALU-pipe instructions per lattice corner, and the
+	// ALU pipe (LOP3/SHF/ISETP/FSEL) is what bounds the sampling kernel (profiles/r01_a).  The table lives in shared memory
+	// instead: 64 entries x 8 copies of a float4, copy = lane & 7, so that the 8 lanes of every quarter-warp phase of an
+	// LDS.128 hit 8 different bank groups whatever their entries are (conflict free).  One SHF + LOP3 + IMAD + LDS.128, then
+	// three multiplies and two adds on the FMA pipe -- the very expression the library evaluates.
+	// Every kernel that evaluates gradient noise calls grad_table_init() (+ __syncthreads()) before its first sample.
+#if defined(__CUDACC__)
+	static __shared__ float4 upg_grad_lds[64 * 8];
+	// the 64 entries as literals (= grad_entry(e), checked by tests/test_host_terrain.py through the host build)
+	static __constant__ float4 upg_grad_const[64] = {
+		{ 0, 1, 1, 0 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { 0, -1, -1, 0 },
+		{ 1, 0, 1, 0 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 }, { -1, 0, -1, 0 },
+		{ 1, 1, 0, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { -1, -1, 0, 0 },
+		{ 0, 1, 1, 0 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { 0, -1, -1, 0 },
+		{ 1, 0, 1, 0 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 }, { -1, 0, -1, 0 },
+		{ 1, 1, 0, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { -1, -1, 0, 0 },
+		{ 0, 1, 1, 0 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { 0, -1, -1, 0 },
+		{ 1, 0, 1, 0 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 }, { -1, 0, -1, 0 },
+		{ 1, 1, 0, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { -1, -1, 0, 0 },
+		{ 0, 1, 1, 0 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { 0, -1, -1, 0 },
+		{ 1, 0, 1, 0 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 }, { -1, 0, -1, 0 },
+		{ 1, 1, 0, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { -1, -1, 0, 0 },
+		{ 0, 1, 1, 0 }, { 0, -1, 1, 0 }, { 0, 1, -1, 0 }, { 0, -1, -1, 0 },
+		{ 1, 0, 1, 0 }, { -1, 0, 1, 0 }, { 1, 0, -1, 0 }, { -1, 0, -1, 0 },
+		{ 1, 1, 0, 0 }, { -1, 1, 0, 0 }, { 1, -1, 0, 0 }, { -1, -1, 0, 0 },
+		{ 1, 1, 0, 0 }, { 0, -1, 1, 0 }, { -1, 1, 0, 0 }, { 0, -1, -1, 0 },
+	};
+#endif
+	template<int BLOCK_THREADS>
+	UPG_HD void grad_table_init()
+	{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+		for (uint32_t i = threadIdx.x; i < 64u * 8u; i += BLOCK_THREADS)
+			upg_grad_lds[i] = upg_grad_const[i >> 3];
+#endif
+	}
 	UPG_HD float grad_dot(int32_t h, float xd, float yd, float zd)
 	{
+#if defined(__CUDA_ARCH__)
+		const uint32_t t = ((uint32_t)h ^ ((uint32_t)(h >> 15))) & (63u << 2);
+		const float4 g = upg_grad_lds[t * 2u + (threadIdx.x & 7u)];
+		return (xd * g.x + yd * g.y) + zd * g.z;
+#else
 		h ^= h >> 15;
-		const uint32_t e = ((uint32_t)h >> 2) & 63u;
-		// e < 60: e % 12; fillers 60..63 -> entries 8, 1, 9, 3 of the 12
-		uint32_t c = e - 12u * ((e * 43u) >> 9);
-		if (e >= 60u)
-			c = (0x3918u >> ((e - 60u) * 4u)) & 15u;
-		const uint32_t grp = c >> 2; // 0: (0,s1,s2)  1: (s1,0,s2)  2: (s1,s2,0)
-		const float a = grp == 0u ? yd : xd;
-		const float b = grp == 2u ? yd : zd;
-		const float sa = (c & 1u) ? -a : a;
-		const float sb = (c & 2u) ? -b : b;
-		return sa + sb;
+		float gx, gy, gz;
+		grad_entry(((uint32_t)h >> 2) & 63u, gx, gy, gz);
+		return (xd * gx + yd * gy) + zd * gz;
+#endif
 	}
 	UPG_HD float grad_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) { return grad_dot(lattice_hash(seed, xp, yp, zp), xd, yd, zd); }
 
@@ -139,13 +191,14 @@ namespace upg
 		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y), z1 = iadd(z0, PRIME_Z);
 		// hoist the seed ^ y ^ z part of the eight hashes
 		const int32_t s00 = seed ^ y0 ^ z0, s10 = seed ^ y1 ^ z0, s01 = seed ^ y0 ^ z1, s11 = seed ^ y1 ^ z1;
-		const float xf00 = nlerp(value_from_hash(imul(s00 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s00 ^ x1, 0x27d4eb2d)), xs);
-		const float xf10 = nlerp(value_from_hash(imul(s10 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s10 ^ x1, 0x27d4eb2d)), xs);
-		const float xf01 = nlerp(value_from_hash(imul(s01 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s01 ^ x1, 0x27d4eb2d)), xs);
-		const float xf11 = nlerp(value_from_hash(imul(s11 ^ x0, 0x27d4eb2d)), value_from_hash(imul(s11 ^ x1, 0x27d4eb2d)), xs);
+		// unscaled corner values, one exact power-of-two scale at the end (see VALUE_SCALE)
+		const float xf00 = nlerp(value_bits_from_hash(imul(s00 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s00 ^ x1, 0x27d4eb2d)), xs);
+		const float xf10 = nlerp(value_bits_from_hash(imul(s10 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s10 ^ x1, 0x27d4eb2d)), xs);
+		const float xf01 = nlerp(value_bits_from_hash(imul(s01 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s01 ^ x1, 0x27d4eb2d)), xs);
+		const float xf11 = nlerp(value_bits_from_hash(imul(s11 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s11 ^ x1, 0x27d4eb2d)), xs);
 		const float yf0 = nlerp(xf00, xf10, ys);
 		const float yf1 = nlerp(xf01, xf11, ys);
-		return nlerp(yf0, yf1, zs);
+		return nlerp(yf0, yf1, zs) * VALUE_SCALE;
 	}
 
 	// 2-D value noise: what cage's evaluate(Real) reaches as GetNoise(x, 0) (noiseFunction.cpp:111-115)
@@ -202,13 +255,14 @@ namespace upg
 			for (int j = 0; j < 4; j++)
 			{
 				const int32_t s = seed ^ yp ^ zp;
-				yr[j] = cubic_lerp(value_from_hash(imul(s ^ xi0, 0x27d4eb2d)), value_from_hash(imul(s ^ x1, 0x27d4eb2d)), value_from_hash(imul(s ^ xi2, 0x27d4eb2d)), value_from_hash(imul(s ^ xi3, 0x27d4eb2d)), xs);
+				yr[j] = cubic_lerp(value_bits_from_hash(imul(s ^ xi0, 0x27d4eb2d)), value_bits_from_hash(imul(s ^ x1, 0x27d4eb2d)), value_bits_from_hash(imul(s ^ xi2, 0x27d4eb2d)), value_bits_from_hash(imul(s ^ xi3, 0x27d4eb2d)), xs);
 				yp = iadd(yp, PRIME_Y);
 			}
 			zr[k] = cubic_lerp(yr[0], yr[1], yr[2], yr[3], ys);
 			zp = iadd(zp, PRIME_Z);
 		}
-		return cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * (1 / (1.5f * 1.5f * 1.5f));
+		// corners unscaled, one exact power-of-two scale here (see VALUE_SCALE)
+		return (cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * VALUE_SCALE) * (1 / (1.5f * 1.5f * 1.5f));
 	}
 
 	// OpenSimplex2, 3-D: two half-offset cubic lattices (seed and ~seed), <= 2 kernel terms from each
@@ -238,31 +292,24 @@ namespace upg
 			if (a > 0)
 				value += (a * a) * (a * a) * grad_coord(seed, i, j, k, x0, y0, z0);
 
-			if (ax0 >= ay0 && ax0 >= az0)
+			// the library's three-way branch on the dominant axis, as selects feeding ONE gradient term: the branch is
+			// lane-divergent almost everywhere, so the warp used to run all three bodies back to back
 			{
-				float b = a + ax0 + ax0;
+				const bool xm = ax0 >= ay0 && ax0 >= az0;
+				const bool ym = !xm && (ay0 > ax0 && ay0 >= az0);
+				const bool zm = !xm && !ym;
+				const float am = xm ? ax0 : ym ? ay0 : az0;
+				float b = a + am + am;
 				if (b > 1)
 				{
 					b -= 1;
-					value += (b * b) * (b * b) * grad_coord(seed, isub(i, imul(xNSign, PRIME_X)), j, k, x0 + (float)xNSign, y0, z0);
-				}
-			}
-			else if (ay0 > ax0 && ay0 >= az0)
-			{
-				float b = a + ay0 + ay0;
-				if (b > 1)
-				{
-					b -= 1;
-					value += (b * b) * (b * b) * grad_coord(seed, i, isub(j, imul(yNSign, PRIME_Y)), k, x0, y0 + (float)yNSign, z0);
-				}
-			}
-			else
-			{
-				float b = a + az0 + az0;
-				if (b > 1)
-				{
-					b -= 1;
-					value += (b * b) * (b * b) * grad_coord(seed, i, j, isub(k, imul(zNSign, PRIME_Z)), x0, y0, z0 + (float)zNSign);
+					const int32_t ii = xm ? isub(i, imul(xNSign, PRIME_X)) : i;
+					const int32_t jj = ym ? isub(j, imul(yNSign, PRIME_Y)) : j;
+					const int32_t kk = zm ? isub(k, imul(zNSign, PRIME_Z)) : k;
+					const float xx = xm ? x0 + (float)xNSign : x0;
+					const float yy = ym ? y0 + (float)yNSign : y0;
+					const float zz = zm ? z0 + (float)zNSign : z0;
+					value += (b * b) * (b * b) * grad_coord(seed, ii, jj, kk, xx, yy, zz);
 				}
 			}
 
