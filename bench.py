@@ -43,6 +43,9 @@ SHAPE, ELEVATION, COLORING = "sphere", "lakes", "default"
 # algorithmic FP32 work (FMA = 2) per unit, counted from the un-contracted arithmetic; DESIGN.md "Work per unit"
 FLOPS_PER_SAMPLE_LAND = 640.0
 FLOPS_PER_TEXEL_LAND = 7200.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused K1 launch per grid node, from the committed `ncu --set full` capture
+# (profiles/); None until a capture of this kernel exists
+K1_TRAFFIC_BYTES_PER_NODE = None
 
 
 def workload(args):
@@ -218,8 +221,8 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- leg 1: SDF sampling (the contract's timed region) ---------------------------------------------------------
     def step():
-        for f, b in zip(FIELDS, bufs):
-            planet.field_samples_device(f, 0, res, b.data_ptr(), stream.cuda_stream)
+        # the three fields of one planet from ONE fused K1 launch: shape + elevation evaluated once per grid node, three stores
+        planet.fields_samples_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
 
     for _ in range(args.warmup):
         step()
@@ -234,16 +237,19 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_total = e0.elapsed_time(e1)
 
-    # the dominant kernel alone (land field), CUDA events on the launching stream
+    # the same kernel restricted to one field each (what three separate upg_field_samples_device calls cost), CUDA events on
+    # the launching stream
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    for _ in range(max(3, args.steps)):
-        k0.record(stream)
-        planet.field_samples_device("land", 0, res, bufs[0].data_ptr(), stream.cuda_stream)
-        k1.record(stream)
-        k1.synchronize()
-        kernel_ms.append(k0.elapsed_time(k1))
-    land_ms = statistics.mean(kernel_ms)
+    single_ms = {}
+    for f, b in zip(FIELDS, bufs):
+        kernel_ms = []
+        for _ in range(max(3, min(args.steps, 5))):
+            k0.record(stream)
+            planet.field_samples_device(f, 0, res, b.data_ptr(), stream.cuda_stream)
+            k1.record(stream)
+            k1.synchronize()
+            kernel_ms.append(k0.elapsed_time(k1))
+        single_ms[f] = statistics.mean(kernel_ms)
 
     # end to end through the host-buffer C-ABI call: device->host copies inside the timed region
     host = torch.empty(n, dtype=torch.float32, pin_memory=True)
@@ -269,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
     planet.field_mesh("land")  # warm the memory pool like a second planet of a batch would find it
     barrier()
     t = time.perf_counter()
-    raw = {f: planet.field_mesh(f) for f in FIELDS}
+    raw = planet.field_meshes(FIELDS)
     mesh_s = time.perf_counter() - t
     t = time.perf_counter()
     m2 = planet.field_mesh("land")
@@ -405,15 +411,17 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = samples_per_step / (e2e_ms * 1e-3)
 
     peak = fp32_peak(capi, local_rank)
-    achieved = FLOPS_PER_SAMPLE_LAND * n / (land_ms * 1e-3) / 1e12
+    fused_ms = ms_total / args.steps  # one launch per step
+    achieved = FLOPS_PER_SAMPLE_LAND * n / (fused_ms * 1e-3) / 1e12
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     peak_source = "FP32 FMA ceiling measured in this run by upg_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 SIMT figure)"
     roofline = {
-        "bound": "fp32", "kernel": "sdf_sample_kernel<sphere,lakes> (land field)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_source,
-        "kernel_ms": land_ms, "flops_per_sample": FLOPS_PER_SAMPLE_LAND,
-        "hbm": {"achieved_gbs": 4.0 * n / (land_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "4 B/sample written; the kernel is compute bound"},
+        "bound": "fp32", "kernel": "sdf_sample_kernel<sphere,lakes> (fused land + water + navigation launch)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": K1_TRAFFIC_BYTES_PER_NODE * n if K1_TRAFFIC_BYTES_PER_NODE else None, "peak_source": peak_source,
+        "kernel_ms": fused_ms, "flops_per_grid_node": FLOPS_PER_SAMPLE_LAND, "samples_per_grid_node": len(FIELDS),
+        "single_field_kernel_ms": single_ms,
+        "hbm": {"achieved_gbs": 4.0 * len(FIELDS) * n / (fused_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "12 B written per grid node (3 fields); the kernel is FP32/INT32 issue bound"},
     }
     bake_achieved = FLOPS_PER_TEXEL_LAND * covered["land"] / (bake_land_ms * 1e-3) / 1e12
     texel_bake = {
@@ -426,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
     planet_ms = mesh_ms + bake_e2e_ms
     planet_line = {
         "ms": planet_ms, "isosurface_ms": mesh_ms, "bake_ms": bake_e2e_ms, "field_mesh_land_ms": field_mesh_land_s * 1e3,
-        "what": "3 x upg_field_mesh (sampling + Dual Marching Cubes + mesh download) + 2 x upg_bake, host buffers, wall clock", "mesh": mesh_stats,
+        "what": "upg_field_meshes (fused sampling of the 3 fields + 3 concurrent Dual Marching Cubes extractions + mesh downloads) + 2 x upg_bake, host buffers, wall clock", "mesh": mesh_stats,
     }
 
     threads = os.cpu_count() or 1
@@ -444,7 +452,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception as ex:  # the baseline is reported, never required for the GPU number
         cpu["sample"] = "failed: %r" % (ex,)
 
-    launches_sampling = len(FIELDS) * args.steps
+    launches_sampling = args.steps  # one fused sdf_sample_kernel launch per step
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -110,6 +110,11 @@ int upg_field_samples(upg_planet *planet, int field, int z0, int z1, float *host
  * keep the field on the GPU (bench.py's device-resident metric, the isosurface stage) */
 int upg_field_samples_device(upg_planet *planet, int field, int z0, int z1, float *device_out, void *cuda_stream);
 
+/* land, water and navigation of the same slices from ONE evaluation of the shape and the elevation function per sample
+ * (the three fields differ only in how the two combine, sources/modesConfiguration.cpp:248-279, and the generator asks for
+ * all three: sources/generator.cpp:432-439).  Each output is bit-identical to the single-field call; any pointer may be NULL. */
+int upg_fields_samples_device(upg_planet *planet, int z0, int z1, float *device_land, float *device_water, float *device_navigation, void *cuda_stream);
+
 /* one terrainSdf* value per explicit position (n x 3 floats): the per-vertex terrainSdfElevationRaw loop of the water
  * mesh culling (sources/meshGeneration.cpp:62-68) and the parity probes */
 int upg_field_points(upg_planet *planet, int field, const float *host_positions, uint64_t n, float *host_out);
@@ -143,6 +148,12 @@ typedef struct upg_mesh
  * samples `field` over the planet's grid on the device and extracts the isosurface without the samples ever leaving HBM.
  * UPG_ERR_EMPTY_MESH when no triangle results (the reference throws "generated empty base land mesh", :51-52). */
 int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out);
+
+/* The three base meshes of a planet in one call (replaces the three concurrent tasks meshGenerateBaseLand / Water / Navigation,
+ * sources/generator.cpp:432-439): the fields of `field_mask` (bit 0 land, bit 1 water, bit 2 navigation) are sampled by one
+ * fused K1 pass and extracted concurrently.  out3[field] is filled for every requested field (others zeroed); each mesh is
+ * bit-identical to upg_field_mesh(field) and is released with upg_mesh_free. */
+int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3);
 
 /*
  * Multi-GPU sharding of K1 + K2..K4 by z-slab ("grid sampling shards naturally by z-slab").  dualmc's scan over z in [0, res-2)

@@ -143,3 +143,29 @@ def test_nan_sample_is_reported_like_the_reference_throw():
     assert e.value.code == 3
     # and the planet stays usable afterwards
     assert np.isfinite(p.field_points("land", np.zeros((1, 3), dtype=np.float32))).all()
+
+
+@pytest.mark.parametrize("shape,elev,res", [("sphere", "lakes", 70), ("torus", "craters", 45), ("asteroid", "islands", 33), ("knot", "simple", 40), ("bunny", "legacy", 24), ("cube", "none", 17)])
+def test_fused_three_field_sampling_is_bit_identical(shape, elev, res):
+    # upg_fields_samples_device evaluates shape + elevation once per sample for land / water / navigation: every output
+    # must equal the single-field kernel bit for bit, on any slice range and with any subset of outputs
+    import torch
+
+    p = Planet(shape=shape, elevation=elev, grid=res)
+    s = torch.cuda.current_stream()
+    z0, z1 = 3, res - 5
+    want = {f: p.field_samples(f, z0, z1) for f in ("land", "water", "navigation")}
+    bufs = {f: torch.full((z1 - z0, res, res), -7.0, dtype=torch.float32, device="cuda") for f in want}
+    p.fields_samples_device(z0, z1, bufs["land"].data_ptr(), bufs["water"].data_ptr(), bufs["navigation"].data_ptr(), s.cuda_stream)
+    s.synchronize()
+    for f in want:
+        assert same_bits(bufs[f].cpu().numpy(), want[f]).all(), f
+    # subsets: untouched buffers stay untouched
+    only = torch.full((z1 - z0, res, res), -7.0, dtype=torch.float32, device="cuda")
+    p.fields_samples_device(z0, z1, 0, 0, only.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    assert same_bits(only.cpu().numpy(), want["navigation"]).all()
+    with pytest.raises(UpgError):
+        p.fields_samples_device(z0, z1, 0, 0, 0, s.cuda_stream)
+    with pytest.raises(UpgError):
+        p.fields_samples_device(2, res + 1, only.data_ptr(), 0, 0, s.cuda_stream)

@@ -106,3 +106,25 @@ def test_slab_extraction_stitches_to_the_whole_mesh(shape, elev, res, slabs):
     if shape == "sphere" and 1 < slabs < res:
         # interior slabs do reference vertices of their lower neighbour (negative relative ids)
         assert any((s["indices"].view(np.int32) < 0).any() for s in parts[1:] if len(s["indices"]))
+
+
+@pytest.mark.parametrize("shape,elev,res", [("sphere", "lakes", 96), ("torus", "craters", 60), ("hemispheres", "simple", 50)])
+def test_field_meshes_equal_single_field_calls(shape, elev, res):
+    # upg_field_meshes: one fused sampling pass + three concurrent extractions == three upg_field_mesh calls, bit for bit
+    p = Planet(shape=shape, elevation=elev, grid=res)
+    got = p.field_meshes(("land", "water", "navigation"))
+    for f in ("land", "water", "navigation"):
+        assert_same_mesh(got[f], p.field_mesh(f))
+        assert got[f]["near_zero_samples"] == p.field_mesh(f)["near_zero_samples"]
+    two = p.field_meshes(("water", "land"))
+    assert set(two) == {"water", "land"}
+    assert_same_mesh(two["water"], got["water"])
+
+
+def test_field_meshes_errors():
+    p = Planet(shape="sphere", elevation="none", grid=16, box=100.0)  # the planet lies outside the box
+    with pytest.raises(UpgError) as e:
+        p.field_meshes(("land", "water"))
+    assert e.value.code == 4
+    with pytest.raises(ValueError):
+        p.field_meshes(("elevation",))

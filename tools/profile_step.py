@@ -20,8 +20,7 @@ a = ap.parse_args()
 p = Planet(shape="sphere", elevation="lakes", coloring="default", grid=a.grid, poles=bool(a.poles), flowers=bool(a.flowers))
 for r in range(a.repeat):
     meshes = {}
-    for f in ("land", "water", "navigation"):
-        m = p.field_mesh(f)
+    for f, m in p.field_meshes(("land", "water", "navigation")).items():
         if f != "navigation":
             uv = synth.octahedral_uv(m["positions"])
             meshes[f] = (m["positions"], -m["normals"], uv, synth.drop_folded_triangles(uv, m["indices"]))

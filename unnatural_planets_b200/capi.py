@@ -99,6 +99,8 @@ def load_library():
     L.upg_planet_seed_log.argtypes = [vp, fp, i32]
     L.upg_field_samples.argtypes = [vp, i32, i32, i32, fp]
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
+    L.upg_fields_samples_device.argtypes = [vp, i32, i32, fp, fp, fp, vp]
+    L.upg_field_meshes.argtypes = [vp, C.c_uint, C.POINTER(Mesh)]
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
     L.upg_field_mesh.argtypes = [vp, i32, C.POINTER(Mesh)]
     L.upg_field_mesh_slab.argtypes = [vp, i32, i32, i32, C.POINTER(Mesh)]

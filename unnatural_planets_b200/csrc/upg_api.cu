@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 
 #include "../../include/upg.h"
 #include "upg_internal.h"
@@ -297,6 +298,29 @@ extern "C"
 		L.count = (uint64_t)(z1 - z0) * res * res;
 		L.z0 = (uint32_t)z0;
 		L.field = field;
+		L.status = p->status;
+		return launch_field(p, L, (cudaStream_t)cuda_stream);
+	}
+
+	int upg_fields_samples_device(upg_planet *planet, int z0, int z1, float *device_land, float *device_water, float *device_navigation, void *cuda_stream)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || (!device_land && !device_water && !device_navigation))
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		const int res = p->params.grid.res;
+		if (z0 < 0 || z1 > res || z0 > z1)
+			return fail(UPG_ERR_ARGUMENT, "bad slice range [%d, %d)", z0, z1);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		FieldLaunch L;
+		L.out = device_land;
+		L.outWater = device_water;
+		L.outNavigation = device_navigation;
+		L.positions = nullptr;
+		L.count = (uint64_t)(z1 - z0) * res * res;
+		L.z0 = (uint32_t)z0;
+		L.field = FD_ALL;
 		L.status = p->status;
 		return launch_field(p, L, (cudaStream_t)cuda_stream);
 	}
@@ -610,6 +634,124 @@ extern "C"
 			cudaFreeAsync(dens, cs.compute);
 		cudaStreamSynchronize(cs.compute);
 		cs.close();
+		return rc;
+	}
+
+	int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !out3)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		std::memset(out3, 0, sizeof(upg_mesh) * 3);
+		if ((field_mask & 7u) == 0 || (field_mask & ~7u))
+			return fail(UPG_ERR_ARGUMENT, "bad field mask %#x (bit 0 land, bit 1 water, bit 2 navigation)", field_mask);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		const int res = p->params.grid.res;
+		const uint64_t count = (uint64_t)res * res * res;
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		const bool trace = trace_enabled();
+		const double t0 = trace ? now_ms() : 0;
+		float *dens[3] = { nullptr, nullptr, nullptr };
+		for (int f = 0; f < 3 && rc == UPG_OK; f++)
+			if (field_mask & (1u << f))
+			{
+				e = cudaMallocAsync(&dens[f], sizeof(float) * count, cs.compute);
+				if (e != cudaSuccess)
+					rc = cuda_fail(e, "cudaMallocAsync(field)");
+			}
+		if (rc == UPG_OK)
+		{
+			// shape and elevation are evaluated ONCE per sample for all requested fields
+			FieldLaunch L;
+			L.out = dens[FD_LAND];
+			L.outWater = dens[FD_WATER];
+			L.outNavigation = dens[FD_NAVIGATION];
+			L.positions = nullptr;
+			L.count = count;
+			L.z0 = 0;
+			L.field = FD_ALL;
+			L.status = p->status;
+			rc = launch_field(p, L, cs.compute);
+		}
+		cudaEvent_t sampled = nullptr;
+		if (rc == UPG_OK)
+		{
+			e = cudaEventCreateWithFlags(&sampled, cudaEventDisableTiming);
+			if (e == cudaSuccess)
+				e = cudaEventRecord(sampled, cs.compute);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "cudaEventRecord");
+		}
+		if (rc == UPG_OK)
+			rc = check_status(p, cs.compute, "upg_field_meshes");
+		const double t1 = trace ? now_ms() : 0;
+		// the three extractions are independent: one host thread and one stream pair each, like the generator's three tasks
+		// (sources/generator.cpp:432-439); their sparse passes and downloads overlap
+		int rcs[3] = { UPG_OK, UPG_OK, UPG_OK };
+		std::string errs[3];
+		if (rc == UPG_OK)
+		{
+			std::thread workers[3];
+			for (int f = 0; f < 3; f++)
+			{
+				if (!dens[f])
+					continue;
+				workers[f] = std::thread(
+					[&, f]()
+					{
+						int r = UPG_OK;
+						cudaError_t ee = cudaSetDevice(p->device);
+						CallStreams ws;
+						if (ee != cudaSuccess)
+							r = cuda_fail(ee, "cudaSetDevice");
+						if (r == UPG_OK)
+							r = ws.open();
+						if (r == UPG_OK)
+						{
+							ee = cudaStreamWaitEvent(ws.compute, sampled, 0);
+							if (ee != cudaSuccess)
+								r = cuda_fail(ee, "cudaStreamWaitEvent");
+						}
+						DmcResult d;
+						if (r == UPG_OK)
+							r = dmc_extract(dens[f], res, res, res, p->boxSize, res, ws.compute, d);
+						if (r == UPG_OK && d.triangleCount == 0)
+							r = fail(UPG_ERR_EMPTY_MESH, "generated empty mesh (field %d)", f);
+						if (r == UPG_OK)
+							r = mesh_to_host(d, ws.compute, &out3[f]);
+						dmc_release(d, ws.compute);
+						if (ws.compute)
+							cudaStreamSynchronize(ws.compute);
+						ws.close();
+						rcs[f] = r;
+						if (r != UPG_OK)
+							errs[f] = upg_last_error();
+					});
+			}
+			for (int f = 0; f < 3; f++)
+				if (workers[f].joinable())
+					workers[f].join();
+			for (int f = 0; f < 3 && rc == UPG_OK; f++)
+				if (rcs[f] != UPG_OK)
+					rc = fail(rcs[f], "%s", errs[f].c_str());
+		}
+		if (trace)
+			std::fprintf(stderr, "[upg] field_meshes(mask %#x) res %d: fused sampling %.2f ms, extraction + download %.2f ms\n", field_mask, res, t1 - t0, now_ms() - t1);
+		if (sampled)
+			cudaEventDestroy(sampled);
+		for (int f = 0; f < 3; f++)
+			if (dens[f])
+				cudaFreeAsync(dens[f], cs.compute);
+		cudaStreamSynchronize(cs.compute);
+		cs.close();
+		if (rc != UPG_OK)
+			for (int f = 0; f < 3; f++)
+				upg_mesh_free(&out3[f]);
 		return rc;
 	}
 

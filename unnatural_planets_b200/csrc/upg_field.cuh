@@ -17,7 +17,9 @@ namespace upg
 	// everything one launch needs besides the planet
 	struct FieldLaunch
 	{
-		float *out; // device, `count` floats
+		float *out; // device, `count` floats (FD_ALL: the land field, may be null)
+		float *outWater = nullptr; // FD_ALL only: the water field, may be null
+		float *outNavigation = nullptr; // FD_ALL only: the navigation field, may be null
 		const float *positions; // device, count x 3 floats, or nullptr = grid mode
 		uint64_t count; // samples in this launch
 		uint32_t z0; // first z-slice (grid mode)
@@ -73,7 +75,61 @@ namespace upg
 			const uint32_t y = row - zl * res;
 			pos = v3(grid_coord(P.grid, x), grid_coord(P.grid, y), grid_coord(P.grid, L.z0 + zl));
 		}
-		const float v = terrain_field_rt<SHAPE, ELEV>(P, L.field, pos);
+		// One inlined copy of the shape and of the elevation function serves every field (the instruction cache is the scarce
+		// resource of this kernel); the field only selects which of the two run and how they combine
+		// (sources/modesConfiguration.cpp:230-279).
+		const int field = L.field;
+		float base = 0, elev = 0;
+		if (field != FD_ELEVATION_RAW)
+			base = shape_sdf<SHAPE>(P, pos);
+		if (field != FD_WATER && field != FD_ELEVATION)
+			elev = elevation_raw<ELEV>(P, pos);
+		if (field == FD_ALL)
+		{
+			// land, water and navigation of the same sample share the shape and the elevation: the generator asks for all three
+			// (sources/generator.cpp:432-439), so they are produced by one evaluation and up to three coalesced stores
+			const float e10 = elev / 10.0f;
+			const float land = base - e10;
+			const float nav = base - fmax_(e10, 0.0f);
+			bool bad = false;
+			if (L.out)
+			{
+				L.out[idx] = land;
+				bad |= isnan_(land);
+			}
+			if (L.outWater)
+			{
+				L.outWater[idx] = base;
+				bad |= isnan_(base);
+			}
+			if (L.outNavigation)
+			{
+				L.outNavigation[idx] = nav;
+				bad |= isnan_(nav);
+			}
+			if (bad)
+				atomicOr(L.status, 1u);
+			return;
+		}
+		float v;
+		switch (field)
+		{
+			case FD_WATER:
+				v = base;
+				break;
+			case FD_ELEVATION:
+				v = base * 10.0f;
+				break;
+			case FD_ELEVATION_RAW:
+				v = elev;
+				break;
+			case FD_NAVIGATION:
+				v = base - fmax_(elev / 10.0f, 0.0f);
+				break;
+			default:
+				v = base - elev / 10.0f;
+				break;
+		}
 		if (isnan_(v))
 			atomicOr(L.status, 1u);
 		L.out[idx] = v;

@@ -78,7 +78,8 @@ namespace upg
 		FD_NAVIGATION = 2, // shape - max(elev, 0) / 10
 		FD_ELEVATION_RAW = 3, // elev                (terrainSdfElevationRaw)
 		FD_ELEVATION = 4, // shape * 10          (terrainSdfElevation)
-		FD_COUNT
+		FD_COUNT,
+		FD_ALL = FD_COUNT // internal to K1: land + water + navigation from one evaluation (upg_fields_samples_device)
 	};
 
 	// a triangle with everything closestPoint(Triangle) derives from it (geometry.cpp:644-673), prepared on the host

@@ -610,17 +610,30 @@ namespace upg
 		const float rm = smoothstep_(saturate_(mask * +7 - 0.3f));
 		const float tm = smoothstep_(saturate_(mask * -7 - 1.5f));
 
-		float ridge = noise3<NT_SIMPLEX, FT_RIDGED, 4>(E.n[2], pos);
-		ridge = fmax_(ridge - 0.1f, 0.0f);
-		ridge = powf(ridge, 1.6f);
-		ridge *= rm * cover;
-		ridge *= 1000;
+		// The two masks are never non-zero together (rm > 0 needs mask > 0.3/7, tm > 0 needs mask < -1.5/7), and a mask that is
+		// exactly +0 makes its term exactly +0: pow(max(.,0), 1.6) and terrace(max(.,0) * 2.5, 4) are finite and >= +0, so
+		// term * (+0 * cover) * scale == +0.0f bit for bit.  The noise behind a zero mask is therefore not evaluated: 4
+		// OpenSimplex2 octaves and / or 3 Perlin octaves saved per sample with IDENTICAL results (tests/test_host_terrain.py
+		// checks the host compilation of this header against the reference bit for bit).
+		float ridge = 0.0f;
+		if (rm != 0.0f)
+		{
+			ridge = noise3<NT_SIMPLEX, FT_RIDGED, 4>(E.n[2], pos);
+			ridge = fmax_(ridge - 0.1f, 0.0f);
+			ridge = powf(ridge, 1.6f);
+			ridge *= rm * cover;
+			ridge *= 1000;
+		}
 
-		float terraces = noise3<NT_PERLIN, FT_FBM, 3>(E.n[3], pos);
-		terraces = fmax_(terraces + 0.1f, 0.0f) * 2.5f;
-		terraces = terrace(terraces, 4);
-		terraces *= tm * cover;
-		terraces *= 250;
+		float terraces = 0.0f;
+		if (tm != 0.0f)
+		{
+			terraces = noise3<NT_PERLIN, FT_FBM, 3>(E.n[3], pos);
+			terraces = fmax_(terraces + 0.1f, 0.0f) * 2.5f;
+			terraces = terrace(terraces, 4);
+			terraces *= tm * cover;
+			terraces *= 250;
+		}
 
 		return land + smooth_max(0, fmax_(ridge, terraces), 50);
 	}

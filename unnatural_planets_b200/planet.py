@@ -142,7 +142,24 @@ class Planet:
         """asynchronous, into device memory (an integer device pointer), on CUDA stream handle `stream`."""
         capi.check(self._lib.upg_field_samples_device(self._h, capi.FIELDS[field], z0, z1, C.c_void_p(device_ptr), C.c_void_p(stream)))
 
+    def fields_samples_device(self, z0, z1, d_land=0, d_water=0, d_navigation=0, stream=0):
+        """land / water / navigation of the same slices from one evaluation per sample (upg_fields_samples_device); device
+        pointers as integers, 0 = field not wanted."""
+        vp = C.c_void_p
+        capi.check(self._lib.upg_fields_samples_device(self._h, z0, z1, vp(d_land or None), vp(d_water or None), vp(d_navigation or None), vp(stream)))
+
     # K1 + K2..K4 ---------------------------------------------------------------------------------
+    def field_meshes(self, fields=("land", "water", "navigation")):
+        """the base meshes of several fields from one fused sampling pass (upg_field_meshes) -> {field: mesh dict}."""
+        ms = (capi.Mesh * 3)()
+        mask = 0
+        for f in fields:
+            if capi.FIELDS[f] > 2:
+                raise ValueError("field_meshes: land, water and navigation only")
+            mask |= 1 << capi.FIELDS[f]
+        capi.check(self._lib.upg_field_meshes(self._h, mask, ms))
+        return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
+
     def field_mesh(self, field="land"):
         """meshGenerateGeneric up to makeMesh's normals (upg_field_mesh) -> dict of numpy arrays."""
         m = capi.Mesh()
