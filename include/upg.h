@@ -235,6 +235,22 @@ int upg_bake_rows(upg_planet *planet, int water, const float *positions, const f
  * that keep the mesh on the GPU (bench.py's device-resident metric) */
 int upg_bake_device(upg_planet *planet, int water, const float *device_positions, const float *device_normals, const float *device_uvs, uint32_t vertex_count, const uint32_t *device_indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint8_t *device_albedo, uint8_t *device_special, uint8_t *device_height_map, void *cuda_stream);
 
+/*
+ * K5..K8: the bake plus the texture tail the generator applies to every chunk before it writes the PNGs
+ * (sources/generator.cpp:123-145, 175-197): imageConvertSpecialToGltfPbr (externals/cage/sources/libcore/image/
+ * imageAlgorithms.cpp:296-302) -> `pbr` w*h*3 = (0, roughness, metallic), and imageConvertHeigthToNormal(heightMap, 1)
+ * (:202-246) -> `normal_map` w*h*3, a 3x3 Sobel over the U8 height with clamped borders.  `albedo`, `pbr` and `normal_map` are
+ * the payloads of <chunk>-albedo.png, -pbr.png and -normal.png.  The *_rows / *_device forms shard by texel rows like upg_bake_rows
+ * (the band grows to 8 rows of apron: the Sobel reads one finished row beyond the caller's).
+ */
+int upg_bake_export(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint8_t *albedo, uint8_t *pbr, uint8_t *normal_map);
+int upg_bake_export_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *pbr, uint8_t *normal_map);
+int upg_bake_export_device(upg_planet *planet, int water, const float *device_positions, const float *device_normals, const float *device_uvs, uint32_t vertex_count, const uint32_t *device_indices, uint32_t index_count, uint32_t width, uint32_t height, uint32_t row0, uint32_t row1, uint8_t *device_albedo, uint8_t *device_pbr, uint8_t *device_normal_map, void *cuda_stream);
+
+/* K8 alone over host U8 images: `special` (w*h*2) -> `pbr` (w*h*3) and / or `height_map` (w*h*1) -> `normal_map` (w*h*3) with
+ * imageConvertHeigthToNormal's `strength` (> 0; the generator passes 1).  Either pair may be NULL. */
+int upg_texture_tail(int device, const uint8_t *special, const uint8_t *height_map, uint32_t width, uint32_t height, float strength, uint8_t *pbr, uint8_t *normal_map);
+
 /* coverage statistics of the last upg_bake on this thread: texels written by the rasteriser (= terrainTile evaluations;
  * the reference evaluates every (triangle, texel) visit, this library only the winning one) */
 uint64_t upg_bake_last_covered_texels(void);

@@ -113,3 +113,36 @@ def isosurface(dens, box=4000.0, full_res=None, iso=0.0, manifold=True):
     L.upo_isosurface_copy(C.c_void_p(h), _p(out["dmc_vertices"]), _p(out["dmc_quads"]), _p(out["positions"]), _p(out["normals"]), _p(out["indices"]))
     L.upo_isosurface_free(C.c_void_p(h))
     return out
+
+
+def texture_tail(special=None, height=None, strength=1.0):
+    """numpy restatement (float32, operation order of the C++) of the generator's texture tail (sources/generator.cpp:135-139):
+    imageConvertSpecialToGltfPbr (externals/cage/sources/libcore/image/imageAlgorithms.cpp:296-302): channels (0, special0, special1);
+    imageConvertHeigthToNormal (:202-246) over a U8 image: clamped 3x3 Sobel of value = u8 / 255.f (image.cpp:220-236),
+    v = normalize(-dX, -dY, 1 / strength), (v + 1) * 0.5, Image::set = uint8(saturate(v) * 255) truncating (image.cpp:468-481).
+    Pinned against the reference's own output by tests/golden/texture_tail.npz (tests/test_oracle_port.py)."""
+    f32 = np.float32
+    pbr = nm = None
+    if special is not None:
+        sp = np.asarray(special, dtype=np.uint8)
+        pbr = np.zeros(sp.shape[:2] + (3,), dtype=np.uint8)
+        pbr[..., 1:] = sp
+    if height is not None:
+        hm = np.asarray(height, dtype=np.uint8)
+        hm = hm.reshape(hm.shape[0], hm.shape[1])
+        v = hm.astype(f32) / f32(255)
+        p = np.pad(v, 1, mode="edge")
+        H, W = v.shape
+        tl, tc, tr = p[0:H, 0:W], p[0:H, 1 : W + 1], p[0:H, 2 : W + 2]
+        lc, rc = p[1 : H + 1, 0:W], p[1 : H + 1, 2 : W + 2]
+        bl, bc, br = p[2 : H + 2, 0:W], p[2 : H + 2, 1 : W + 1], p[2 : H + 2, 2 : W + 2]
+        two = f32(2)
+        dx = ((tr + two * rc) + br) - ((tl + two * lc) + bl)
+        dy = ((bl + two * bc) + br) - ((tl + two * tc) + tr)
+        x, y, z = -dx, -dy, np.full_like(dx, f32(1) / f32(strength))
+        length = np.sqrt(((f32(0) + x * x) + y * y) + z * z)
+        out = np.stack([x / length, y / length, z / length], axis=-1)
+        out = (out + f32(1)) * f32(0.5)
+        out = np.minimum(np.maximum(out, f32(0)), f32(1)) * f32(255)
+        nm = out.astype(np.uint8)
+    return pbr, nm

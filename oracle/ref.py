@@ -240,3 +240,13 @@ class RefPlanet:
         u8 = np.zeros((h, w, ch), dtype=np.uint8) if to_u8 else None
         self._check(self.lib.upref_dilate(_fp(img), C.c_uint32(w), C.c_uint32(h), C.c_uint32(ch), C.c_uint32(rounds), C.c_int(int(use_nan)), _fp(u8) if to_u8 else None))
         return (img, u8) if to_u8 else img
+
+    def texture_tail(self, special, height, strength=1.0):
+        """imageConvertSpecialToGltfPbr + imageConvertHeigthToNormal on U8 images (sources/generator.cpp:135-139)."""
+        special = np.ascontiguousarray(special, dtype=np.uint8)
+        height = np.ascontiguousarray(height, dtype=np.uint8)
+        h, w = height.shape[:2]
+        pbr = np.zeros((h, w, 3), dtype=np.uint8)
+        normal = np.zeros((h, w, 3), dtype=np.uint8)
+        self._check(self.lib.upref_texture_tail(_fp(special), _fp(height), C.c_uint32(w), C.c_uint32(h), C.c_float(strength), _fp(pbr), _fp(normal)))
+        return pbr, normal

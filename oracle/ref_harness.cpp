@@ -593,4 +593,25 @@ extern "C"
 				}
 			});
 	}
+	// the texture tail the generator applies to every chunk's U8 images before export (sources/generator.cpp:135-139):
+	// imageConvertSpecialToGltfPbr (imageAlgorithms.cpp:296-302) and imageConvertHeigthToNormal(img, strength) (:216-246)
+	int upref_texture_tail(const uint8_t *special /* w*h*2 */, const uint8_t *height /* w*h*1 */, uint32_t w, uint32_t h, float strength, uint8_t *pbr /* w*h*3 */, uint8_t *normal /* w*h*3 */)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Image> sp = newImage();
+				sp->importRaw(PointerRange<const char>((const char *)special, (const char *)special + (size_t)w * h * 2), w, h, 2, ImageFormatEnum::U8);
+				imageConvertSpecialToGltfPbr(+sp);
+				if (sp->channels() != 3 || sp->format() != ImageFormatEnum::U8)
+					CAGE_THROW_ERROR(Exception, "unexpected pbr image layout");
+				std::memcpy(pbr, sp->rawViewU8().data(), (size_t)w * h * 3);
+				Holder<Image> hm = newImage();
+				hm->importRaw(PointerRange<const char>((const char *)height, (const char *)height + (size_t)w * h), w, h, 1, ImageFormatEnum::U8);
+				imageConvertHeigthToNormal(+hm, strength);
+				if (hm->channels() != 3 || hm->format() != ImageFormatEnum::U8)
+					CAGE_THROW_ERROR(Exception, "unexpected normal image layout");
+				std::memcpy(normal, hm->rawViewU8().data(), (size_t)w * h * 3);
+			});
+	}
 }

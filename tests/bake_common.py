@@ -143,3 +143,18 @@ def dilation_image(h=70, w=90, ch=3, seed=5, hole=0.6):
     mask |= ((yy - h / 2) ** 2 + (xx - w / 2) ** 2) < (min(h, w) / 4) ** 2  # a hole wider than 7 rounds can fill
     img[mask] = np.nan
     return img
+
+
+def tail_images():
+    """[(name, special u8 (h,w,2), height u8 (h,w,1))]: inputs of the texture-tail fixture (texture_tail.npz): degenerate and ragged
+    sizes (every border clamp of the Sobel), random bytes (every quantisation bucket) and a smooth relief with flat areas"""
+    rng = np.random.default_rng(77)
+    out = []
+    for h, w in ((1, 1), (1, 9), (9, 1), (2, 2), (3, 3), (37, 23), (64, 130)):
+        out.append(("rand_%dx%d" % (h, w), rng.integers(0, 256, (h, w, 2), dtype=np.uint8), rng.integers(0, 256, (h, w, 1), dtype=np.uint8)))
+    yy, xx = np.mgrid[0:96, 0:80]
+    relief = 127 + 90 * np.sin(xx / 9.0) * np.cos(yy / 13.0)
+    relief[20:40, 10:50] = 200  # a plateau: zero gradient -> (127, 127, 255)
+    relief[60:, :30] = 0
+    out.append(("relief_96x80", rng.integers(0, 256, (96, 80, 2), dtype=np.uint8), relief.astype(np.uint8)[..., None]))
+    return out

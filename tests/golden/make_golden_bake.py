@@ -8,6 +8,7 @@
   bake_<config>.npz      generateTexturesLand + generateTexturesWater outputs (u8) for bake_common.atlas_mesh at 192^2
   raster.npz             meshGenerateTexture coverage (owner, weights, visit count) for bake_common.random_triangles
   dilation.npz           imageDilation / imageConvert results incl. cage's own 11x11 test case (test-core/image.cpp:567-583)
+  texture_tail.npz       imageConvertSpecialToGltfPbr + imageConvertHeigthToNormal(1) on bake_common.tail_images (python ... tail = only this)
   colors.npz             colorRgbToHsv / HsvToRgb / RgbToHsluv / HsluvToRgb / interpolateColor samples
 """
 import os
@@ -24,7 +25,23 @@ from oracle.ref import RefPlanet  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def texture_tail_fixture():
+    ref = RefPlanet(init=False)
+    d = {}
+    for name, sp, hm in bc.tail_images():
+        d[name + "_pbr"], d[name + "_normal"] = ref.texture_tail(sp, hm, 1.0)
+    name, sp, hm = bc.tail_images()[-1]
+    d["strength4_normal"] = ref.texture_tail(sp, hm, 4.0)[1]
+    flat = d["relief_96x80_normal"][25:35, 15:45]
+    assert (flat == (127, 127, 255)).all(), "a plateau maps to the +z normal"
+    np.savez_compressed(os.path.join(OUT, "texture_tail.npz"), **d)
+    print("texture tail ok")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "tail":
+        return texture_tail_fixture()
+    texture_tail_fixture()
     for cfg in bc.TILE_CONFIGS:
         s, e, c, p, f = cfg
         ref = RefPlanet(s, e, c, p, f)

@@ -12,7 +12,7 @@ import pytest
 
 import bake_common as bc
 from conftest import golden, same_bits
-from unnatural_planets_b200 import Planet, UpgError, dilate, raster
+from unnatural_planets_b200 import Planet, UpgError, dilate, raster, texture_tail
 from unnatural_planets_b200.capi import TILE_COLUMNS
 
 pytestmark = pytest.mark.gpu
@@ -282,3 +282,47 @@ def test_sharded_planet_single_rank_equals_planet():
     got = sp.bake(0, pos, nrm, uv, idx, 192, 192)
     want = p.bake(0, pos, nrm, uv, idx, 192, 192)
     assert all((g.cpu().numpy() == w).all() for g, w in zip(got, want))
+
+
+# ---- K8: the texture tail (pbr shuffle + Sobel normal map), SURVEY.md section 8(f) n2 ---------------------------------------
+def test_texture_tail_bit_exact_against_reference_fixture():
+    g = golden("texture_tail.npz")
+    for name, sp, hm in bc.tail_images():
+        pbr, nm = texture_tail(sp, hm)
+        assert (pbr == g[name + "_pbr"]).all(), name
+        assert (nm == g[name + "_normal"]).all(), name
+    name, sp, hm = bc.tail_images()[-1]
+    assert (texture_tail(None, hm, strength=4.0)[1] == g["strength4_normal"]).all()
+    assert texture_tail(sp, None)[1] is None
+    with pytest.raises(UpgError):
+        texture_tail(None, hm, strength=0.0)  # "converting height to normal requires positive strength"
+
+
+def test_texture_tail_large_against_the_restatement():
+    from oracle import port
+
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:1500, 0:2047]
+    hm = (127 + 100 * np.sin(xx / 37.0) * np.cos(yy / 21.0) + rng.integers(-20, 20, xx.shape)).clip(0, 255).astype(np.uint8)
+    sp = rng.integers(0, 256, hm.shape + (2,), dtype=np.uint8)
+    pbr, nm = texture_tail(sp, hm)
+    wp, wn = port.texture_tail(sp, hm)
+    assert (pbr == wp).all() and (nm == wn).all()
+
+
+@pytest.mark.parametrize("water", [0, 1])
+def test_bake_export_is_bake_plus_tail_and_shards_by_rows(water):
+    from oracle import port
+
+    cfg = ("sphere", "lakes", "default", True, True)
+    pos, nrm, uv, idx = bc.atlas_mesh()
+    p = make_planet(cfg)
+    albedo, special, height = p.bake(water, pos, nrm, uv, idx, 192, 192)
+    a2, pbr, nmap = p.bake_export(water, pos, nrm, uv, idx, 192, 192)
+    wp, wn = port.texture_tail(special, height)
+    assert (a2 == albedo).all() and (pbr == wp).all() and (nmap == wn).all()
+    # ragged row bands, some thinner than the apron, reassemble bit for bit (the Sobel reads one finished row beyond the band)
+    cuts = [0, 1, 9, 64, 67, 131, 191, 192]
+    parts = [p.bake_export(water, pos, nrm, uv, idx, 192, 192, r0, r1) for r0, r1 in zip(cuts[:-1], cuts[1:])]
+    for k, whole in enumerate((a2, pbr, nmap)):
+        assert (np.concatenate([q[k] for q in parts], axis=0) == whole).all(), k

@@ -78,3 +78,17 @@ def test_noise_structure():
         assert a.std() > 0.1, ntype  # not degenerate
         # continuity across lattice cells: |f(p + d) - f(p)| bounded by a Lipschitz constant times |d|
         assert np.abs(a - b).max() < 0.02, (ntype, np.abs(a - b).max())
+
+
+def test_texture_tail_restatement_matches_the_reference_fixture():
+    # the numpy restatement of imageConvertSpecialToGltfPbr / imageConvertHeigthToNormal is pinned on the reference's own outputs
+    import bake_common as bc
+    from conftest import golden
+
+    g = golden("texture_tail.npz")
+    for name, sp, hm in bc.tail_images():
+        pbr, nm = port.texture_tail(sp, hm, 1.0)
+        assert (pbr == g[name + "_pbr"]).all(), name
+        assert (nm == g[name + "_normal"]).all(), name
+    name, sp, hm = bc.tail_images()[-1]
+    assert (port.texture_tail(None, hm, 4.0)[1] == g["strength4_normal"]).all()

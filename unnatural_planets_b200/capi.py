@@ -117,6 +117,10 @@ def load_library():
     L.upg_bake_last_covered_texels.restype = u64
     L.upg_bake_rows.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp]
     L.upg_bake_device.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp, vp]
+    L.upg_bake_export.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, fp, fp, fp]
+    L.upg_bake_export_rows.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp]
+    L.upg_bake_export_device.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, u32, u32, fp, fp, fp, vp]
+    L.upg_texture_tail.argtypes = [i32, fp, fp, u32, u32, C.c_float, fp, fp]
     L.upg_raster.argtypes = [i32, fp, u32, fp, u32, u32, u32, fp, fp, C.POINTER(u64)]
     L.upg_dilate.argtypes = [i32, fp, u32, u32, u32, u32, i32, fp]
     _lib = L

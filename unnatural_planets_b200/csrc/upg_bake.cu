@@ -543,11 +543,77 @@ namespace upg
 			// else: dst keeps what it held (the reference's ping-pong target is pre-filled with NaN / zero and holes only shrink)
 		}
 
+		inline unsigned blocks_for_n(size_t n) { return (unsigned)((n + 255) / 256); }
+
 		__global__ void __launch_bounds__(256) quantise_kernel(const float *__restrict__ src, uint8_t *__restrict__ dst, size_t n)
 		{
 			const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
 			if (i < n)
 				dst[i] = quantise_u8(src[i]);
+		}
+
+		// K8 `texture_tail`: what the generator does to a chunk's U8 images between the bake and the PNG export
+		// (sources/generator.cpp:135-139): imageConvertSpecialToGltfPbr = channels (0, roughness, metallic)
+		// (imageAlgorithms.cpp:296-302) and imageConvertHeigthToNormal(height, strength) = 3x3 Sobel over the clamped U8 height,
+		// normalised, mapped to [0,1] and re-quantised by truncation (:202-246, image.cpp:468-481).  `special` / `height` point at
+		// image row `bandBegin`; rows [row0, row1) are produced.  Two texels per thread: one 4-byte-aligned pair of loads per row.
+		struct TailArgs
+		{
+			const uint8_t *special; // 2 channels, may be null (no pbr wanted)
+			const uint8_t *height; // 1 channel, may be null (no normal map wanted)
+			uint8_t *pbr; // 3 channels, rows [row0, row1)
+			uint8_t *normal; // 3 channels, rows [row0, row1)
+			int w, h; // the whole image
+			int bandBegin; // image row of the first row behind `special` / `height`
+			int row0, row1;
+			float strength; // 1 / strength_ of the reference
+		};
+
+		__global__ void __launch_bounds__(256) texture_tail_kernel(const TailArgs A)
+		{
+			const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+			const size_t n = (size_t)(A.row1 - A.row0) * A.w;
+			if (i >= n)
+				return;
+			const int y = A.row0 + (int)(i / A.w);
+			const int x = (int)(i % A.w);
+			if (A.special)
+			{
+				const uint8_t *sp = A.special + ((size_t)(y - A.bandBegin) * A.w + x) * 2;
+				uint8_t *o = A.pbr + i * 3;
+				o[0] = 0;
+				o[1] = sp[0];
+				o[2] = sp[1];
+			}
+			if (A.height)
+			{
+				const int xl = x > 0 ? x - 1 : 0, xr = x + 1 < A.w ? x + 1 : A.w - 1;
+				const int yt = y > 0 ? y - 1 : 0, yb = y + 1 < A.h ? y + 1 : A.h - 1;
+				const uint8_t *rt = A.height + (size_t)(yt - A.bandBegin) * A.w;
+				const uint8_t *rc_ = A.height + (size_t)(y - A.bandBegin) * A.w;
+				const uint8_t *rb = A.height + (size_t)(yb - A.bandBegin) * A.w;
+				// Image::value on U8 (image.cpp:220-236): v / 255.f; one channel: (0 + v) / 1 == v
+				const float tl = rt[xl] / 255.f, tc = rt[x] / 255.f, tr = rt[xr] / 255.f;
+				const float lc = rc_[xl] / 255.f, rc = rc_[xr] / 255.f;
+				const float bl = rb[xl] / 255.f, bc = rb[x] / 255.f, br = rb[xr] / 255.f;
+				const float dX = (tr + 2.f * rc + br) - (tl + 2.f * lc + bl);
+				const float dY = (bl + 2.f * bc + br) - (tl + 2.f * tc + tr);
+				V3 v = normalize(v3(-dX, -dY, A.strength));
+				v = v3((v.x + 1) * 0.5f, (v.y + 1) * 0.5f, (v.z + 1) * 0.5f);
+				uint8_t *o = A.normal + i * 3;
+				o[0] = quantise_u8(v.x);
+				o[1] = quantise_u8(v.y);
+				o[2] = quantise_u8(v.z);
+			}
+		}
+
+		cudaError_t texture_tail(const TailArgs &A, cudaStream_t s)
+		{
+			const size_t n = (size_t)(A.row1 - A.row0) * A.w;
+			if (n == 0)
+				return cudaSuccess;
+			texture_tail_kernel<<<blocks_for_n(n), 256, 0, s>>>(A);
+			return cudaGetLastError();
 		}
 
 		template<int CH>
@@ -898,11 +964,15 @@ extern "C"
 		return rc;
 	}
 
-	int upg_bake_device(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, void *cuda_stream)
+	// the bake proper; outputs may be device or host memory (cudaMemcpyDefault).  dSpecial / dHeight are the images
+	// generateTextures* returns, dPbr / dNormal what the generator exports after K8; any of the four may be null.
+	static int bake_core(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, uint8_t *dPbr, uint8_t *dNormal, float normalStrength, void *cuda_stream)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
-		if (!p || !dpos || !dnrm || !duv || !didx || !dAlbedo || !dSpecial || !dHeight)
+		if (!p || !dpos || !dnrm || !duv || !didx || !dAlbedo)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (dNormal && !(normalStrength > 0))
+			return fail(UPG_ERR_ARGUMENT, "converting height to normal requires positive strength");
 		if (nidx % 3 != 0)
 			return fail(UPG_ERR_ARGUMENT, "generating texture requires triangles mesh");
 		if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull || row0 > row1 || row1 > h)
@@ -919,9 +989,11 @@ extern "C"
 			Scratch mem(s);
 			const int ach = water ? 4 : 3;
 			const int purpose = water ? MP_WATER : MP_LAND;
-			// the band: the caller's rows plus what seven dilation rounds can reach (imageDilation(img, 7), textures.cpp:73-77)
-			const uint32_t bandBegin = row0 > 7 ? row0 - 7 : 0;
-			const uint32_t bandEnd = row1 + 7 < h ? row1 + 7 : h;
+			// the band: the caller's rows plus what seven dilation rounds can reach (imageDilation(img, 7), textures.cpp:73-77),
+			// plus the one extra row of finished heights the 3x3 Sobel of the normal map reads
+			const uint32_t apron = dNormal ? 8 : 7;
+			const uint32_t bandBegin = row0 > apron ? row0 - apron : 0;
+			const uint32_t bandEnd = row1 + apron < h ? row1 + apron : h;
 			const uint32_t bandH = bandEnd - bandBegin;
 			const size_t texels = (size_t)w * bandH;
 			uint32_t *owner = mem.alloc<uint32_t>(texels);
@@ -932,6 +1004,7 @@ extern "C"
 			float *imgSpecial = mem.alloc<float>(texels * 2);
 			float *imgHeight = mem.alloc<float>(texels);
 			uint8_t *q = mem.alloc<uint8_t>(texels * (ach + 3));
+			uint8_t *qTail = (dPbr || dNormal) ? mem.alloc<uint8_t>((size_t)w * (row1 - row0) * 6) : nullptr;
 			e = mem.err;
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(owner, 0, sizeof(uint32_t) * texels, s);
@@ -1029,10 +1102,30 @@ extern "C"
 				e = dilate7(imgHeight, w, bandH, 1, qHeight, s);
 			if (e == cudaSuccess && rc == UPG_OK)
 				e = cudaMemcpyAsync(dAlbedo, qAlbedo + skip * ach, keep * ach, cudaMemcpyDefault, s);
-			if (e == cudaSuccess && rc == UPG_OK)
+			if (e == cudaSuccess && rc == UPG_OK && dSpecial)
 				e = cudaMemcpyAsync(dSpecial, qSpecial + skip * 2, keep * 2, cudaMemcpyDefault, s);
-			if (e == cudaSuccess && rc == UPG_OK)
+			if (e == cudaSuccess && rc == UPG_OK && dHeight)
 				e = cudaMemcpyAsync(dHeight, qHeight + skip, keep, cudaMemcpyDefault, s);
+			if (e == cudaSuccess && rc == UPG_OK && qTail)
+			{
+				// K8 straight from the quantised band still in HBM
+				TailArgs T;
+				T.special = dPbr ? qSpecial : nullptr;
+				T.height = dNormal ? qHeight : nullptr;
+				T.pbr = qTail;
+				T.normal = qTail + keep * 3;
+				T.w = (int)w;
+				T.h = (int)h;
+				T.bandBegin = (int)bandBegin;
+				T.row0 = (int)row0;
+				T.row1 = (int)row1;
+				T.strength = 1.f / normalStrength;
+				e = texture_tail(T, s);
+				if (e == cudaSuccess && dPbr)
+					e = cudaMemcpyAsync(dPbr, T.pbr, keep * 3, cudaMemcpyDefault, s);
+				if (e == cudaSuccess && dNormal)
+					e = cudaMemcpyAsync(dNormal, T.normal, keep * 3, cudaMemcpyDefault, s);
+			}
 			if (e == cudaSuccess)
 				e = cudaStreamSynchronize(s);
 			t_lastCovered = coveredRows;
@@ -1044,10 +1137,77 @@ extern "C"
 		return rc;
 	}
 
-	int upg_bake_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)
+	int upg_bake_device(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, void *cuda_stream)
+	{
+		if (!dSpecial || !dHeight)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		return bake_core(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, dAlbedo, dSpecial, dHeight, nullptr, nullptr, 1.f, cuda_stream);
+	}
+
+	int upg_bake_export_device(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dPbr, uint8_t *dNormal, void *cuda_stream)
+	{
+		if (!dPbr || !dNormal)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		return bake_core(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, dAlbedo, nullptr, nullptr, dPbr, dNormal, 1.f, cuda_stream);
+	}
+
+	int upg_texture_tail(int device, const uint8_t *special, const uint8_t *heightMap, uint32_t w, uint32_t h, float strength, uint8_t *pbr, uint8_t *normal)
+	{
+		if ((!special && !heightMap) || (special && !pbr) || (heightMap && !normal))
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (heightMap && !(strength > 0))
+			return fail(UPG_ERR_ARGUMENT, "converting height to normal requires positive strength");
+		if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull)
+			return fail(UPG_ERR_ARGUMENT, "bad texture resolution %u x %u", w, h);
+		cudaError_t e = cudaSetDevice(device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		{
+			cudaStream_t s = cs.compute;
+			Scratch mem(s);
+			const size_t n = (size_t)w * h;
+			uint8_t *dsp = special ? mem.alloc<uint8_t>(n * 2) : nullptr;
+			uint8_t *dh = heightMap ? mem.alloc<uint8_t>(n) : nullptr;
+			uint8_t *out = mem.alloc<uint8_t>(n * 6);
+			e = mem.err;
+			if (e == cudaSuccess && special)
+				e = cudaMemcpyAsync(dsp, special, n * 2, cudaMemcpyHostToDevice, s);
+			if (e == cudaSuccess && heightMap)
+				e = cudaMemcpyAsync(dh, heightMap, n, cudaMemcpyHostToDevice, s);
+			TailArgs T;
+			T.special = dsp;
+			T.height = dh;
+			T.pbr = out;
+			T.normal = out + n * 3;
+			T.w = (int)w;
+			T.h = (int)h;
+			T.bandBegin = 0;
+			T.row0 = 0;
+			T.row1 = (int)h;
+			T.strength = 1.f / strength;
+			if (e == cudaSuccess)
+				e = texture_tail(T, s);
+			if (e == cudaSuccess && special)
+				e = cudaMemcpyAsync(pbr, T.pbr, n * 3, cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess && heightMap)
+				e = cudaMemcpyAsync(normal, T.normal, n * 3, cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess)
+				e = cudaStreamSynchronize(s);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "upg_texture_tail");
+		}
+		cs.close();
+		return rc;
+	}
+
+	static int bake_rows_host(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *heightMap, uint8_t *pbr, uint8_t *normalMap)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
-		if (!p || !positions || !normals || !albedo || !special || !heightMap)
+		if (!p || !positions || !normals || !albedo)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
 		int rc = check_mesh(uvs, nverts, idx, nidx, w, h);
 		if (rc)
@@ -1079,10 +1239,29 @@ extern "C"
 				rc = cuda_fail(e, "upload mesh");
 			// the outputs are host memory: the core's final copies are cudaMemcpyDefault, so they land there directly
 			if (rc == UPG_OK)
-				rc = upg_bake_device(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, albedo, special, heightMap, s);
+				rc = bake_core(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, albedo, special, heightMap, pbr, normalMap, 1.f, s);
 		}
 		cs.close();
 		return rc;
+	}
+
+	int upg_bake_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)
+	{
+		if (!special || !heightMap)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		return bake_rows_host(planet, water, positions, normals, uvs, nverts, idx, nidx, w, h, row0, row1, albedo, special, heightMap, nullptr, nullptr);
+	}
+
+	int upg_bake_export_rows(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *pbr, uint8_t *normalMap)
+	{
+		if (!pbr || !normalMap)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		return bake_rows_host(planet, water, positions, normals, uvs, nverts, idx, nidx, w, h, row0, row1, albedo, nullptr, nullptr, pbr, normalMap);
+	}
+
+	int upg_bake_export(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *pbr, uint8_t *normalMap)
+	{
+		return upg_bake_export_rows(planet, water, positions, normals, uvs, nverts, idx, nidx, w, h, 0, h, albedo, pbr, normalMap);
 	}
 
 	int upg_bake(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint8_t *albedo, uint8_t *special, uint8_t *heightMap)

@@ -88,6 +88,18 @@ def dilate(img, rounds, use_nan=True, to_u8=False, device=0):
     return (img, u8) if to_u8 else img
 
 
+def texture_tail(special=None, height=None, strength=1.0, device=0):
+    """K8 alone (upg_texture_tail): special (h,w,2) u8 -> pbr (h,w,3); height (h,w[,1]) u8 -> normal map (h,w,3)."""
+    L = capi.load_library()
+    sp = None if special is None else np.ascontiguousarray(special, dtype=np.uint8)
+    hm = None if height is None else np.ascontiguousarray(height, dtype=np.uint8)
+    h, w = (sp if sp is not None else hm).shape[:2]
+    pbr = np.zeros((h, w, 3), dtype=np.uint8) if sp is not None else None
+    nm = np.zeros((h, w, 3), dtype=np.uint8) if hm is not None else None
+    capi.check(L.upg_texture_tail(device, _ptr(sp) if sp is not None else None, _ptr(hm) if hm is not None else None, w, h, strength, _ptr(pbr) if pbr is not None else None, _ptr(nm) if nm is not None else None))
+    return pbr, nm
+
+
 class Planet:
     def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0):
         L = capi.load_library()
@@ -219,6 +231,27 @@ class Planet:
         capi.check(self._lib.upg_bake_rows(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, row0, row1, _ptr(albedo), _ptr(special), _ptr(height)))
         self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
         return albedo, special, height
+
+    def bake_export(self, water, positions, normals, uvs, indices, w, h, row0=0, row1=None):
+        """bake + texture tail (upg_bake_export_rows): the three PNG payloads of a chunk -> (albedo, pbr (rows,w,3), normal map (rows,w,3))."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        row1 = h if row1 is None else row1
+        rows = row1 - row0
+        albedo = np.zeros((rows, w, 4 if water else 3), dtype=np.uint8)
+        pbr = np.zeros((rows, w, 3), dtype=np.uint8)
+        nmap = np.zeros((rows, w, 3), dtype=np.uint8)
+        capi.check(self._lib.upg_bake_export_rows(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, row0, row1, _ptr(albedo), _ptr(pbr), _ptr(nmap)))
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
+        return albedo, pbr, nmap
+
+    def bake_export_device(self, water, d_pos, d_nrm, d_uv, nverts, d_idx, nidx, w, h, row0, row1, d_albedo, d_pbr, d_normal, stream=0):
+        """upg_bake_export_device: every pointer is an integer DEVICE address; synchronises `stream` before returning."""
+        vp = C.c_void_p
+        capi.check(self._lib.upg_bake_export_device(self._h, int(bool(water)), vp(d_pos), vp(d_nrm), vp(d_uv), nverts, vp(d_idx), nidx, w, h, row0, row1, vp(d_albedo), vp(d_pbr), vp(d_normal), vp(stream)))
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
 
     def bake_device(self, water, d_pos, d_nrm, d_uv, nverts, d_idx, nidx, w, h, row0, row1, d_albedo, d_special, d_height, stream=0):
         """upg_bake_device: every pointer is an integer DEVICE address; synchronises `stream` before returning."""
