@@ -156,6 +156,32 @@ int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out);
 int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3);
 
 /*
+ * K9: the clean-up the reference applies to every extracted mesh, on the device, with the reference's vertex and triangle order.
+ * `stages` is a combination of:
+ */
+enum
+{
+	/* the tail of MarchingCubes::makeMesh (externals/cage/sources/libcore/mesh/marchingCubes.cpp:237-240): removeNonManifoldTriangles
+	 * (:28-96) and meshClip(mesh, box) (mesh/meshAlgorithms.cpp:1056-1114) including its removeUnusedVertices / meshRemoveInvalid /
+	 * meshMergeCloseVertices({}) tail */
+	UPG_MESH_MAKEMESH_TAIL = 1,
+	UPG_MESH_REMOVE_DISCONNECTED = 2, /* meshRemoveDisconnected (meshAlgorithms.cpp:1313-1333; sources/meshGeneration.cpp:41) */
+	UPG_MESH_FLIP_NORMALS = 4, /* meshFlipNormals (meshAlgorithms.cpp:313-326; sources/meshGeneration.cpp:42) */
+	UPG_MESH_WATER_CULL = 8, /* meshGenerateBaseWater's vertex culling (sources/meshGeneration.cpp:62-95); water field only */
+	UPG_MESH_GENERATOR = 15 /* everything: out3[] = what meshGenerateBaseLand / Water / Navigation return */
+};
+
+/* upg_field_meshes + K9 without the meshes leaving HBM in between: with UPG_MESH_GENERATOR the three results are the complete
+ * bodies of meshGenerateBaseLand / meshGenerateBaseWater / meshGenerateBaseNavigation (sources/meshGeneration.cpp:47-107).
+ * dmc_vertices / dmc_quads of a cleaned mesh are NULL.  UPG_ERR_EMPTY_MESH for an empty land or navigation mesh (the reference
+ * throws for those two only); an empty water mesh is a valid result. */
+int upg_field_meshes_clean(upg_planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3);
+
+/* K9 alone over a caller's triangle mesh in host memory (positions / normals: vertex_count x 3, indices: 3 per triangle);
+ * `box_size` is the clip box edge (the generator's 4000).  The water culling needs the planet: not available here. */
+int upg_mesh_clean(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float box_size, unsigned stages, upg_mesh *out);
+
+/*
  * Multi-GPU sharding of K1 + K2..K4 by z-slab ("grid sampling shards naturally by z-slab").  dualmc's scan over z in [0, res-2)
  * (dualmc.tpp:401) is split into `slab_count` contiguous ranges (upg_slab_range); slab k samples its slices plus a 3-slice halo on
  * each side ON ITS OWN DEVICE (recomputed, not exchanged) and returns the quads / triangles its scan iterations emit and the

@@ -250,3 +250,12 @@ class RefPlanet:
         normal = np.zeros((h, w, 3), dtype=np.uint8)
         self._check(self.lib.upref_texture_tail(_fp(special), _fp(height), C.c_uint32(w), C.c_uint32(h), C.c_float(strength), _fp(pbr), _fp(normal)))
         return pbr, normal
+
+    def water_cull(self, positions, normals, indices):
+        """the vertex culling of meshGenerateBaseWater (sources/meshGeneration.cpp:62-95) over a given mesh."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        p, n, i = _Buf(), _Buf(), _Buf()
+        self._check(self.lib.upref_water_cull(_fp(pos), _fp(nrm), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), C.byref(p), C.byref(n), C.byref(i)))
+        return self._take(p, np.float32, 3), self._take(n, np.float32, 3), self._take(i, np.uint32, 1)

@@ -614,4 +614,55 @@ extern "C"
 				std::memcpy(normal, hm->rawViewU8().data(), (size_t)w * h * 3);
 			});
 	}
+	// the vertex culling of meshGenerateBaseWater (sources/meshGeneration.cpp:62-95) applied to a given mesh: that translation unit
+	// drags the whole generator in, so its few lines are re-stated here over the reference's own terrainSdfElevationRaw,
+	// meshConvertToIndexed and meshRemoveInvalid
+	int upref_water_cull(const float *pos, const float *nrm, uint32_t nverts, const uint32_t *idx, uint32_t nidx, upref_buf *positions, upref_buf *normals, upref_buf *indices)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> poly = newMesh();
+				poly->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nverts));
+				poly->normals(PointerRange<const Vec3>((const Vec3 *)nrm, (const Vec3 *)nrm + nverts));
+				poly->indices(PointerRange<const uint32>(idx, idx + nidx));
+				meshConvertToIndexed(+poly);
+				std::vector<bool> valid;
+				valid.reserve(poly->verticesCount());
+				for (const Vec3 &p : poly->positions())
+					valid.push_back(unnatural::terrainSdfElevationRaw(p) < 0.1);
+				for (uint32 j = 0; j < 2; j++)
+				{
+					std::vector<bool> valid2 = valid;
+					const uint32 cnt = poly->indicesCount();
+					const auto inds = poly->indices();
+					for (uint32 i = 0; i < cnt; i += 3)
+					{
+						const uint32 is[3] = { inds[i + 0], inds[i + 1], inds[i + 2] };
+						if (valid[is[0]] || valid[is[1]] || valid[is[2]])
+							valid2[is[0]] = valid2[is[1]] = valid2[is[2]] = true;
+					}
+					std::swap(valid, valid2);
+				}
+				{
+					std::vector<Vec3> ps(poly->positions().begin(), poly->positions().end());
+					for (uint32 i = 0; i < ps.size(); i++)
+						if (!valid[i])
+							ps[i] = Vec3::Nan();
+					poly->positions(ps);
+				}
+				meshRemoveInvalid(+poly);
+				const uint32 nv = poly->verticesCount();
+				const uint32 ni = poly->indicesCount();
+				positions->count = nv;
+				positions->ptr = std::malloc(sizeof(float) * 3 * nv + 16);
+				std::memcpy(positions->ptr, poly->positions().data(), sizeof(float) * 3 * nv);
+				normals->count = poly->normals().size();
+				normals->ptr = std::malloc(sizeof(float) * 3 * nv + 16);
+				std::memcpy(normals->ptr, poly->normals().data(), sizeof(float) * 3 * poly->normals().size());
+				indices->count = ni;
+				indices->ptr = std::malloc(sizeof(uint32_t) * ni + 16);
+				std::memcpy(indices->ptr, poly->indices().data(), sizeof(uint32_t) * ni);
+			});
+	}
 }

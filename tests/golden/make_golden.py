@@ -52,7 +52,40 @@ def near_surface(ref, pts, rng, count):
     return out
 
 
+def cleanup_volume(seed=5, res=22):
+    """a dense random volume (every dualmc configuration, many components, non-manifold edges, a surface that leaves the clip
+    box everywhere) smoothed once so that components are more than single cells"""
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((res + 2, res + 2, res + 2)).astype(np.float32)
+    v = (v[1:-1, 1:-1, 1:-1] + v[2:, 1:-1, 1:-1] + v[:-2, 1:-1, 1:-1] + v[1:-1, 2:, 1:-1] + v[1:-1, :-2, 1:-1] + v[1:-1, 1:-1, 2:] + v[1:-1, 1:-1, :-2]).astype(np.float32)
+    return np.ascontiguousarray(v)
+
+
+def cleanup_fixture():
+    """mesh_cleanup.npz: the clean-up chain (makeMesh tail, meshRemoveDisconnected, meshFlipNormals, water culling) on inputs the
+    planet grids do not reach; python tests/golden/make_golden.py cleanup = only this"""
+    d = {}
+    g = cleanup_volume()
+    ref = RefPlanet(init=False)
+    d["volume"] = g
+    d["mesh_positions"], d["mesh_normals"], d["mesh_indices"] = ref.make_mesh(g)
+    d["final_positions"], d["final_normals"], d["final_indices"] = ref.make_mesh(g, remove_disconnected=True, flip=True)
+    # the water mesh of a small planet through meshGenerateBaseWater's culling
+    ref = RefPlanet(shape="sphere", elevation="lakes")
+    w = ref.grid("water", 44)
+    fp, fn, fi = ref.make_mesh(w, remove_disconnected=True, flip=True)
+    d["water_grid"] = w
+    d["water_positions"], d["water_normals"], d["water_indices"] = ref.water_cull(fp, fn, fi)
+    d["water_elevation_raw"] = ref.eval("elevraw", fp)
+    d["water_before_cull_vertices"] = np.array([len(fp)], dtype=np.uint32)
+    np.savez_compressed(os.path.join(OUT, "mesh_cleanup.npz"), **d)
+    print("cleanup: volume mesh tris", len(d["mesh_indices"]) // 3, "final", len(d["final_indices"]) // 3, "water", len(fi) // 3, "->", len(d["water_indices"]) // 3)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "cleanup":
+        return cleanup_fixture()
+    cleanup_fixture()
     pts = probe_points()
     np.save(os.path.join(OUT, "probe_points.npy"), pts)
 

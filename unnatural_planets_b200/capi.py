@@ -63,6 +63,9 @@ class Tile(C.Structure):
     ]
 
 
+# K9 stages (include/upg.h UPG_MESH_*)
+MESH_MAKEMESH_TAIL, MESH_REMOVE_DISCONNECTED, MESH_FLIP_NORMALS, MESH_WATER_CULL, MESH_GENERATOR = 1, 2, 4, 8, 15
+
 PURPOSES = {"land": 1, "water": 2, "navigation": 3}
 TILE_COLUMNS = ("albedo_r", "albedo_g", "albedo_b", "roughness", "metallic", "height", "elevation", "slope", "temperature", "precipitation", "opacity", "biome", "type")
 
@@ -101,6 +104,8 @@ def load_library():
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_fields_samples_device.argtypes = [vp, i32, i32, fp, fp, fp, vp]
     L.upg_field_meshes.argtypes = [vp, C.c_uint, C.POINTER(Mesh)]
+    L.upg_field_meshes_clean.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(Mesh)]
+    L.upg_mesh_clean.argtypes = [i32, fp, fp, C.c_uint32, fp, C.c_uint32, C.c_float, C.c_uint, C.POINTER(Mesh)]
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
     L.upg_field_mesh.argtypes = [vp, i32, C.POINTER(Mesh)]
     L.upg_field_mesh_slab.argtypes = [vp, i32, i32, i32, C.POINTER(Mesh)]

@@ -523,7 +523,7 @@ namespace upg
 	static int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
 	{
 		// a slab result only hands out the blocks it owns (DmcResult::first* / owned*); a whole volume owns everything
-		const uint64_t nv = r.ownedVertices, nq = r.ownedQuads, ni = (uint64_t)r.ownedTriangles * 3;
+		const uint64_t nv = r.ownedVertices, nq = r.quads ? r.ownedQuads : 0, ni = (uint64_t)r.ownedTriangles * 3;
 		const uint64_t v0 = (uint64_t)r.firstVertex * 3, q0 = (uint64_t)r.firstQuad * 4, i0 = (uint64_t)r.firstTriangle * 3;
 		const uint64_t bytes = sizeof(float) * nv * 9 + sizeof(uint32_t) * (ni + nq * 4);
 		char *block = nullptr;
@@ -540,15 +540,17 @@ namespace upg
 		p += sizeof(float) * nv * 3;
 		out->indices = (uint32_t *)p;
 		p += sizeof(uint32_t) * ni;
-		out->dmc_quads = (uint32_t *)p;
+		out->dmc_quads = nq ? (uint32_t *)p : nullptr;
 		if (nv)
 		{
 			e = cudaMemcpyAsync(out->positions, r.positions + v0, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(out->normals, r.normals + v0, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
-			if (e == cudaSuccess)
+			if (e == cudaSuccess && r.rawVertices)
 				e = cudaMemcpyAsync(out->dmc_vertices, r.rawVertices + v0, sizeof(float) * nv * 3, cudaMemcpyDeviceToHost, s);
 		}
+		if (!r.rawVertices)
+			out->dmc_vertices = nullptr; // a cleaned mesh (K9) has no dualmc counterpart
 		if (e == cudaSuccess && ni)
 			e = cudaMemcpyAsync(out->indices, r.indices + i0, sizeof(uint32_t) * ni, cudaMemcpyDeviceToHost, s);
 		if (e == cudaSuccess && nq)
@@ -637,12 +639,14 @@ extern "C"
 		return rc;
 	}
 
-	int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3)
+	static int field_meshes_impl(upg_planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !out3)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
 		std::memset(out3, 0, sizeof(upg_mesh) * 3);
+		if (stages & ~(unsigned)UPG_MESH_GENERATOR)
+			return fail(UPG_ERR_ARGUMENT, "bad clean-up stages %#x", stages);
 		if ((field_mask & 7u) == 0 || (field_mask & ~7u))
 			return fail(UPG_ERR_ARGUMENT, "bad field mask %#x (bit 0 land, bit 1 water, bit 2 navigation)", field_mask);
 		cudaError_t e = cudaSetDevice(p->device);
@@ -720,8 +724,20 @@ extern "C"
 						DmcResult d;
 						if (r == UPG_OK)
 							r = dmc_extract(dens[f], res, res, res, p->boxSize, res, ws.compute, d);
-						if (r == UPG_OK && d.triangleCount == 0)
-							r = fail(UPG_ERR_EMPTY_MESH, "generated empty mesh (field %d)", f);
+						if (r == UPG_OK && stages)
+						{
+							// K9 on the arrays still in HBM; the water culling belongs to the water mesh alone (sources/meshGeneration.cpp:57-98)
+							DmcResult c;
+							r = mesh_clean(p, d.positions, d.normals, d.vertexCount, d.indices, d.triangleCount, p->boxSize, f == FD_WATER ? stages : (stages & ~(unsigned)UPG_MESH_WATER_CULL), ws.compute, c);
+							c.nearZeroSamples = d.nearZeroSamples;
+							dmc_release(d, ws.compute);
+							d = c;
+							if (r == UPG_OK)
+								r = check_status(p, ws.compute, "upg_field_meshes_clean");
+						}
+						// the reference throws for an empty land / navigation mesh only (sources/meshGeneration.cpp:51-52, 104-105)
+						if (r == UPG_OK && d.triangleCount == 0 && !(stages && f == FD_WATER))
+							r = fail(UPG_ERR_EMPTY_MESH, "generated empty base %s mesh", f == FD_LAND ? "land" : f == FD_WATER ? "water" : "navigation");
 						if (r == UPG_OK)
 							r = mesh_to_host(d, ws.compute, &out3[f]);
 						dmc_release(d, ws.compute);
@@ -752,6 +768,74 @@ extern "C"
 		if (rc != UPG_OK)
 			for (int f = 0; f < 3; f++)
 				upg_mesh_free(&out3[f]);
+		return rc;
+	}
+
+	int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3)
+	{
+		return field_meshes_impl(planet, field_mask, 0, out3);
+	}
+
+	int upg_field_meshes_clean(upg_planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3)
+	{
+		if (stages == 0)
+			return fail(UPG_ERR_ARGUMENT, "no clean-up stage requested");
+		return field_meshes_impl(planet, field_mask, stages, out3);
+	}
+
+	int upg_mesh_clean(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float box_size, unsigned stages, upg_mesh *out)
+	{
+		if (!out)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		std::memset(out, 0, sizeof(*out));
+		if ((!positions || !normals) && vertex_count)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (!indices && index_count)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (index_count % 3 != 0)
+			return fail(UPG_ERR_ARGUMENT, "the clean-up requires a triangle mesh");
+		if (stages == 0 || (stages & ~(unsigned)(UPG_MESH_MAKEMESH_TAIL | UPG_MESH_REMOVE_DISCONNECTED | UPG_MESH_FLIP_NORMALS)))
+			return fail(UPG_ERR_ARGUMENT, "bad clean-up stages %#x (the water culling needs a planet: upg_field_meshes_clean)", stages);
+		for (uint32_t i = 0; i < index_count; i++)
+			if (indices[i] >= vertex_count)
+				return fail(UPG_ERR_ARGUMENT, "index %u out of range (%u vertices)", indices[i], vertex_count);
+		cudaError_t e = cudaSetDevice(device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		cudaStream_t s = cs.compute;
+		float *dp = nullptr, *dn = nullptr;
+		uint32_t *di = nullptr;
+		e = cudaMallocAsync((void **)&dp, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
+		if (e == cudaSuccess)
+			e = cudaMallocAsync((void **)&dn, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
+		if (e == cudaSuccess)
+			e = cudaMallocAsync((void **)&di, sizeof(uint32_t) * (index_count ? index_count : 1), s);
+		if (e == cudaSuccess && vertex_count)
+			e = cudaMemcpyAsync(dp, positions, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess && vertex_count)
+			e = cudaMemcpyAsync(dn, normals, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess && index_count)
+			e = cudaMemcpyAsync(di, indices, sizeof(uint32_t) * index_count, cudaMemcpyHostToDevice, s);
+		if (e != cudaSuccess)
+			rc = cuda_fail(e, "upload mesh");
+		DmcResult r;
+		if (rc == UPG_OK)
+			rc = mesh_clean(nullptr, dp, dn, vertex_count, di, index_count / 3, box_size, stages, s, r);
+		if (rc == UPG_OK)
+			rc = mesh_to_host(r, s, out);
+		dmc_release(r, s);
+		if (dp)
+			cudaFreeAsync(dp, s);
+		if (dn)
+			cudaFreeAsync(dn, s);
+		if (di)
+			cudaFreeAsync(di, s);
+		cudaStreamSynchronize(s);
+		cs.close();
 		return rc;
 	}
 

@@ -71,6 +71,10 @@ namespace upg
 	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset = 0, int ownZ0 = 0, int ownZ1 = 0x7fffffff);
 	void dmc_release(DmcResult &r, cudaStream_t s);
 
+	// K9 (upg_meshfix.cu): the clean-up chain of makeMesh / meshGenerateGeneric / meshGenerateBaseWater over device arrays; `stages` are
+	// the UPG_MESH_* bits of include/upg.h.  `out` receives fresh pool arrays (positions, normals, indices; no dualmc arrays).
+	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out);
+
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
 	int check_status(Planet *planet, cudaStream_t stream, const char *what);
 }

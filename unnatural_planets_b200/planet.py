@@ -24,7 +24,7 @@ def _mesh_to_numpy(lib, m):
     nv, ni, nq = m.vertex_count, m.index_count, m.quad_count
 
     def take(ptr, count, dtype):
-        if count == 0:
+        if count == 0 or not ptr:  # a cleaned mesh (K9) carries no dualmc arrays
             return np.zeros(0, dtype=dtype)
         return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
 
@@ -86,6 +86,17 @@ def dilate(img, rounds, use_nan=True, to_u8=False, device=0):
     u8 = np.zeros((h, w, ch), dtype=np.uint8) if to_u8 else None
     capi.check(L.upg_dilate(device, _ptr(img), w, h, ch, rounds, int(use_nan), _ptr(u8) if to_u8 else None))
     return (img, u8) if to_u8 else img
+
+
+def mesh_clean(positions, normals, indices, box=4000.0, stages=7, device=0):
+    """K9 alone (upg_mesh_clean) over a host triangle mesh -> dict(positions, normals, indices); stages = capi.MESH_* bits."""
+    L = capi.load_library()
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    m = capi.Mesh()
+    capi.check(L.upg_mesh_clean(device, _ptr(pos), _ptr(nrm), len(pos), _ptr(idx), len(idx), box, stages, C.byref(m)))
+    return _mesh_to_numpy(L, m)
 
 
 def texture_tail(special=None, height=None, strength=1.0, device=0):
@@ -177,6 +188,18 @@ class Planet:
         m = capi.Mesh()
         capi.check(self._lib.upg_field_mesh(self._h, capi.FIELDS[field], C.byref(m)))
         return _mesh_to_numpy(self._lib, m)
+
+    def field_meshes_clean(self, fields=("land", "water", "navigation"), stages=capi.MESH_GENERATOR):
+        """upg_field_meshes_clean: fused sampling + extraction + K9 clean-up; with MESH_GENERATOR the results are what
+        meshGenerateBaseLand / Water / Navigation return (sources/meshGeneration.cpp:47-107)."""
+        ms = (capi.Mesh * 3)()
+        mask = 0
+        for f in fields:
+            if capi.FIELDS[f] > 2:
+                raise ValueError("field_meshes_clean: land, water and navigation only")
+            mask |= 1 << capi.FIELDS[f]
+        capi.check(self._lib.upg_field_meshes_clean(self._h, mask, stages, ms))
+        return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
 
     def field_mesh_slab(self, field, slab, slab_count):
         """slab `slab` of `slab_count` of field_mesh() (upg_field_mesh_slab): indices / dmc_quads are relative to the slab's
