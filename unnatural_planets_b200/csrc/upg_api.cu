@@ -722,8 +722,15 @@ extern "C"
 								r = cuda_fail(ee, "cudaStreamWaitEvent");
 						}
 						DmcResult d;
+						const double w0 = trace ? now_ms() : 0;
+						double w1 = 0, w2 = 0;
 						if (r == UPG_OK)
 							r = dmc_extract(dens[f], res, res, res, p->boxSize, res, ws.compute, d);
+						if (trace)
+						{
+							cudaStreamSynchronize(ws.compute);
+							w1 = now_ms();
+						}
 						if (r == UPG_OK && stages)
 						{
 							// K9 on the arrays still in HBM; the water culling belongs to the water mesh alone (sources/meshGeneration.cpp:57-98)
@@ -738,8 +745,15 @@ extern "C"
 						// the reference throws for an empty land / navigation mesh only (sources/meshGeneration.cpp:51-52, 104-105)
 						if (r == UPG_OK && d.triangleCount == 0 && !(stages && f == FD_WATER))
 							r = fail(UPG_ERR_EMPTY_MESH, "generated empty base %s mesh", f == FD_LAND ? "land" : f == FD_WATER ? "water" : "navigation");
+						if (trace)
+						{
+							cudaStreamSynchronize(ws.compute);
+							w2 = now_ms();
+						}
 						if (r == UPG_OK)
 							r = mesh_to_host(d, ws.compute, &out3[f]);
+						if (trace)
+							std::fprintf(stderr, "[upg]   field %d: extract %.2f ms, clean-up %.2f ms, download %.2f ms (%u vertices, %u triangles)\n", f, w1 - w0, w2 - w1, now_ms() - w2, d.vertexCount, d.triangleCount);
 						dmc_release(d, ws.compute);
 						if (ws.compute)
 							cudaStreamSynchronize(ws.compute);

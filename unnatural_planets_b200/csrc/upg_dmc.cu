@@ -49,6 +49,9 @@ namespace upg
 			__host__ __device__ int32_t cy() const { return ry - 1; }
 			__host__ __device__ int32_t cz() const { return rz - 1; }
 			__host__ __device__ uint64_t cells() const { return (uint64_t)cx() * cy() * cz(); }
+			// the 1-byte cell codes are stored with rows padded to a multiple of 4 so that four codes move as one aligned word
+			__host__ __device__ int32_t codePitch() const { return (cx() + 3) & ~3; }
+			__host__ __device__ uint64_t rows() const { return (uint64_t)cy() * cz(); }
 		};
 
 		__device__ __forceinline__ uint64_t sample_index(const Dims &d, int32_t x, int32_t y, int32_t z)
@@ -58,6 +61,10 @@ namespace upg
 		__device__ __forceinline__ uint32_t cell_index(const Dims &d, int32_t x, int32_t y, int32_t z)
 		{
 			return (uint32_t)(((uint64_t)z * d.cy() + y) * d.cx() + x);
+		}
+		__device__ __forceinline__ uint64_t code_index(const Dims &d, int32_t x, int32_t y, int32_t z)
+		{
+			return ((uint64_t)z * d.cy() + y) * (uint32_t)d.codePitch() + x;
 		}
 		__device__ __forceinline__ void cell_coords(const Dims &d, uint32_t L, int32_t &x, int32_t &y, int32_t &z)
 		{
@@ -85,113 +92,199 @@ namespace upg
 		}
 
 		// ---- pass 1: cell codes ---------------------------------------------------------------------------
-		__global__ void __launch_bounds__(DMC_BLOCK) dmc_cell_codes(const float *__restrict__ dens, Dims d, uint8_t *__restrict__ codes, uint32_t *__restrict__ blockQuads, unsigned long long *__restrict__ nearZero, float nearTol)
+		// Both dense passes are bandwidth work (4 B read per cell here, 1 B per cell in pass 2) and were instruction bound as
+		// one-thread-per-cell kernels (profiles/r01_b: 80-90 % issue active at < 10 % of HBM).  Now one block walks one ROW of
+		// cells (fixed y, z) and a thread handles four consecutive cells: five samples from each of the four sample rows that
+		// bound the cell row (one 16-byte load + one scalar each), five sign tests per row instead of eight per cell, four codes
+		// stored as one word.  Rows are visited in scan order, so per-row quad counts scan into ordered offsets as before.
+		constexpr int DMC_ROW_MAX_THREADS = 256;
+
+		// sign bits of samples x0 .. x0+4 of one sample row; `near` = how many of the first four (those that are cell origins,
+		// x < cx) lie within `tol` of zero
+		__device__ __forceinline__ uint32_t sign_bits5(const float *__restrict__ row, int32_t x0, int32_t rx, bool vec, float tol, uint32_t &near)
 		{
-			const uint64_t L = (uint64_t)blockIdx.x * DMC_BLOCK + threadIdx.x;
-			uint32_t nq = 0, nz = 0;
-			if (L < d.cells())
+			float v[5];
+			if (vec)
 			{
-				int32_t x, y, z;
-				cell_coords(d, (uint32_t)L, x, y, z);
-				const uint64_t s = sample_index(d, x, y, z);
-				const uint64_t sy = (uint64_t)d.rx, sz = (uint64_t)d.rx * d.ry;
-				// getCellCode: bit set when the sample is >= iso (iso = 0); corner id = x + 2y + 4z
-				const float v0 = __ldg(dens + s);
-				uint32_t code = 0;
-				code |= v0 >= 0.0f ? 1u : 0u;
-				code |= __ldg(dens + s + 1) >= 0.0f ? 2u : 0u;
-				code |= __ldg(dens + s + sy) >= 0.0f ? 4u : 0u;
-				code |= __ldg(dens + s + sy + 1) >= 0.0f ? 8u : 0u;
-				code |= __ldg(dens + s + sz) >= 0.0f ? 16u : 0u;
-				code |= __ldg(dens + s + sz + 1) >= 0.0f ? 32u : 0u;
-				code |= __ldg(dens + s + sz + sy) >= 0.0f ? 64u : 0u;
-				code |= __ldg(dens + s + sz + sy + 1) >= 0.0f ? 128u : 0u;
-				codes[L] = (uint8_t)code;
-				nq = __popc(quad_mask(d, x, y, z, code));
-				nz = fabsf(v0) < nearTol ? 1u : 0u;
+				const float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
+				v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+				v[4] = x0 + 4 < rx ? __ldg(row + x0 + 4) : -1.0f;
 			}
-			// block totals (warp shuffle, then one shared-memory hop)
-			__shared__ uint32_t sq[DMC_BLOCK / 32], sn[DMC_BLOCK / 32];
+			else
+			{
+#pragma unroll
+				for (int k = 0; k < 5; k++)
+					v[k] = x0 + k < rx ? __ldg(row + x0 + k) : -1.0f;
+			}
+			uint32_t bits = 0;
+			near = 0;
+#pragma unroll
+			for (int k = 0; k < 5; k++)
+			{
+				bits |= (v[k] >= 0.0f ? 1u : 0u) << k; // getCellCode: bit set when the sample is >= iso (iso = 0)
+				if (k < 4 && x0 + k < rx - 1)
+					near += fabsf(v[k]) < tol ? 1u : 0u;
+			}
+			return bits;
+		}
+
+		// block-wide sum of two counters; valid in thread 0
+		__device__ __forceinline__ void block_sum2(uint32_t &a, uint32_t &b)
+		{
+			__shared__ uint32_t sa[DMC_ROW_MAX_THREADS / 32], sb[DMC_ROW_MAX_THREADS / 32];
 			for (int o = 16; o > 0; o >>= 1)
 			{
-				nq += __shfl_down_sync(0xffffffffu, nq, o);
-				nz += __shfl_down_sync(0xffffffffu, nz, o);
+				a += __shfl_down_sync(0xffffffffu, a, o);
+				b += __shfl_down_sync(0xffffffffu, b, o);
 			}
 			if ((threadIdx.x & 31) == 0)
 			{
-				sq[threadIdx.x >> 5] = nq;
-				sn[threadIdx.x >> 5] = nz;
+				sa[threadIdx.x >> 5] = a;
+				sb[threadIdx.x >> 5] = b;
 			}
 			__syncthreads();
 			if (threadIdx.x == 0)
 			{
-				uint32_t tq = 0, tn = 0;
-				for (int i = 0; i < DMC_BLOCK / 32; i++)
+				a = b = 0;
+				for (uint32_t i = 0; i < (blockDim.x + 31) / 32; i++)
 				{
-					tq += sq[i];
-					tn += sn[i];
+					a += sa[i];
+					b += sb[i];
 				}
-				blockQuads[blockIdx.x] = tq;
-				if (tn)
-					atomicAdd(nearZero, (unsigned long long)tn);
+			}
+		}
+
+		__global__ void __launch_bounds__(DMC_ROW_MAX_THREADS) dmc_cell_codes(const float *__restrict__ dens, Dims d, uint8_t *__restrict__ codes, uint32_t *__restrict__ rowQuads, unsigned long long *__restrict__ nearZero, float nearTol)
+		{
+			const uint32_t row = blockIdx.x;
+			const int32_t z = (int32_t)(row / (uint32_t)d.cy()), y = (int32_t)(row - (uint32_t)z * (uint32_t)d.cy());
+			const int32_t cx = d.cx();
+			const float *r00 = dens + sample_index(d, 0, y, z);
+			const float *r01 = r00 + d.rx; // y + 1
+			const float *r10 = r00 + (uint64_t)d.rx * d.ry; // z + 1
+			const float *r11 = r10 + d.rx;
+			// 16-byte loads need rows that start on 16-byte boundaries
+			const bool vec = (d.rx & 3) == 0 && (reinterpret_cast<uintptr_t>(dens) & 15) == 0;
+			uint32_t *codeWords = reinterpret_cast<uint32_t *>(codes + (uint64_t)row * (uint32_t)d.codePitch());
+			uint32_t nq = 0, nz = 0;
+			for (int32_t x0 = (int32_t)threadIdx.x * 4; x0 < cx; x0 += (int32_t)blockDim.x * 4)
+			{
+				uint32_t near, unused;
+				const uint32_t s00 = sign_bits5(r00, x0, d.rx, vec, nearTol, near);
+				const uint32_t s01 = sign_bits5(r01, x0, d.rx, vec, nearTol, unused);
+				const uint32_t s10 = sign_bits5(r10, x0, d.rx, vec, nearTol, unused);
+				const uint32_t s11 = sign_bits5(r11, x0, d.rx, vec, nearTol, unused);
+				nz += near; // samples within tolerance of zero: where sign / topology parity with a CPU run is not promised
+				uint32_t word = 0;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					if (x0 + k >= cx)
+						break;
+					// corner id = x + 2y + 4z
+					const uint32_t code = ((s00 >> k) & 3u) | (((s01 >> k) & 3u) << 2) | (((s10 >> k) & 3u) << 4) | (((s11 >> k) & 3u) << 6);
+					word |= code << (8 * k);
+					nq += __popc(quad_mask(d, x0 + k, y, z, code));
+				}
+				codeWords[x0 >> 2] = word;
+			}
+			block_sum2(nq, nz);
+			if (threadIdx.x == 0)
+			{
+				rowQuads[row] = nq;
+				if (nz)
+					atomicAdd(nearZero, (unsigned long long)nz);
 			}
 		}
 
 		// ---- pass 2: ordered quad compaction ----------------------------------------------------------------
 		// quadCell[q] = linear cell index of the anchoring grid point, quadInfo[q] = axis | firstOrder << 2
-		__global__ void __launch_bounds__(DMC_BLOCK) dmc_emit_quads(Dims d, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ blockOffsets, uint32_t *__restrict__ quadCell, uint8_t *__restrict__ quadInfo, uint32_t *__restrict__ quadBase)
+		__global__ void __launch_bounds__(DMC_ROW_MAX_THREADS) dmc_emit_quads(Dims d, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ rowOffsets, const uint32_t *__restrict__ rowQuads, uint32_t *__restrict__ quadCell, uint8_t *__restrict__ quadInfo, uint32_t *__restrict__ quadBase)
 		{
-			const uint64_t L = (uint64_t)blockIdx.x * DMC_BLOCK + threadIdx.x;
-			uint32_t mask = 0, code = 0;
-			if (L < d.cells())
-			{
-				int32_t x, y, z;
-				cell_coords(d, (uint32_t)L, x, y, z);
-				code = codes[L];
-				mask = quad_mask(d, x, y, z, code);
-			}
-			const uint32_t nq = __popc(mask);
-			// exclusive prefix inside the block
-			uint32_t incl = nq;
-			const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-				if (lane >= (uint32_t)o)
-					incl += t;
-			}
-			__shared__ uint32_t warpSum[DMC_BLOCK / 32];
-			if (lane == 31)
-				warpSum[warp] = incl;
+			const uint32_t row = blockIdx.x;
+			if (rowQuads[row] == 0)
+				return; // nothing to emit in this row (the vast majority): 4 bytes read
+			const int32_t z = (int32_t)(row / (uint32_t)d.cy()), y = (int32_t)(row - (uint32_t)z * (uint32_t)d.cy());
+			const int32_t cx = d.cx();
+			const uint32_t *codeWords = reinterpret_cast<const uint32_t *>(codes + (uint64_t)row * (uint32_t)d.codePitch());
+			const uint32_t rowL = row * (uint32_t)cx; // linear index of the row's first cell
+			__shared__ uint32_t warpSum[DMC_ROW_MAX_THREADS / 32];
+			__shared__ uint32_t carry;
+			if (threadIdx.x == 0)
+				carry = rowOffsets[row];
 			__syncthreads();
-			uint32_t base = blockOffsets[blockIdx.x];
-			for (uint32_t w = 0; w < warp; w++)
-				base += warpSum[w];
-			uint32_t q = base + incl - nq;
-			if (nq)
+			const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) / 32;
+			for (int32_t c0 = 0; c0 < cx; c0 += (int32_t)blockDim.x * 4)
 			{
-				quadBase[L] = q;
-				const uint32_t b0 = code & 1u;
-				// x edge: entering (first sample < iso, second >= iso) keeps (i0,i1,i2,i3); y and z edges keep it when
-				// exiting (dualmc.tpp:415-419, 434-438, 453-457).  entering <=> b0 == 0
-				if (mask & 1u)
+				const int32_t x0 = c0 + (int32_t)threadIdx.x * 4;
+				uint32_t word = 0, masks = 0, nq = 0;
+				if (x0 < cx)
 				{
-					quadCell[q] = (uint32_t)L;
-					quadInfo[q] = (uint8_t)(0u | ((b0 == 0u ? 1u : 0u) << 2));
-					q++;
+					word = __ldg(codeWords + (x0 >> 2));
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+					{
+						if (x0 + k >= cx)
+							break;
+						const uint32_t m = quad_mask(d, x0 + k, y, z, (word >> (8 * k)) & 0xffu);
+						masks |= m << (4 * k);
+						nq += __popc(m);
+					}
 				}
-				if (mask & 2u)
+				// exclusive prefix inside the block, in x order
+				uint32_t incl = nq;
+				for (int o = 1; o < 32; o <<= 1)
 				{
-					quadCell[q] = (uint32_t)L;
-					quadInfo[q] = (uint8_t)(1u | ((b0 == 1u ? 1u : 0u) << 2));
-					q++;
+					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+					if (lane >= (uint32_t)o)
+						incl += t;
 				}
-				if (mask & 4u)
+				if (lane == 31)
+					warpSum[warp] = incl;
+				__syncthreads();
+				uint32_t base = carry;
+				for (uint32_t w = 0; w < warp; w++)
+					base += warpSum[w];
+				uint32_t q = base + incl - nq;
+#pragma unroll
+				for (int k = 0; k < 4; k++)
 				{
-					quadCell[q] = (uint32_t)L;
-					quadInfo[q] = (uint8_t)(2u | ((b0 == 1u ? 1u : 0u) << 2));
-					q++;
+					const uint32_t mask = (masks >> (4 * k)) & 7u;
+					if (!mask)
+						continue;
+					const uint32_t L = rowL + (uint32_t)(x0 + k);
+					const uint32_t b0 = (word >> (8 * k)) & 1u;
+					quadBase[L] = q;
+					// x edge: entering (first sample < iso, second >= iso) keeps (i0,i1,i2,i3); y and z edges keep it when
+					// exiting (dualmc.tpp:415-419, 434-438, 453-457).  entering <=> b0 == 0
+					if (mask & 1u)
+					{
+						quadCell[q] = L;
+						quadInfo[q] = (uint8_t)(0u | ((b0 == 0u ? 1u : 0u) << 2));
+						q++;
+					}
+					if (mask & 2u)
+					{
+						quadCell[q] = L;
+						quadInfo[q] = (uint8_t)(1u | ((b0 == 1u ? 1u : 0u) << 2));
+						q++;
+					}
+					if (mask & 4u)
+					{
+						quadCell[q] = L;
+						quadInfo[q] = (uint8_t)(2u | ((b0 == 1u ? 1u : 0u) << 2));
+						q++;
+					}
 				}
+				__syncthreads();
+				if (threadIdx.x == 0)
+				{
+					uint32_t total = 0;
+					for (uint32_t w = 0; w < warps; w++)
+						total += warpSum[w];
+					carry += total;
+				}
+				__syncthreads();
 			}
 		}
 
@@ -211,7 +304,7 @@ namespace upg
 		// getDualPointCode (dualmc.tpp:37-86) with generateManifold = true
 		__device__ __forceinline__ uint32_t dual_point_code(const Dims &d, const uint8_t *__restrict__ codes, int32_t cx, int32_t cy, int32_t cz, uint32_t edgeBit)
 		{
-			uint32_t code = codes[cell_index(d, cx, cy, cz)];
+			uint32_t code = codes[code_index(d, cx, cy, cz)];
 			const uint32_t dir = c_problematic[code];
 			if (dir != 255u)
 			{
@@ -221,7 +314,7 @@ namespace upg
 				const int32_t lim = (comp == 0 ? d.rx : comp == 1 ? d.ry : d.rz) - 1;
 				if (n[comp] >= 0 && n[comp] < lim)
 				{
-					const uint32_t ncode = codes[cell_index(d, n[0], n[1], n[2])];
+					const uint32_t ncode = codes[code_index(d, n[0], n[1], n[2])];
 					if (c_problematic[ncode] != 255u)
 						code ^= 0xffu;
 				}
@@ -397,7 +490,7 @@ namespace upg
 		__device__ __forceinline__ uint32_t quad_lookup(const Dims &d, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ quadBase, int32_t bx, int32_t by, int32_t bz, uint32_t axis)
 		{
 			const uint32_t L = cell_index(d, bx, by, bz);
-			const uint32_t mask = quad_mask(d, bx, by, bz, codes[L]);
+			const uint32_t mask = quad_mask(d, bx, by, bz, codes[code_index(d, bx, by, bz)]);
 			return quadBase[L] + __popc(mask & ((1u << axis) - 1u));
 		}
 
@@ -655,7 +748,10 @@ namespace upg
 		const uint64_t cells = d.cells();
 		if (cells >= (1ull << 32))
 			return fail(UPG_ERR_ARGUMENT, "volume too large (cell index must fit 32 bits)");
-		const uint32_t blocks = (uint32_t)((cells + DMC_BLOCK - 1) / DMC_BLOCK);
+		// the dense passes run one block per row of cells, a thread per four cells
+		const uint32_t blocks = (uint32_t)d.rows();
+		int rowThreads = ((d.cx() + 3) / 4 + 31) / 32 * 32;
+		rowThreads = rowThreads > DMC_ROW_MAX_THREADS ? DMC_ROW_MAX_THREADS : rowThreads;
 
 		uint8_t *codes = nullptr;
 		uint32_t *blockQuads = nullptr, *blockOffsets = nullptr, *quadBase = nullptr;
@@ -681,7 +777,7 @@ namespace upg
 			e = cudaGetLastError(); \
 	} while (0)
 
-		UPG_TRY(dalloc(&codes, cells, s));
+		UPG_TRY(dalloc(&codes, d.rows() * (uint64_t)d.codePitch(), s));
 		UPG_TRY(dalloc(&blockQuads, blocks, s));
 		UPG_TRY(dalloc(&blockOffsets, blocks, s));
 		UPG_TRY(dalloc(&quadBase, cells, s));
@@ -689,7 +785,7 @@ namespace upg
 		UPG_TRY(cudaMemsetAsync(nearZero, 0, sizeof(unsigned long long), s));
 		if (e == cudaSuccess)
 		{
-			dmc_cell_codes<<<blocks, DMC_BLOCK, 0, s>>>(dens, d, codes, blockQuads, nearZero, 1e-3f);
+			dmc_cell_codes<<<blocks, rowThreads, 0, s>>>(dens, d, codes, blockQuads, nearZero, 1e-3f);
 			UPG_LAUNCHED();
 		}
 		UPG_TRY(exclusive_scan_u32(blockQuads, blockOffsets, blocks, s));
@@ -712,7 +808,7 @@ namespace upg
 			UPG_TRY(dalloc(&vids, nSlots, s));
 			if (e == cudaSuccess)
 			{
-				dmc_emit_quads<<<blocks, DMC_BLOCK, 0, s>>>(d, codes, blockOffsets, quadCell, quadInfo, quadBase);
+				dmc_emit_quads<<<blocks, rowThreads, 0, s>>>(d, codes, blockOffsets, blockQuads, quadCell, quadInfo, quadBase);
 				UPG_LAUNCHED();
 			}
 			const uint32_t slotBlocks = (nSlots + DMC_BLOCK - 1) / DMC_BLOCK;

@@ -4,6 +4,7 @@ explicit seed the reference lacks."""
 from __future__ import annotations
 
 import ctypes as C
+import time
 
 import numpy as np
 
@@ -180,7 +181,9 @@ class Planet:
             if capi.FIELDS[f] > 2:
                 raise ValueError("field_meshes: land, water and navigation only")
             mask |= 1 << capi.FIELDS[f]
+        t = time.perf_counter()
         capi.check(self._lib.upg_field_meshes(self._h, mask, ms))
+        self.last_call_s = time.perf_counter() - t
         return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
 
     def field_mesh(self, field="land"):
@@ -198,7 +201,9 @@ class Planet:
             if capi.FIELDS[f] > 2:
                 raise ValueError("field_meshes_clean: land, water and navigation only")
             mask |= 1 << capi.FIELDS[f]
+        t = time.perf_counter()
         capi.check(self._lib.upg_field_meshes_clean(self._h, mask, stages, ms))
+        self.last_call_s = time.perf_counter() - t  # the C call alone (the numpy copies below are the binding's, not the library's)
         return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
 
     def field_mesh_slab(self, field, slab, slab_count):
