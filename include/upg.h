@@ -193,6 +193,30 @@ int upg_mesh_clean(int device, const float *positions, const float *normals, uin
 void upg_slab_range(int grid_resolution, int slab, int slab_count, int *z0, int *z1);
 int upg_field_mesh_slab(upg_planet *planet, int field, int slab, int slab_count, upg_mesh *out);
 
+/* all requested fields of one slab from ONE fused K1 pass over the slab's slices (upg_field_meshes restricted to slab k): each
+ * out3[field] equals upg_field_mesh_slab(field, slab, slab_count) */
+int upg_field_meshes_slab(upg_planet *planet, unsigned field_mask, int slab, int slab_count, upg_mesh *out3);
+
+/* the same with the result left in HBM, for callers that gather the slab chunks device to device (NCCL over NVLink) instead of
+ * through host memory.  Pointers are device memory on `device`, valid until upg_device_mesh_free(); the work that filled them has
+ * completed when the call returns. */
+typedef struct upg_device_mesh
+{
+	float *positions; /* vertex_count x 3 */
+	float *normals; /* vertex_count x 3 */
+	uint32_t *indices; /* index_count, relative vertex ids like upg_field_mesh_slab */
+	float *dmc_vertices; /* vertex_count x 3 */
+	uint32_t *dmc_quads; /* quad_count x 4 */
+	uint32_t vertex_count;
+	uint32_t index_count;
+	uint32_t quad_count;
+	int32_t device;
+	uint64_t near_zero_samples;
+	void *owner; /* internal */
+} upg_device_mesh;
+int upg_field_meshes_slab_device(upg_planet *planet, unsigned field_mask, int slab, int slab_count, upg_device_mesh *out3);
+void upg_device_mesh_free(upg_device_mesh *mesh); /* stream-ordered on the device's default stream: finish your own reads first */
+
 /* K2..K4 alone over caller-provided samples (host memory, layout [z][y][x]): MarchingCubes::densities(values) followed by
  * makeMesh() (include/cage-core/marchingCubes.h:16,27).  `full_resolution` / `box_size` define the grid -> world mapping
  * (MarchingCubesCreateConfig::position); pass rx = ry = rz = full_resolution for a whole grid. */

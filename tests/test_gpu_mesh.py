@@ -128,3 +128,30 @@ def test_field_meshes_errors():
     assert e.value.code == 4
     with pytest.raises(ValueError):
         p.field_meshes(("elevation",))
+
+
+@pytest.mark.parametrize("slabs", [1, 3, 8])
+def test_fused_slab_meshes_host_and_device_resident(slabs):
+    # upg_field_meshes_slab[_device]: one fused sampling pass per slab for all fields; chunks equal the single-field slab calls and
+    # stitch to the whole meshes bit for bit, whether they come back through pinned host memory or stay in HBM
+    from unnatural_planets_b200 import sharded, stitch_slabs
+
+    p = Planet(shape="torus", elevation="lakes", grid=56)
+    fields = ("land", "water", "navigation")
+    whole = p.field_meshes(fields)
+    host = [p.field_meshes_slab(fields, k, slabs) for k in range(slabs)]
+    dev = [p.field_meshes_slab_device(fields, k, slabs) for k in range(slabs)]
+    for f in fields:
+        got = stitch_slabs([h[f] for h in host])
+        for k in ("positions", "normals", "dmc_vertices", "indices", "dmc_quads"):
+            assert (got[k].view(np.uint32) == whole[f][k].view(np.uint32)).all(), (f, k)
+        for k in range(slabs):
+            one = p.field_mesh_slab(f, k, slabs)
+            for key in ("positions", "normals", "dmc_vertices", "indices", "dmc_quads"):
+                assert (dev[k][f][key].cpu().numpy().view(np.uint32).reshape(-1) == one[key].view(np.uint32).reshape(-1)).all(), (f, k, key)
+            assert dev[k][f]["near_zero_samples"] == one["near_zero_samples"]
+    # a group of one: the tensor assembly reduces to a download
+    m = sharded.assemble_mesh_tensors(p.field_meshes_slab_device(("land",), 0, 1)["land"], keys=[k for k, _ in sharded.MESH_KEYS])
+    assert_same_mesh(m, whole["land"])
+    m = sharded.assemble_mesh_tensors(p.field_meshes_slab_device(("land",), 0, 1)["land"])
+    assert set(m) == {"positions", "normals", "indices", "near_zero_samples"} and np.array_equal(m["indices"], whole["land"]["indices"])

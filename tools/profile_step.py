@@ -20,11 +20,12 @@ a = ap.parse_args()
 p = Planet(shape="sphere", elevation="lakes", coloring="default", grid=a.grid, poles=bool(a.poles), flowers=bool(a.flowers))
 for r in range(a.repeat):
     meshes = {}
-    for f, m in p.field_meshes(("land", "water", "navigation")).items():
+    final = p.field_meshes_clean(("land", "water", "navigation"))  # K1 fused + K2..K4 + K9: what the generator keeps
+    for f, m in p.field_meshes(("land", "water", "navigation")).items():  # raw meshes feed the synthetic UV chart below
         if f != "navigation":
             uv = synth.octahedral_uv(m["positions"])
             meshes[f] = (m["positions"], -m["normals"], uv, synth.drop_folded_triangles(uv, m["indices"]))
     for f, water in (("land", 0), ("water", 1)):
         pos, nrm, uv, idx = meshes[f]
-        out = p.bake(water, pos, nrm, uv, idx, a.texture, a.texture)
+        out = p.bake_export(water, pos, nrm, uv, idx, a.texture, a.texture)
     print("pass", r, "covered", p.last_covered_texels, "albedo mean", float(out[0].mean()))

@@ -47,6 +47,22 @@ class Mesh(C.Structure):
     ]
 
 
+class DeviceMesh(C.Structure):
+    _fields_ = [
+        ("positions", C.c_void_p),
+        ("normals", C.c_void_p),
+        ("indices", C.c_void_p),
+        ("dmc_vertices", C.c_void_p),
+        ("dmc_quads", C.c_void_p),
+        ("vertex_count", C.c_uint32),
+        ("index_count", C.c_uint32),
+        ("quad_count", C.c_uint32),
+        ("device", C.c_int32),
+        ("near_zero_samples", C.c_uint64),
+        ("owner", C.c_void_p),
+    ]
+
+
 class Tile(C.Structure):
     _fields_ = [
         ("albedo", C.c_float * 3),
@@ -104,6 +120,10 @@ def load_library():
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_fields_samples_device.argtypes = [vp, i32, i32, fp, fp, fp, vp]
     L.upg_field_meshes.argtypes = [vp, C.c_uint, C.POINTER(Mesh)]
+    L.upg_field_meshes_slab.argtypes = [vp, C.c_uint, i32, i32, C.POINTER(Mesh)]
+    L.upg_field_meshes_slab_device.argtypes = [vp, C.c_uint, i32, i32, C.POINTER(DeviceMesh)]
+    L.upg_device_mesh_free.argtypes = [C.POINTER(DeviceMesh)]
+    L.upg_device_mesh_free.restype = None
     L.upg_field_meshes_clean.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(Mesh)]
     L.upg_mesh_clean.argtypes = [i32, fp, fp, C.c_uint32, fp, C.c_uint32, C.c_float, C.c_uint, C.POINTER(Mesh)]
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]

@@ -639,12 +639,39 @@ extern "C"
 		return rc;
 	}
 
-	static int field_meshes_impl(upg_planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3)
+	// hands a device-side result over to the caller as it is (arrays stay in HBM, owned until upg_device_mesh_free)
+	static void mesh_to_device_struct(DmcResult &r, int device, upg_device_mesh *out)
+	{
+		const uint64_t v0 = (uint64_t)r.firstVertex * 3, q0 = (uint64_t)r.firstQuad * 4, i0 = (uint64_t)r.firstTriangle * 3;
+		out->positions = r.positions ? r.positions + v0 : nullptr;
+		out->normals = r.normals ? r.normals + v0 : nullptr;
+		out->dmc_vertices = r.rawVertices ? r.rawVertices + v0 : nullptr;
+		out->indices = r.indices ? r.indices + i0 : nullptr;
+		out->dmc_quads = r.quads ? r.quads + q0 : nullptr;
+		out->vertex_count = r.ownedVertices;
+		out->index_count = r.ownedTriangles * 3;
+		out->quad_count = r.quads ? r.ownedQuads : 0;
+		out->device = device;
+		out->near_zero_samples = r.nearZeroSamples;
+		void **own = new void *[5]{ r.positions, r.normals, r.rawVertices, r.indices, r.quads };
+		out->owner = own;
+		r = DmcResult(); // ownership moved
+	}
+
+	// slabCount == 0: the whole grid.  Exactly one of hostOut3 / deviceOut3 is given.
+	static int field_meshes_impl(upg_planet *planet, unsigned field_mask, unsigned stages, int slab, int slabCount, upg_mesh *out3, upg_device_mesh *deviceOut3 = nullptr)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
-		if (!p || !out3)
+		if (!p || (!out3 && !deviceOut3))
 			return fail(UPG_ERR_ARGUMENT, "null argument");
-		std::memset(out3, 0, sizeof(upg_mesh) * 3);
+		if (out3)
+			std::memset(out3, 0, sizeof(upg_mesh) * 3);
+		if (deviceOut3)
+			std::memset(deviceOut3, 0, sizeof(upg_device_mesh) * 3);
+		if (slabCount < 0 || (slabCount > 0 && (slab < 0 || slab >= slabCount)))
+			return fail(UPG_ERR_ARGUMENT, "bad slab %d of %d", slab, slabCount);
+		if (slabCount > 0 && stages)
+			return fail(UPG_ERR_ARGUMENT, "the clean-up works on whole meshes, not on slabs");
 		if (stages & ~(unsigned)UPG_MESH_GENERATOR)
 			return fail(UPG_ERR_ARGUMENT, "bad clean-up stages %#x", stages);
 		if ((field_mask & 7u) == 0 || (field_mask & ~7u))
@@ -653,7 +680,17 @@ extern "C"
 		if (e != cudaSuccess)
 			return cuda_fail(e, "cudaSetDevice");
 		const int res = p->params.grid.res;
-		const uint64_t count = (uint64_t)res * res * res;
+		// a slab samples its scan iterations plus three slices of halo on each side (see upg_field_mesh_slab)
+		int z0 = 0, z1 = res, za = 0, zb = res;
+		if (slabCount > 0)
+		{
+			upg_slab_range(res, slab, slabCount, &z0, &z1);
+			if (z0 == z1)
+				return UPG_OK; // more slabs than scan iterations: an empty share
+			za = z0 - 3 > 0 ? z0 - 3 : 0;
+			zb = z1 + 3 < res ? z1 + 3 : res;
+		}
+		const uint64_t count = (uint64_t)(zb - za) * res * res;
 		CallStreams cs;
 		int rc = cs.open();
 		if (rc)
@@ -677,7 +714,7 @@ extern "C"
 			L.outNavigation = dens[FD_NAVIGATION];
 			L.positions = nullptr;
 			L.count = count;
-			L.z0 = 0;
+			L.z0 = (uint32_t)za;
 			L.field = FD_ALL;
 			L.status = p->status;
 			rc = launch_field(p, L, cs.compute);
@@ -725,7 +762,7 @@ extern "C"
 						const double w0 = trace ? now_ms() : 0;
 						double w1 = 0, w2 = 0;
 						if (r == UPG_OK)
-							r = dmc_extract(dens[f], res, res, res, p->boxSize, res, ws.compute, d);
+							r = slabCount > 0 ? dmc_extract(dens[f], res, res, zb - za, p->boxSize, res, ws.compute, d, za, z0, z1) : dmc_extract(dens[f], res, res, res, p->boxSize, res, ws.compute, d);
 						if (trace)
 						{
 							cudaStreamSynchronize(ws.compute);
@@ -743,15 +780,23 @@ extern "C"
 								r = check_status(p, ws.compute, "upg_field_meshes_clean");
 						}
 						// the reference throws for an empty land / navigation mesh only (sources/meshGeneration.cpp:51-52, 104-105)
-						if (r == UPG_OK && d.triangleCount == 0 && !(stages && f == FD_WATER))
+						if (r == UPG_OK && slabCount == 0 && d.triangleCount == 0 && !(stages && f == FD_WATER))
 							r = fail(UPG_ERR_EMPTY_MESH, "generated empty base %s mesh", f == FD_LAND ? "land" : f == FD_WATER ? "water" : "navigation");
 						if (trace)
 						{
 							cudaStreamSynchronize(ws.compute);
 							w2 = now_ms();
 						}
-						if (r == UPG_OK)
+						if (r == UPG_OK && out3)
 							r = mesh_to_host(d, ws.compute, &out3[f]);
+						else if (r == UPG_OK)
+						{
+							ee = cudaStreamSynchronize(ws.compute);
+							if (ee != cudaSuccess)
+								r = cuda_fail(ee, "extraction");
+							else
+								mesh_to_device_struct(d, p->device, &deviceOut3[f]);
+						}
 						if (trace)
 							std::fprintf(stderr, "[upg]   field %d: extract %.2f ms, clean-up %.2f ms, download %.2f ms (%u vertices, %u triangles)\n", f, w1 - w0, w2 - w1, now_ms() - w2, d.vertexCount, d.triangleCount);
 						dmc_release(d, ws.compute);
@@ -781,20 +826,58 @@ extern "C"
 		cs.close();
 		if (rc != UPG_OK)
 			for (int f = 0; f < 3; f++)
-				upg_mesh_free(&out3[f]);
+			{
+				if (out3)
+					upg_mesh_free(&out3[f]);
+				if (deviceOut3)
+					upg_device_mesh_free(&deviceOut3[f]);
+			}
 		return rc;
 	}
 
 	int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3)
 	{
-		return field_meshes_impl(planet, field_mask, 0, out3);
+		return field_meshes_impl(planet, field_mask, 0, 0, 0, out3);
+	}
+
+	int upg_field_meshes_slab(upg_planet *planet, unsigned field_mask, int slab, int slab_count, upg_mesh *out3)
+	{
+		if (slab_count < 1)
+			return fail(UPG_ERR_ARGUMENT, "bad slab %d of %d", slab, slab_count);
+		return field_meshes_impl(planet, field_mask, 0, slab, slab_count, out3);
+	}
+
+	int upg_field_meshes_slab_device(upg_planet *planet, unsigned field_mask, int slab, int slab_count, upg_device_mesh *out3)
+	{
+		if (slab_count < 1)
+			return fail(UPG_ERR_ARGUMENT, "bad slab %d of %d", slab, slab_count);
+		return field_meshes_impl(planet, field_mask, 0, slab, slab_count, nullptr, out3);
+	}
+
+	void upg_device_mesh_free(upg_device_mesh *mesh)
+	{
+		if (!mesh)
+			return;
+		if (mesh->owner)
+		{
+			void **own = reinterpret_cast<void **>(mesh->owner);
+			int previous = 0;
+			cudaGetDevice(&previous);
+			cudaSetDevice(mesh->device);
+			for (int i = 0; i < 5; i++)
+				if (own[i])
+					cudaFreeAsync(own[i], nullptr);
+			cudaSetDevice(previous);
+			delete[] own;
+		}
+		std::memset(mesh, 0, sizeof(*mesh));
 	}
 
 	int upg_field_meshes_clean(upg_planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3)
 	{
 		if (stages == 0)
 			return fail(UPG_ERR_ARGUMENT, "no clean-up stage requested");
-		return field_meshes_impl(planet, field_mask, stages, out3);
+		return field_meshes_impl(planet, field_mask, stages, 0, 0, out3);
 	}
 
 	int upg_mesh_clean(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float box_size, unsigned stages, upg_mesh *out)

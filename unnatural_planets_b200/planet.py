@@ -206,6 +206,56 @@ class Planet:
         self.last_call_s = time.perf_counter() - t  # the C call alone (the numpy copies below are the binding's, not the library's)
         return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
 
+    def _field_mask(self, fields):
+        mask = 0
+        for f in fields:
+            if capi.FIELDS[f] > 2:
+                raise ValueError("land, water and navigation only")
+            mask |= 1 << capi.FIELDS[f]
+        return mask
+
+    def field_meshes_slab(self, fields, slab, slab_count):
+        """slab `slab` of `slab_count` of several fields from one fused sampling pass over the slab (upg_field_meshes_slab)."""
+        ms = (capi.Mesh * 3)()
+        capi.check(self._lib.upg_field_meshes_slab(self._h, self._field_mask(fields), slab, slab_count, ms))
+        return {f: _mesh_to_numpy(self._lib, ms[capi.FIELDS[f]]) for f in fields}
+
+    def field_meshes_slab_device(self, fields, slab, slab_count):
+        """the same, left in HBM (upg_field_meshes_slab_device): {field: dict of CUDA tensors + near_zero_samples}.  The tensors are
+        torch-owned copies (one device-to-device copy of the chunk), so the library's arrays are released before returning."""
+        import torch
+
+        ms = (capi.DeviceMesh * 3)()
+        capi.check(self._lib.upg_field_meshes_slab_device(self._h, self._field_mask(fields), slab, slab_count, ms))
+        dev = torch.device("cuda", self.device)
+
+        class _View:  # zero-copy view of library memory through the CUDA array interface
+            def __init__(self, ptr, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def take(ptr, count, typestr, dtype):
+            if not ptr or count == 0:
+                return torch.zeros(0, dtype=dtype, device=dev)
+            return torch.as_tensor(_View(ptr, count, typestr), device=dev).clone()
+
+        out = {}
+        with torch.cuda.device(dev):
+            for f in fields:
+                m = ms[capi.FIELDS[f]]
+                nv, ni, nq = m.vertex_count, m.index_count, m.quad_count
+                out[f] = dict(
+                    positions=take(m.positions, nv * 3, "<f4", torch.float32).view(-1, 3),
+                    normals=take(m.normals, nv * 3, "<f4", torch.float32).view(-1, 3),
+                    dmc_vertices=take(m.dmc_vertices, nv * 3, "<f4", torch.float32).view(-1, 3),
+                    indices=take(m.indices, ni, "<i4", torch.int32),
+                    dmc_quads=take(m.dmc_quads, nq * 4, "<i4", torch.int32).view(-1, 4),
+                    near_zero_samples=int(m.near_zero_samples),
+                )
+            torch.cuda.current_stream().synchronize()  # the copies above are done before the library frees its arrays
+            for k in range(3):
+                self._lib.upg_device_mesh_free(C.byref(ms[k]))
+        return out
+
     def field_mesh_slab(self, field, slab, slab_count):
         """slab `slab` of `slab_count` of field_mesh() (upg_field_mesh_slab): indices / dmc_quads are relative to the slab's
         first vertex (uint32, two's complement); see stitch_slabs()."""
