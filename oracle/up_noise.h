@@ -156,9 +156,18 @@ static inline void upo_grad3(int32_t idx4, float *gx, float *gy, float *gz)
 
 static inline float upo_gradcoord3(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd)
 {
+#ifdef UPO_WORST_CASE_GRADIENTS
+	/* tools/noise_bounds.cpp: the largest value ANY of the gradients (two non-zero components of magnitude 1) can give at this offset,
+	 * i.e. the sum of the two largest |components|: turns the Perlin / OpenSimplex2 generators into tight upper bounds of themselves */
+	(void)seed, (void)xp, (void)yp, (void)zp;
+	const float ax = xd < 0 ? -xd : xd, ay = yd < 0 ? -yd : yd, az = zd < 0 ? -zd : zd;
+	const float mn = ax < ay ? (ax < az ? ax : az) : (ay < az ? ay : az);
+	return (ax + ay + az) - mn;
+#else
 	float gx, gy, gz;
 	upo_grad3(upo_gradindex3(upo_hash3(seed, xp, yp, zp)), &gx, &gy, &gz);
 	return xd * gx + yd * gy + zd * gz;
+#endif
 }
 
 static inline int32_t upo_fastfloor(float f)

@@ -540,9 +540,13 @@ namespace upg
 		__global__ void __launch_bounds__(MF_BLOCK) component_faces_kernel(const uint32_t *__restrict__ idx, const uint8_t *__restrict__ dead, uint32_t tris, const uint32_t *__restrict__ rep, uint32_t *__restrict__ faces)
 		{
 			const uint32_t t = blockIdx.x * MF_BLOCK + threadIdx.x;
-			if (t >= tris || dead[t])
-				return;
-			atomicAdd(&faces[rep[idx[t * 3 + 0]]], 1u);
+			const bool live = t < tris && !dead[t];
+			const uint32_t r = live ? rep[idx[t * 3 + 0]] : 0xffffffffu;
+			// a planet is one big component: nearly every lane of a warp counts into the same word, so lanes with equal
+			// representatives elect one of them to add their number (one atomic per distinct component per warp)
+			const uint32_t peers = __match_any_sync(0xffffffffu, r);
+			if (live && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1))
+				atomicAdd(&faces[r], (uint32_t)__popc(peers));
 		}
 		// the component with the most faces; the FIRST one on ties, and components are ordered by their smallest vertex (:705-706, 1321-1330)
 		__global__ void __launch_bounds__(MF_BLOCK) largest_component_kernel(const uint32_t *__restrict__ faces, uint32_t verts, unsigned long long *__restrict__ best)
