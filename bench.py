@@ -297,6 +297,27 @@ def run_ours(args, rank, world, local_rank):
     mesh_stats = {"land_vertices": int(len(m2["positions"])), "land_triangles": int(len(m2["indices"]) // 3), "navigation_triangles": int(len(raw["navigation"]["indices"]) // 3), "near_zero_samples": m2["near_zero_samples"]}
     meshes = bench_mesh(raw)  # synthetic UVs (host numpy, outside every timing); the input of the bake
     del raw, m2
+    # how the grid got filled for those meshes: band sampling (K1b: water field densely, elevation only where the isosurface can see it)
+    # against the dense fused launch of leg 1 -- device timed, plus the same mesh call on a planet forced to dense sampling
+    bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in FIELDS]
+    evaluated = planet.fields_samples_band_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream, count=True)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    band_steps = max(3, min(args.steps, 10))
+    s0.record(stream)
+    for _ in range(band_steps):
+        planet.fields_samples_band_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
+    s1.record(stream)
+    s1.synchronize()
+    band_ms = s0.elapsed_time(s1) / band_steps
+    del bufs
+    torch.cuda.empty_cache()
+    dense_planet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank), mesh_sampling="dense")
+    dense_planet.field_meshes_clean(FIELDS)
+    dense_planet.field_meshes_clean(FIELDS)
+    mesh_dense_s = dense_planet.last_call_s
+    dense_planet.close()
+    sampling_stats = {"mode": "band", "band_sampling_ms": band_ms, "evaluated_nodes": int(evaluated), "evaluated_fraction": evaluated / n, "base_meshes_ms_with_dense_sampling": mesh_dense_s * 1e3,
+                      "what": "upg_fields_samples_band_device over the whole grid (3 fields): dense water launch + band_sample_kernel, CUDA events; the extracted meshes are bit-identical to dense sampling (tests/test_gpu_mesh.py)"}
 
     # ---- leg 3: texel baking -------------------------------------------------------------------------------------------
     dmesh = {}
@@ -452,8 +473,8 @@ def run_ours(args, rank, world, local_rank):
     planet_ms = mesh_ms + bake_e2e_ms
     planet_line = {
         "ms": planet_ms, "base_meshes_ms": mesh_ms, "base_meshes_without_cleanup_ms": mesh_raw_ms, "bake_ms": bake_e2e_ms, "field_mesh_land_ms": field_mesh_land_s * 1e3,
-        "what": "upg_field_meshes_clean (fused sampling of the 3 fields + 3 concurrent Dual Marching Cubes extractions + K9 clean-up = the bodies of meshGenerateBaseLand/Water/Navigation + mesh downloads) + 2 x upg_bake_export (bake + pbr / normal-map tail), host buffers, wall clock",
-        "mesh": mesh_stats, "base_meshes": final_stats,
+        "what": "upg_field_meshes_clean (band sampling of the 3 fields + 3 concurrent Dual Marching Cubes extractions + K9 clean-up = the bodies of meshGenerateBaseLand/Water/Navigation + mesh downloads) + 2 x upg_bake_export (bake + pbr / normal-map tail), host buffers, wall clock",
+        "mesh": mesh_stats, "base_meshes": final_stats, "mesh_sampling": sampling_stats,
     }
 
     threads = os.cpu_count() or 1

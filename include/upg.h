@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define UPG_API_VERSION 1
+#define UPG_API_VERSION 2
 
 enum
 {
@@ -49,6 +49,19 @@ enum
 	UPG_FIELD_NAVIGATION = 2, /* terrainSdfNavigation: shape - max(elevation, 0) / 10 */
 	UPG_FIELD_ELEVATION_RAW = 3, /* terrainSdfElevationRaw: elevation */
 	UPG_FIELD_ELEVATION = 4 /* terrainSdfElevation:  shape * 10 */
+};
+
+/*
+ * How upg_field_meshes* sample the land / navigation grids before the extraction.  dualmc reads of a sample only its sign, and its
+ * value where it ends a grid edge whose signs differ (dualmc.tpp:12-32, 91-188); elevation / 10 is bounded per elevation mode, so far
+ * from the surface the shape alone settles the sign.  BAND evaluates the elevation function exactly on every node that can end a
+ * sign-changing edge and stores a value of the settled sign elsewhere: same meshes bit for bit, a few percent of the noise
+ * evaluations.  DENSE evaluates every node like MarchingCubes::updateByPosition does.  upg_field_samples* are always dense.
+ */
+enum
+{
+	UPG_SAMPLING_BAND = 0,
+	UPG_SAMPLING_DENSE = 1
 };
 
 typedef struct upg_planet upg_planet;
@@ -71,6 +84,7 @@ typedef struct upg_planet_desc
 	float box_size; /* meshing box side, reference constant 4000 (sources/meshGeneration.cpp:19) */
 	int32_t grid_resolution; /* samples per axis, reference constant 500 (110 in debug builds) (:20-28) */
 	int32_t device; /* CUDA device ordinal */
+	int32_t mesh_sampling; /* UPG_SAMPLING_*: how the mesh entry points (upg_field_meshes*) fill the grid; the meshes are identical */
 } upg_planet_desc;
 
 /* fills the reference's defaults: shape "random" is NOT resolved here (pass an explicit id), elevation lakes,
@@ -114,6 +128,14 @@ int upg_field_samples_device(upg_planet *planet, int field, int z0, int z1, floa
  * (the three fields differ only in how the two combine, sources/modesConfiguration.cpp:248-279, and the generator asks for
  * all three: sources/generator.cpp:432-439).  Each output is bit-identical to the single-field call; any pointer may be NULL. */
 int upg_fields_samples_device(upg_planet *planet, int z0, int z1, float *device_land, float *device_water, float *device_navigation, void *cuda_stream);
+
+/* the samples the mesh entry points extract from under UPG_SAMPLING_BAND (whatever the planet's own setting), same layout and
+ * arguments: water is the dense shape field; land / navigation are EXACT (bit-identical to upg_fields_samples_device) on both end
+ * points of every grid edge inside [z0, z1) whose signs differ -- in fact on every node whose sign the shape value alone does not
+ * settle, and on the six neighbours of such nodes -- and carry a value of the correct sign, at least 1/64 from zero, elsewhere.
+ * `evaluated_nodes` (may be NULL; host memory, written after a stream synchronisation inside the call) receives the number of nodes
+ * whose elevation was evaluated.  Elevation "none" falls back to the dense kernel (nothing to skip). */
+int upg_fields_samples_band_device(upg_planet *planet, int z0, int z1, float *device_land, float *device_water, float *device_navigation, void *cuda_stream, uint64_t *evaluated_nodes);
 
 /* one terrainSdf* value per explicit position (n x 3 floats): the per-vertex terrainSdfElevationRaw loop of the water
  * mesh culling (sources/meshGeneration.cpp:62-68) and the parity probes */

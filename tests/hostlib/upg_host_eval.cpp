@@ -117,6 +117,11 @@ extern "C"
 				for (uint32_t x = 0; x < res; x++)
 					*out++ = eval_field(p->params, field, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, z)));
 	}
+	// the bounds of elevation / 10 the band sampler (csrc/upg_band.cu) classifies with
+	void upgh_elevation_interval10(int elevation, double *lo10, double *hi10)
+	{
+		elevation_interval10(elevation, lo10, hi10);
+	}
 	void upgh_grid_coords(const upgh_planet *p, float *out)
 	{
 		for (int i = 0; i < p->params.grid.res; i++)

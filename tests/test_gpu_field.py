@@ -169,3 +169,66 @@ def test_fused_three_field_sampling_is_bit_identical(shape, elev, res):
         p.fields_samples_device(z0, z1, 0, 0, 0, s.cuda_stream)
     with pytest.raises(UpgError):
         p.fields_samples_device(2, res + 1, only.data_ptr(), 0, 0, s.cuda_stream)
+
+
+def band_violations(dense, band):
+    """the contract of upg_fields_samples_band_device on one field: (1) the sign of every sample is the dense one, (2) both end
+    points of every grid edge whose signs differ carry the dense bits, (3) no non-exact sample is within 1/64 of zero."""
+    neg_d, neg_b = dense < 0, band < 0
+    same = same_bits(dense, band)
+    bad = int((neg_d != neg_b).sum())
+    for axis in range(3):
+        a = [slice(None)] * 3
+        b = [slice(None)] * 3
+        a[axis], b[axis] = slice(0, -1), slice(1, None)
+        a, b = tuple(a), tuple(b)
+        crossing = neg_d[a] != neg_d[b]
+        bad += int((crossing & ~(same[a] & same[b])).sum())
+    bad += int((~same & (np.abs(band) < 1.0 / 64)).sum())
+    return bad
+
+
+@pytest.mark.parametrize("elev", ["simple", "legacy", "lakes", "islands", "craters", "none"])
+def test_band_sampling_contract_every_shape(elev):
+    # K1b (csrc/upg_band.cu) against the dense kernel, all 34 shapes of sources/sdf.cpp under this elevation mode
+    import torch
+
+    from unnatural_planets_b200.planet import SHAPES
+
+    res = 56
+    s = torch.cuda.current_stream()
+    total_eval = 0
+    for shape in SHAPES:
+        p = Planet(shape=shape, elevation=elev, grid=res)
+        dense = {f: torch.empty((res, res, res), dtype=torch.float32, device="cuda") for f in ("land", "water", "navigation")}
+        band = {f: torch.full((res, res, res), float("nan"), dtype=torch.float32, device="cuda") for f in dense}
+        p.fields_samples_device(0, res, dense["land"].data_ptr(), dense["water"].data_ptr(), dense["navigation"].data_ptr(), s.cuda_stream)
+        n = p.fields_samples_band_device(0, res, band["land"].data_ptr(), band["water"].data_ptr(), band["navigation"].data_ptr(), s.cuda_stream, count=True)
+        s.synchronize()
+        total_eval += n
+        assert 0 < n <= res**3
+        assert same_bits(band["water"].cpu().numpy(), dense["water"].cpu().numpy()).all(), shape
+        for f in ("land", "navigation"):
+            assert band_violations(dense[f].cpu().numpy(), band[f].cpu().numpy()) == 0, (shape, elev, f)
+    if elev in ("lakes", "islands", "craters"):
+        assert total_eval < 0.5 * len(SHAPES) * res**3  # the point of the exercise
+
+
+@pytest.mark.parametrize("shape,elev,res", [("sphere", "lakes", 120), ("torus", "craters", 90), ("mandelbulb", "islands", 64)])
+def test_band_sampling_subsets_slices_and_scratch_shape_field(shape, elev, res):
+    import torch
+
+    p = Planet(shape=shape, elevation=elev, grid=res)
+    s = torch.cuda.current_stream()
+    z0, z1 = 5, res - 9
+    want = {f: p.field_samples(f, z0, z1) for f in ("land", "navigation")}
+    # land alone / navigation alone: the shape field lives in scratch memory of the call
+    for f in want:
+        buf = torch.full((z1 - z0, res, res), float("nan"), dtype=torch.float32, device="cuda")
+        args = dict(d_land=buf.data_ptr()) if f == "land" else dict(d_navigation=buf.data_ptr())
+        n = p.fields_samples_band_device(z0, z1, stream=s.cuda_stream, count=True, **args)
+        s.synchronize()
+        assert band_violations(want[f], buf.cpu().numpy()) == 0, f
+        assert 0 < n <= (z1 - z0) * res * res  # (the mandelbulb at this size lies inside the band everywhere)
+    with pytest.raises(UpgError):
+        p.fields_samples_band_device(z0, z1, 0, 0, 0, s.cuda_stream)

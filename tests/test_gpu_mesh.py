@@ -155,3 +155,45 @@ def test_fused_slab_meshes_host_and_device_resident(slabs):
     assert_same_mesh(m, whole["land"])
     m = sharded.assemble_mesh_tensors(p.field_meshes_slab_device(("land",), 0, 1)["land"])
     assert set(m) == {"positions", "normals", "indices", "near_zero_samples"} and np.array_equal(m["indices"], whole["land"]["indices"])
+
+
+# ---- band sampling (csrc/upg_band.cu): the elevation is evaluated only where the isosurface can see it ---------------------------------
+@pytest.mark.parametrize("elev", ["lakes", "simple", "legacy", "islands", "craters"])
+def test_band_sampled_meshes_equal_dense_sampled_meshes_every_shape(elev):
+    from unnatural_planets_b200.planet import SHAPES
+
+    res = 72
+    for shape in SHAPES:
+        dense = Planet(shape=shape, elevation=elev, grid=res, mesh_sampling="dense")
+        band = Planet(shape=shape, elevation=elev, grid=res, mesh_sampling="band")
+        try:
+            want = dense.field_meshes(("land", "water", "navigation"))
+        except UpgError as e:
+            assert e.code == 4  # a shape that leaves no surface at this size: both paths must agree on that too
+            with pytest.raises(UpgError):
+                band.field_meshes(("land", "water", "navigation"))
+            continue
+        got = band.field_meshes(("land", "water", "navigation"))
+        for f in want:
+            assert_same_mesh(got[f], want[f])
+            assert got[f]["near_zero_samples"] == want[f]["near_zero_samples"], (shape, f)
+
+
+@pytest.mark.parametrize("shape,elev,res", [("sphere", "lakes", 200), ("torus", "craters", 150), ("doubletorus", "islands", 130)])
+def test_band_sampling_through_every_mesh_entry_point(shape, elev, res):
+    from unnatural_planets_b200 import stitch_slabs
+
+    dense = Planet(shape=shape, elevation=elev, grid=res, mesh_sampling="dense")
+    band = Planet(shape=shape, elevation=elev, grid=res, mesh_sampling="band")
+    for f in ("land", "navigation"):
+        assert_same_mesh(band.field_mesh(f), dense.field_mesh(f))  # single field: the shape field is call scratch
+    want = dense.field_mesh("land")
+    for slabs in (2, 5):
+        parts = [band.field_mesh_slab("land", k, slabs) for k in range(slabs)]
+        assert_same_mesh(stitch_slabs(parts), want)
+        fused = [band.field_meshes_slab(("land", "navigation"), k, slabs) for k in range(slabs)]
+        assert_same_mesh(stitch_slabs([c["land"] for c in fused]), want)
+    a, b = band.field_meshes_clean(("land", "water", "navigation")), dense.field_meshes_clean(("land", "water", "navigation"))
+    for f in a:
+        for k in ("positions", "normals", "indices"):
+            assert (a[f][k].view(np.uint32) == b[f][k].view(np.uint32)).all(), (f, k)

@@ -88,6 +88,31 @@ def test_full_grid_matches_reference(hostlib):
         assert same_bits(got, g["land"]).all()
 
 
+@pytest.mark.parametrize("elev", ELEVATIONS)
+def test_elevation_interval_bounds_every_mode(hostlib, elev):
+    """elevation_interval10 (csrc/upg_planet_host.h) is what the band sampler trusts: elevation / 10 of every mode must lie inside
+    it, for any seed and anywhere in (and well beyond) the meshing box; the hull contains 0 so it also bounds max(elevation, 0) / 10."""
+    import ctypes as C
+
+    lo, hi = C.c_double(), C.c_double()
+    hostlib.upgh_elevation_interval10(ELEVATIONS.index(elev), C.byref(lo), C.byref(hi))
+    lo, hi = lo.value, hi.value
+    assert lo <= 0 <= hi
+    rng = np.random.default_rng(12345)
+    seen_lo, seen_hi = np.inf, -np.inf
+    for k in range(6):
+        seed = (int(rng.integers(1, 2**62)), int(rng.integers(1, 2**62)))
+        hp = HostPlanet(hostlib, "sphere", elev, seed=seed)
+        pts = rng.uniform(-2600, 2600, size=(60000, 3)).astype(np.float32)
+        e10 = hp.points("elevraw", pts).astype(np.float64) / 10
+        assert np.isfinite(e10).all()
+        seen_lo, seen_hi = min(seen_lo, e10.min()), max(seen_hi, e10.max())
+    assert lo <= seen_lo and seen_hi <= hi, (elev, lo, seen_lo, seen_hi, hi)
+    # the interval is a bound, not a guess: it must not sit orders of magnitude away from what the mode produces
+    if elev != "none":
+        assert hi - lo < 12 * (seen_hi - seen_lo), (elev, lo, seen_lo, seen_hi, hi)
+
+
 def test_rng_known_answers(hostlib):
     # externals/cage/sources/test-core/random.cpp:37-79 pins randomRange3i(10, 1000) == (730, 955, 866) for this state;
     # the raw stream below was produced by cage's RandomGenerator itself

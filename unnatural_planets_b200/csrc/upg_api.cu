@@ -75,9 +75,11 @@ namespace upg
 		if (L.count == 0)
 			return UPG_OK;
 		const PlanetParams &P = planet->params;
+		// the water field is the bare shape: its grid launches take the row-wise kernel that lives with the elevation-free instantiations
+		const int table = (L.field == FD_WATER && !L.positions) ? (int)EL_NONE : P.elevation;
 		bool done = false;
 		for (int part = 0; part < 4 && !done; part++)
-			done = fieldLaunchers[P.elevation][part](P.shape, P, L, (void *)stream);
+			done = fieldLaunchers[table][part](P.shape, P, L, (void *)stream);
 		if (!done)
 			return fail(UPG_ERR_ARGUMENT, "no kernel for shape %d elevation %d", P.shape, P.elevation);
 		const cudaError_t e = cudaGetLastError();
@@ -184,6 +186,8 @@ extern "C"
 			return fail(UPG_ERR_ARGUMENT, "seed words must be non-zero");
 		if (!(d->box_size > 0))
 			return fail(UPG_ERR_ARGUMENT, "box size must be positive");
+		if (d->mesh_sampling != UPG_SAMPLING_BAND && d->mesh_sampling != UPG_SAMPLING_DENSE)
+			return fail(UPG_ERR_ARGUMENT, "unknown mesh sampling %d", d->mesh_sampling);
 
 		Planet *p = new (std::nothrow) Planet();
 		if (!p)
@@ -197,6 +201,10 @@ extern "C"
 		set_grid(p->params, d->box_size, d->grid_resolution);
 		p->boxSize = d->box_size;
 		p->device = d->device;
+		p->sampling = d->mesh_sampling;
+		// UPG_MESH_SAMPLING=dense|band overrides the descriptor (A/B timing of the two ways to fill the grid)
+		if (const char *env = std::getenv("UPG_MESH_SAMPLING"))
+			p->sampling = std::strcmp(env, "dense") == 0 ? UPG_SAMPLING_DENSE : std::strcmp(env, "band") == 0 ? UPG_SAMPLING_BAND : p->sampling;
 
 		// terrainPreseed order (sources/modesConfiguration.cpp:288-306): shape statics, then elevation statics, ...
 		PlanetBuilder b;
@@ -323,6 +331,110 @@ extern "C"
 		L.field = FD_ALL;
 		L.status = p->status;
 		return launch_field(p, L, (cudaStream_t)cuda_stream);
+	}
+
+	// the samples an extraction needs of slices [za, zb): dense (one fused evaluation per node) or, with `band`, the water field
+	// densely followed by K1b (upg_band.cu), which needs `water` even when the caller does not ask for that field
+	static int sample_for_extraction(Planet *p, bool band, int za, int zb, float *land, float *water, float *navigation, unsigned long long *evaluatedDevice, cudaStream_t stream)
+	{
+		const int res = p->params.grid.res;
+		FieldLaunch L;
+		L.positions = nullptr;
+		L.count = (uint64_t)(zb - za) * res * res;
+		L.z0 = (uint32_t)za;
+		L.status = p->status;
+		if (!band || (!land && !navigation))
+		{
+			L.out = land;
+			L.outWater = water;
+			L.outNavigation = navigation;
+			L.field = FD_ALL;
+			return launch_field(p, L, stream);
+		}
+		L.out = water;
+		L.field = FD_WATER;
+		const int rc = launch_field(p, L, stream);
+		if (rc != UPG_OK)
+			return rc;
+		return band_sample(p, za, zb, water, land, navigation, evaluatedDevice, stream);
+	}
+
+	// one field of slices [za, zb) for an extraction: land / navigation go through the band sampler when the planet asks for it
+	static int sample_one_for_extraction(Planet *p, int field, int za, int zb, float *dens, cudaStream_t stream)
+	{
+		const int res = p->params.grid.res;
+		const uint64_t count = (uint64_t)(zb - za) * res * res;
+		if ((field == FD_LAND || field == FD_NAVIGATION) && band_sampling_applies(p))
+		{
+			float *shape = nullptr;
+			const cudaError_t e = cudaMallocAsync(&shape, sizeof(float) * count, stream);
+			if (e != cudaSuccess)
+				return cuda_fail(e, "cudaMallocAsync(shape field)");
+			const int rc = sample_for_extraction(p, true, za, zb, field == FD_LAND ? dens : nullptr, shape, field == FD_NAVIGATION ? dens : nullptr, nullptr, stream);
+			cudaFreeAsync(shape, stream);
+			return rc;
+		}
+		FieldLaunch L;
+		L.out = dens;
+		L.positions = nullptr;
+		L.count = count;
+		L.z0 = (uint32_t)za;
+		L.field = field;
+		L.status = p->status;
+		return launch_field(p, L, stream);
+	}
+
+	int upg_fields_samples_band_device(upg_planet *planet, int z0, int z1, float *device_land, float *device_water, float *device_navigation, void *cuda_stream, uint64_t *evaluated_nodes)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || (!device_land && !device_water && !device_navigation))
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		const int res = p->params.grid.res;
+		if (z0 < 0 || z1 > res || z0 > z1)
+			return fail(UPG_ERR_ARGUMENT, "bad slice range [%d, %d)", z0, z1);
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		cudaStream_t stream = (cudaStream_t)cuda_stream;
+		const uint64_t count = (uint64_t)(z1 - z0) * res * res;
+		const bool band = p->params.elevation != EL_NONE && (device_land || device_navigation);
+		float *scratch = nullptr;
+		unsigned long long *counter = nullptr;
+		if (band && !device_water && count)
+		{
+			e = cudaMallocAsync(&scratch, sizeof(float) * count, stream);
+			if (e != cudaSuccess)
+				return cuda_fail(e, "cudaMallocAsync(shape field)");
+		}
+		if (evaluated_nodes)
+		{
+			*evaluated_nodes = band ? 0 : count;
+			e = cudaMallocAsync(&counter, sizeof(unsigned long long), stream);
+			if (e == cudaSuccess)
+				e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
+			if (e != cudaSuccess)
+			{
+				if (scratch)
+					cudaFreeAsync(scratch, stream);
+				return cuda_fail(e, "cudaMallocAsync(counter)");
+			}
+		}
+		int rc = count ? sample_for_extraction(p, band, z0, z1, device_land, device_water ? device_water : scratch, device_navigation, counter, stream) : UPG_OK;
+		if (counter)
+		{
+			unsigned long long n = 0;
+			e = cudaMemcpyAsync(&n, counter, sizeof(n), cudaMemcpyDeviceToHost, stream);
+			if (e == cudaSuccess)
+				e = cudaStreamSynchronize(stream);
+			if (e != cudaSuccess && rc == UPG_OK)
+				rc = cuda_fail(e, "upg_fields_samples_band_device");
+			if (band)
+				*evaluated_nodes = n;
+			cudaFreeAsync(counter, stream);
+		}
+		if (scratch)
+			cudaFreeAsync(scratch, stream);
+		return rc;
 	}
 
 	int upg_field_samples(upg_planet *planet, int field, int z0, int z1, float *host_out)
@@ -600,16 +712,7 @@ extern "C"
 		if (e != cudaSuccess)
 			rc = cuda_fail(e, "cudaMallocAsync(field)");
 		if (rc == UPG_OK)
-		{
-			FieldLaunch L;
-			L.out = dens;
-			L.positions = nullptr;
-			L.count = (uint64_t)res * res * res;
-			L.z0 = 0;
-			L.field = field;
-			L.status = p->status;
-			rc = launch_field(p, L, cs.compute);
-		}
+			rc = sample_one_for_extraction(p, field, 0, res, dens, cs.compute);
 		if (trace)
 		{
 			cudaStreamSynchronize(cs.compute);
@@ -705,20 +808,21 @@ extern "C"
 				if (e != cudaSuccess)
 					rc = cuda_fail(e, "cudaMallocAsync(field)");
 			}
-		if (rc == UPG_OK)
+		// band sampling reads the shape from the water field: a scratch copy when the caller does not want that mesh
+		const bool band = band_sampling_applies(p) && (dens[FD_LAND] || dens[FD_NAVIGATION]);
+		float *shapeScratch = nullptr;
+		if (rc == UPG_OK && band && !dens[FD_WATER])
 		{
-			// shape and elevation are evaluated ONCE per sample for all requested fields
-			FieldLaunch L;
-			L.out = dens[FD_LAND];
-			L.outWater = dens[FD_WATER];
-			L.outNavigation = dens[FD_NAVIGATION];
-			L.positions = nullptr;
-			L.count = count;
-			L.z0 = (uint32_t)za;
-			L.field = FD_ALL;
-			L.status = p->status;
-			rc = launch_field(p, L, cs.compute);
+			e = cudaMallocAsync(&shapeScratch, sizeof(float) * count, cs.compute);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "cudaMallocAsync(shape field)");
 		}
+		// shape and elevation are evaluated ONCE per sample for all requested fields (and the elevation only where the isosurface
+		// can see it, UPG_SAMPLING_BAND)
+		if (rc == UPG_OK)
+			rc = sample_for_extraction(p, band, za, zb, dens[FD_LAND], dens[FD_WATER] ? dens[FD_WATER] : shapeScratch, dens[FD_NAVIGATION], nullptr, cs.compute);
+		if (shapeScratch)
+			cudaFreeAsync(shapeScratch, cs.compute);
 		cudaEvent_t sampled = nullptr;
 		if (rc == UPG_OK)
 		{
@@ -816,7 +920,7 @@ extern "C"
 					rc = fail(rcs[f], "%s", errs[f].c_str());
 		}
 		if (trace)
-			std::fprintf(stderr, "[upg] field_meshes(mask %#x) res %d: fused sampling %.2f ms, extraction + download %.2f ms\n", field_mask, res, t1 - t0, now_ms() - t1);
+			std::fprintf(stderr, "[upg] field_meshes(mask %#x) res %d: %s sampling %.2f ms, extraction + download %.2f ms\n", field_mask, res, band ? "band" : "dense fused", t1 - t0, now_ms() - t1);
 		if (sampled)
 			cudaEventDestroy(sampled);
 		for (int f = 0; f < 3; f++)
@@ -980,16 +1084,7 @@ extern "C"
 		if (e != cudaSuccess)
 			rc = cuda_fail(e, "cudaMallocAsync(slab)");
 		if (rc == UPG_OK)
-		{
-			FieldLaunch L;
-			L.out = dens;
-			L.positions = nullptr;
-			L.count = count;
-			L.z0 = (uint32_t)a;
-			L.field = field;
-			L.status = p->status;
-			rc = launch_field(p, L, cs.compute);
-		}
+			rc = sample_one_for_extraction(p, field, a, b, dens, cs.compute);
 		DmcResult r;
 		if (rc == UPG_OK)
 			rc = dmc_extract(dens, res, res, b - a, p->boxSize, res, cs.compute, r, a, z0, z1);

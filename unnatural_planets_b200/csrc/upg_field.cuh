@@ -135,6 +135,41 @@ namespace upg
 		L.out[idx] = v;
 	}
 
+	// The water field (= the bare shape, terrainSdfWater) of whole grid rows: the shape functions cost a few dozen instructions, so
+	// the index arithmetic of the generic kernel above (a 64-bit division and three IEEE divisions per sample) would dominate.  Here
+	// the grid -> world coordinates come from a per-block table (same grid_coord(), same bits) and a block walks SHAPE_ROWS rows.
+	// The band sampler (upg_band.cu) reads the shape of every node from this field.
+	constexpr int SHAPE_ROWS = 16;
+	constexpr int SHAPE_MAX_RES = 2048; // upg_planet_create's limit
+	template<int SHAPE>
+	__global__ void __launch_bounds__(FIELD_BLOCK) shape_rows_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
+	{
+		__shared__ float coord[SHAPE_MAX_RES];
+		const uint32_t res = (uint32_t)P.grid.res;
+		grad_table_init<FIELD_BLOCK>(); // the asteroid shape samples a noise
+		for (uint32_t i = threadIdx.x; i < res; i += FIELD_BLOCK)
+			coord[i] = grid_coord(P.grid, i);
+		__syncthreads();
+		const uint32_t rows = (uint32_t)(L.count / res);
+		const uint32_t row0 = blockIdx.x * SHAPE_ROWS;
+		const uint32_t rowEnd = min(row0 + (uint32_t)SHAPE_ROWS, rows);
+		bool bad = false;
+		for (uint32_t row = row0; row < rowEnd; row++)
+		{
+			const uint32_t zl = row / res;
+			const float cy = coord[row - zl * res], cz = coord[L.z0 + zl];
+			float *out = L.out + (uint64_t)row * res;
+			for (uint32_t x = threadIdx.x; x < res; x += FIELD_BLOCK)
+			{
+				const float v = shape_sdf<SHAPE>(P, v3(coord[x], cy, cz));
+				bad |= isnan_(v);
+				out[x] = v;
+			}
+		}
+		if (bad)
+			atomicOr(L.status, 1u);
+	}
+
 	// host-callable launcher type; one per (elevation, shape range) translation unit, see upg_field_inst.cu
 	typedef bool (*FieldLauncher)(int shape, const PlanetParams &P, const FieldLaunch &L, void *stream);
 #endif

@@ -26,6 +26,15 @@ namespace upg
 			{
 				if (shape == S)
 				{
+#if UPG_ELEV == 0
+					// whole grid rows of the water field: the row-wise kernel (launch_field routes every planet's water launches here)
+					if (L.field == FD_WATER && !L.positions && L.count % (uint64_t)P.grid.res == 0)
+					{
+						const uint64_t rows = L.count / (uint64_t)P.grid.res;
+						shape_rows_kernel<S><<<(unsigned)((rows + SHAPE_ROWS - 1) / SHAPE_ROWS), FIELD_BLOCK, 0, stream>>>(P, L);
+						return true;
+					}
+#endif
 					const uint64_t blocks = (L.count + FIELD_BLOCK - 1) / FIELD_BLOCK;
 					sdf_sample_kernel<S, UPG_ELEV><<<(unsigned)blocks, FIELD_BLOCK, 0, stream>>>(P, L);
 					return true;

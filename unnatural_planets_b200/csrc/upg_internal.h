@@ -20,6 +20,7 @@ namespace upg
 		float *cellularTable = nullptr; // device: 1024 floats (FastNoiseLite RandVecs3D or its declared substitute)
 		float boxSize = 4000;
 		int device = 0;
+		int sampling = 0; // UPG_SAMPLING_* of include/upg.h
 		uint32_t *status = nullptr; // device: bit 0 = NaN sample seen
 	};
 
@@ -74,6 +75,11 @@ namespace upg
 	// K9 (upg_meshfix.cu): the clean-up chain of makeMesh / meshGenerateGeneric / meshGenerateBaseWater over device arrays; `stages` are
 	// the UPG_MESH_* bits of include/upg.h.  `out` receives fresh pool arrays (positions, normals, indices; no dualmc arrays).
 	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out);
+
+	// K1b (upg_band.cu): land / navigation of slices [za, zb) from the water (= shape) field of the same slices, exact wherever the
+	// isosurface can see the value; asynchronous on `stream`.  `evaluated`: optional device counter of evaluated nodes.
+	bool band_sampling_applies(const Planet *planet);
+	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream);
 
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
 	int check_status(Planet *planet, cudaStream_t stream, const char *what);

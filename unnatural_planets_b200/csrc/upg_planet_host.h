@@ -12,6 +12,7 @@
 // 288-306) first passes each static-local declaration.  upg_planet_desc::seed is that generator state.
 #pragma once
 
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 
@@ -368,5 +369,62 @@ namespace upg
 		P.grid.boxA = a;
 		P.grid.boxSpan = b - a;
 		P.grid.resMinus5 = (float)res - 5.0f;
+	}
+
+	// Bounds of elevation / 10 (the term the land and navigation fields subtract from the shape, sources/modesConfiguration.cpp:
+	// 248-279, meshElevationRatio = 10) over ALL positions, per elevation mode (sources/elevationModes.cpp), widened to contain 0
+	// so that the same pair also bounds max(elevation, 0) / 10.  Used by the band sampler (upg_band.cu) to decide where the sign
+	// of a sample is already settled by the shape alone.  Derivation: every single-octave generator is bounded by S (Value is a
+	// convex combination of hashes in [-1, 1); the Perlin / OpenSimplex2 suprema are 0.99999 / 0.99997, tools/noise_bounds.cpp;
+	// S carries 2 % on top), an fBm sum by S (the amplitudes are normalised by `bounding`), a ridged sum by 2S - 1; the rest is
+	// the monotone pieces of each mode followed through.  tests/test_host_terrain.py samples every mode against these numbers.
+	inline void elevation_interval10(int elevation, double *lo10, double *hi10)
+	{
+		const double S = 1.02;
+		const double F = 2 * S - 1;
+		double a = 0, b = 0;
+		switch (elevation)
+		{
+			case EL_NONE:
+				a = b = 100;
+				break;
+			case EL_SIMPLE:
+			{
+				// a = -ridged + 0.3; a = (a * 1.3 - 0.35)^3 + 0.1; 100 - a * 1000
+				const double tmin = (0.3 - F) * 1.3 - 0.35, tmax = (0.3 + F) * 1.3 - 0.35;
+				a = 100 - (tmax * tmax * tmax + 0.1) * 1000;
+				b = 100 - (tmin * tmin * tmin + 0.1) * 1000;
+				break;
+			}
+			case EL_LEGACY:
+				// a = fbm + 0.11; a < 0 ? -(-a)^0.85 : a^1.7; a * 2500
+				a = -std::pow(S - 0.11, 0.85) * 2500;
+				b = std::pow(S + 0.11, 1.7) * 2500;
+				break;
+			case EL_LAKES:
+			case EL_ISLANDS:
+			{
+				// land = l / (|l| + 0.17) + 0.15 with l in [-1, 1], times 150; the mountains add smoothMax(0, max(ridge, terraces), 50)
+				// which lies in [0, max(ridge, terraces) + 12.5]; ridge <= (F - 0.1)^1.6 * 1000, terraces <= (floor((S + 0.1) * 2.5) + 1) * 250
+				const double ridge = std::pow(F - 0.1, 1.6) * 1000;
+				const double terraces = (std::floor((S + 0.1) * 2.5) + 1) * 250;
+				a = (-1 / 1.17 + 0.15) * 150;
+				b = (1 / 1.17 + 0.15) * 150 + (ridge > terraces ? ridge : terraces) + 12.5;
+				break;
+			}
+			case EL_CRATERS:
+			{
+				// h = (x^4 - 0.9 x^5 - 0.1) * 10 on x in [0, 1]: -1 at 0, maximum at x = 8 / 9; 200 + h * 190
+				const double x = 8.0 / 9.0;
+				a = 200 + (-0.1 * 10) * 190;
+				b = 200 + (x * x * x * x - 0.9 * x * x * x * x * x - 0.1) * 10 * 190;
+				break;
+			}
+		}
+		const double slop = (b - a) * 0.01 + 0.5;
+		a = (a - slop) / 10;
+		b = (b + slop) / 10;
+		*lo10 = a < 0 ? a : 0;
+		*hi10 = b > 0 ? b : 0;
 	}
 }

@@ -113,7 +113,7 @@ def texture_tail(special=None, height=None, strength=1.0, device=0):
 
 
 class Planet:
-    def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0):
+    def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0, mesh_sampling="band"):
         L = capi.load_library()
         d = capi.PlanetDesc()
         L.upg_planet_desc_default(C.byref(d))
@@ -130,6 +130,7 @@ class Planet:
         d.box_size = box
         d.grid_resolution = grid
         d.device = device
+        d.mesh_sampling = capi.SAMPLING[mesh_sampling]
         self.res = grid
         self.box = box
         self.device = device
@@ -171,6 +172,14 @@ class Planet:
         pointers as integers, 0 = field not wanted."""
         vp = C.c_void_p
         capi.check(self._lib.upg_fields_samples_device(self._h, z0, z1, vp(d_land or None), vp(d_water or None), vp(d_navigation or None), vp(stream)))
+
+    def fields_samples_band_device(self, z0, z1, d_land=0, d_water=0, d_navigation=0, stream=0, count=False):
+        """the samples the mesh entry points extract from (upg_fields_samples_band_device): exact wherever the isosurface can see
+        the value, a value of the settled sign elsewhere; with count=True returns the number of nodes whose elevation was evaluated."""
+        vp = C.c_void_p
+        n = C.c_uint64(0)
+        capi.check(self._lib.upg_fields_samples_band_device(self._h, z0, z1, vp(d_land or None), vp(d_water or None), vp(d_navigation or None), vp(stream), C.byref(n) if count else None))
+        return int(n.value) if count else None
 
     # K1 + K2..K4 ---------------------------------------------------------------------------------
     def field_meshes(self, fields=("land", "water", "navigation")):
