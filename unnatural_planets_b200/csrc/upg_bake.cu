@@ -283,11 +283,14 @@ namespace upg
 			uint32_t *status;
 		};
 
+		// 80 registers per thread leave room for 768 resident threads per SM.  Two blocks of 384 beat one of 768 by 3.5 % (A/B on B200,
+		// profiles/r01_l_ab_color_block.txt: 15.19 vs 15.74 ms per 16.5 M-texel land bake; 3 x 256: 16.7, 1 x 512: 16.2): while one
+		// block waits at a layer barrier the other issues, and both still share the instruction cache.
 #ifndef UPG_COLOR_BLOCK
-#define UPG_COLOR_BLOCK 768
+#define UPG_COLOR_BLOCK 384
 #endif
 #ifndef UPG_COLOR_BLOCKS_PER_SM
-#define UPG_COLOR_BLOCKS_PER_SM 1
+#define UPG_COLOR_BLOCKS_PER_SM 2
 #endif
 		constexpr int COLOR_BLOCK = UPG_COLOR_BLOCK;
 
@@ -985,6 +988,8 @@ extern "C"
 		if (row0 == row1)
 			return UPG_OK;
 		int rc = UPG_OK;
+		const bool trace = trace_enabled();
+		double tr[6] = { trace ? now_ms() : 0, 0, 0, 0, 0, 0 };
 		{
 			Scratch mem(s);
 			const int ach = water ? 4 : 3;
@@ -1053,6 +1058,7 @@ extern "C"
 				}
 			}
 
+			tr[1] = trace ? now_ms() : 0; // allocation, clears, raster, compaction (ends in the synchronisation that reads the count)
 			// K6 in chunks of the list: bounds the scratch (9 probes x 16 B per texel) whatever the texture size
 			const uint32_t chunk = 1u << 22;
 			if (e == cudaSuccess && covered)
@@ -1091,6 +1097,11 @@ extern "C"
 				}
 			}
 
+			if (trace)
+			{
+				cudaStreamSynchronize(s);
+				tr[2] = now_ms();
+			}
 			// K7 over the band (its outer 7 rows are apron unless they are the image border), then the caller's rows
 			uint8_t *qAlbedo = q, *qSpecial = q + texels * ach, *qHeight = qSpecial + texels * 2;
 			const size_t skip = (size_t)(row0 - bandBegin) * w, keep = (size_t)(row1 - row0) * w;
@@ -1100,6 +1111,11 @@ extern "C"
 				e = dilate7(imgSpecial, w, bandH, 2, qSpecial, s);
 			if (e == cudaSuccess && rc == UPG_OK)
 				e = dilate7(imgHeight, w, bandH, 1, qHeight, s);
+			if (trace)
+			{
+				cudaStreamSynchronize(s);
+				tr[3] = now_ms();
+			}
 			if (e == cudaSuccess && rc == UPG_OK)
 				e = cudaMemcpyAsync(dAlbedo, qAlbedo + skip * ach, keep * ach, cudaMemcpyDefault, s);
 			if (e == cudaSuccess && rc == UPG_OK && dSpecial)
@@ -1128,6 +1144,8 @@ extern "C"
 			}
 			if (e == cudaSuccess)
 				e = cudaStreamSynchronize(s);
+			if (trace)
+				std::fprintf(stderr, "[upg]   bake core %s %ux%u rows [%u, %u): raster + compaction %.2f ms, colouring %.2f ms (%u texels), dilation %.2f ms, tail + copies out %.2f ms\n", water ? "water" : "land", w, h, row0, row1, tr[1] - tr[0], tr[2] - tr[1], covered, tr[3] - tr[2], now_ms() - tr[3]);
 			t_lastCovered = coveredRows;
 			if (rc == UPG_OK && e != cudaSuccess)
 				rc = cuda_fail(e, "upg_bake");
@@ -1222,24 +1240,39 @@ extern "C"
 		{
 			cudaStream_t s = cs.compute;
 			Scratch mem(s);
+			const double tUp = trace_enabled() ? now_ms() : 0;
 			float *dpos = mem.alloc<float>((size_t)nverts * 3);
 			float *dnrm = mem.alloc<float>((size_t)nverts * 3);
 			float *duv = mem.alloc<float>((size_t)nverts * 2);
 			uint32_t *didx = mem.alloc<uint32_t>(nidx);
 			e = mem.err;
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(dpos, positions, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(dnrm, normals, sizeof(float) * 3 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(duv, uvs, sizeof(float) * 2 * nverts, cudaMemcpyHostToDevice, s);
-			if (e == cudaSuccess)
-				e = cudaMemcpyAsync(didx, idx, sizeof(uint32_t) * nidx, cudaMemcpyHostToDevice, s);
+			void *staging = nullptr;
+			size_t stagingCapacity = 0;
 			if (e != cudaSuccess)
-				rc = cuda_fail(e, "upload mesh");
+				rc = cuda_fail(e, "cudaMallocAsync(mesh)");
+			else
+			{
+				// the rasteriser needs uvs + indices first; positions / normals follow while it runs
+				const HostArray arrays[4] = { { duv, uvs, sizeof(float) * 2 * nverts }, { didx, idx, sizeof(uint32_t) * nidx }, { dpos, positions, sizeof(float) * 3 * nverts }, { dnrm, normals, sizeof(float) * 3 * nverts } };
+				rc = upload_host_arrays(arrays, 4, s, &staging, &stagingCapacity);
+			}
+			const bool trace = trace_enabled();
+			const double t0 = trace ? now_ms() : 0;
+			if (trace)
+			{
+				cudaStreamSynchronize(s);
+				std::fprintf(stderr, "[upg] bake (host buffers): mesh upload %.2f ms (%.1f MB, waited %.2f ms after enqueueing)\n", now_ms() - tUp, (32.0 * nverts + 4.0 * nidx) * 1e-6, now_ms() - t0);
+			}
 			// the outputs are host memory: the core's final copies are cudaMemcpyDefault, so they land there directly
 			if (rc == UPG_OK)
 				rc = bake_core(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, albedo, special, heightMap, pbr, normalMap, 1.f, s);
+			if (staging)
+			{
+				cudaStreamSynchronize(s);
+				pinned_block_release(staging, stagingCapacity);
+			}
+			if (trace)
+				std::fprintf(stderr, "[upg] bake (host buffers): call %.2f ms\n", now_ms() - tUp);
 		}
 		cs.close();
 		return rc;

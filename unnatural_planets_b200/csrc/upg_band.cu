@@ -44,16 +44,35 @@ namespace upg
 			uint32_t zcount; // z-slices in this launch
 			uint32_t z0; // global index of the first one
 			uint32_t vector; // rows are 16-byte aligned in all three arrays: float4 loads / stores
+			uint32_t fill; // store `shape - hi` / `shape - lo` on the nodes whose elevation is not evaluated (0: leave them untouched)
+			// optional bit fields of both outputs (SignBits, upg_internal.h), zero-filled by the caller; bitPitch = 0: none
+			uint32_t *landSigns, *landNear, *navSigns, *navNear;
+			uint32_t bitPitch;
+			float nearTol;
 			float lo, hi, margin; // elevation / 10 lies in [lo, hi] (containing 0)
 			uint32_t *status; // bit 0: NaN sample
 			unsigned long long *evaluated; // statistics: nodes whose elevation was evaluated
 		};
 
-		// class of a node: +1 / -1 = the shape alone settles the sign of land and navigation, 0 = undecided
-		__device__ __forceinline__ int band_class(float w, float lo, float hi, float margin)
+		// class of a node: +1 / -1 = the shape alone settles the sign of land and navigation, 0 = undecided.  A function of the node's
+		// own value only, so every thread that looks at a node sees the same class.
+		__device__ __forceinline__ int band_class(float w, float above, float below)
 		{
 			// NaN compares false twice -> undecided -> evaluated exactly -> flagged like the dense kernel would
-			return (w - hi > margin) ? 1 : (w - lo < -margin) ? -1 : 0;
+			return w > above ? 1 : w < below ? -1 : 0;
+		}
+		// three-input minimum / maximum that return NaN when any input is NaN (FMNMX3.NAN)
+		__device__ __forceinline__ float band_min3(float a, float b, float c)
+		{
+			float r;
+			asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+			return r;
+		}
+		__device__ __forceinline__ float band_max3(float a, float b, float c)
+		{
+			float r;
+			asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+			return r;
 		}
 
 		// four consecutive samples of a row starting at node x (a multiple of 4); nodes beyond the row read as `pad`
@@ -72,6 +91,16 @@ namespace upg
 			}
 		}
 
+		// bit i of the low byte -> bit 4 i
+		__device__ __forceinline__ uint32_t band_spread4(uint32_t b)
+		{
+			b &= 0xffu;
+			b = (b | (b << 12)) & 0x000f000fu;
+			b = (b | (b << 6)) & 0x03030303u;
+			b = (b | (b << 3)) & 0x11111111u;
+			return b;
+		}
+
 		template<int ELEV>
 		__global__ void __launch_bounds__(BAND_BLOCK) band_sample_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ BandLaunch L)
 		{
@@ -88,106 +117,133 @@ namespace upg
 			const uint32_t rowCount = min((uint32_t)BAND_ROWS, L.rows - row0);
 			const uint32_t xSteps = (res + BAND_STEP - 1) / BAND_STEP;
 			const uint32_t steps = rowCount * xSteps;
-			const float lo = L.lo, hi = L.hi, margin = L.margin;
+			const float lo = L.lo, hi = L.hi;
+			const float above = L.hi + L.margin, below = L.lo - L.margin; // class thresholds
 			const bool vector = L.vector != 0;
 			const int64_t plane = (int64_t)res * res;
 			uint32_t head = 0, count = 0; // ring state, identical in every thread
 			uint32_t evaluated = 0;
+			// the scan position advances without divisions: r = row inside the block, xs = 1024-node step inside the row
+			uint32_t r = 0, xs = 0;
+			uint32_t zl = row0 / res;
+			uint32_t y = row0 - zl * res;
 			for (uint32_t step = 0; step < steps; step++)
 			{
-				const uint32_t r = step / xSteps;
-				const uint32_t x = (step - r * xSteps) * BAND_STEP + tid * BAND_NODES;
+				const uint32_t x = xs * BAND_STEP + tid * BAND_NODES;
 				const uint32_t row = row0 + r;
-				const uint32_t zl = row / res;
-				const uint32_t y = row - zl * res;
 				bool need[BAND_NODES] = { false, false, false, false };
+				uint32_t positive = 0; // bit k: node k is settled on the positive side
+				bool any = false;
 				if (x < res)
 				{
 					const uint64_t idx = (uint64_t)row * res + x;
 					const float *w = L.water + idx;
-					float v[BAND_NODES], t[BAND_NODES];
-					int c[BAND_NODES];
-					bool differs[BAND_NODES];
+					float v[BAND_NODES], ym[BAND_NODES], yp[BAND_NODES], zm[BAND_NODES], zp[BAND_NODES];
 					band_load4(w, x, res, vector, 0.0f, v);
 #pragma unroll
-					for (int k = 0; k < BAND_NODES; k++)
-						c[k] = band_class(v[k], lo, hi, margin);
-					// an edge to a node of another class may change sign: both of its end points are evaluated
-					const int left = x > 0 ? band_class(w[-1], lo, hi, margin) : c[0];
-					const int right = x + BAND_NODES < res ? band_class(w[BAND_NODES], lo, hi, margin) : c[BAND_NODES - 1];
+					for (int k = 1; k < BAND_NODES; k++)
+						v[k] = x + k < res ? v[k] : v[0]; // nodes beyond the row: copies of a real one, never stored
+					// the six neighbours; a neighbour that does not exist is replaced by the node itself
+					const float left = x > 0 ? w[-1] : v[0];
+					const float right = x + BAND_NODES < res ? w[BAND_NODES] : v[BAND_NODES - 1];
 #pragma unroll
 					for (int k = 0; k < BAND_NODES; k++)
-					{
-						const int l = k == 0 ? left : c[k - 1];
-						// the right neighbour of the last node of the row does not exist; c[k + 1] of a padded node is never used
-						const int rr = k == BAND_NODES - 1 ? right : (x + k + 1 < res ? c[k + 1] : c[k]);
-						differs[k] = l != c[k] || rr != c[k];
-					}
+						ym[k] = yp[k] = zm[k] = zp[k] = v[k];
 					if (y > 0)
-					{
-						band_load4(w - res, x, res, vector, 0.0f, t);
-#pragma unroll
-						for (int k = 0; k < BAND_NODES; k++)
-							differs[k] |= band_class(t[k], lo, hi, margin) != c[k];
-					}
+						band_load4(w - res, x, res, vector, v[0], ym);
 					if (y + 1 < res)
-					{
-						band_load4(w + res, x, res, vector, 0.0f, t);
-#pragma unroll
-						for (int k = 0; k < BAND_NODES; k++)
-							differs[k] |= band_class(t[k], lo, hi, margin) != c[k];
-					}
+						band_load4(w + res, x, res, vector, v[0], yp);
 					if (zl > 0)
-					{
-						band_load4(w - plane, x, res, vector, 0.0f, t);
-#pragma unroll
-						for (int k = 0; k < BAND_NODES; k++)
-							differs[k] |= band_class(t[k], lo, hi, margin) != c[k];
-					}
+						band_load4(w - plane, x, res, vector, v[0], zm);
 					if (zl + 1 < L.zcount)
+						band_load4(w + plane, x, res, vector, v[0], zp);
+					// nearly always the 22 values lie on one side of the band: two NaN-propagating reductions settle the four nodes
+					float mn = band_min3(band_min3(v[0], v[1], v[2]), band_min3(v[3], left, right), band_min3(ym[0], ym[1], ym[2]));
+					mn = band_min3(mn, band_min3(ym[3], yp[0], yp[1]), band_min3(yp[2], yp[3], zm[0]));
+					mn = band_min3(mn, band_min3(zm[1], zm[2], zm[3]), band_min3(zp[0], zp[1], zp[2]));
+					mn = band_min3(mn, zp[3], zp[3]);
+					float mx = band_max3(band_max3(v[0], v[1], v[2]), band_max3(v[3], left, right), band_max3(ym[0], ym[1], ym[2]));
+					mx = band_max3(mx, band_max3(ym[3], yp[0], yp[1]), band_max3(yp[2], yp[3], zm[0]));
+					mx = band_max3(mx, band_max3(zm[1], zm[2], zm[3]), band_max3(zp[0], zp[1], zp[2]));
+					mx = band_max3(mx, zp[3], zp[3]);
+					const uint32_t inRow = res - x >= BAND_NODES ? 0xfu : (1u << (res - x)) - 1u;
+					if (mn > above)
+						positive = inRow;
+					else if (!(mx < below))
 					{
-						band_load4(w + plane, x, res, vector, 0.0f, t);
+						// near the band: node by node.  An edge to a node of another class may change sign: both of its end points are evaluated
+						int c[BAND_NODES];
 #pragma unroll
 						for (int k = 0; k < BAND_NODES; k++)
-							differs[k] |= band_class(t[k], lo, hi, margin) != c[k];
-					}
-					float fill[BAND_NODES];
-					bool any = false;
-#pragma unroll
-					for (int k = 0; k < BAND_NODES; k++)
-					{
-						need[k] = x + k < res && (c[k] == 0 || differs[k]);
-						any |= need[k];
-						fill[k] = c[k] > 0 ? v[k] - hi : v[k] - lo;
-					}
-					if (!any && vector && x + BAND_NODES <= res)
-					{
-						const float4 f4 = make_float4(fill[0], fill[1], fill[2], fill[3]);
-						if (L.land)
-							*reinterpret_cast<float4 *>(L.land + idx) = f4;
-						if (L.navigation)
-							*reinterpret_cast<float4 *>(L.navigation + idx) = f4;
-					}
-					else
-					{
+							c[k] = band_class(v[k], above, below);
+						const int cl = band_class(left, above, below), cr = band_class(right, above, below);
 #pragma unroll
 						for (int k = 0; k < BAND_NODES; k++)
-							if (x + k < res && !need[k])
-							{
-								if (L.land)
-									L.land[idx + k] = fill[k];
-								if (L.navigation)
-									L.navigation[idx + k] = fill[k];
-							}
+						{
+							const int l = k == 0 ? cl : c[k - 1];
+							const int rr = k == BAND_NODES - 1 ? cr : c[k + 1];
+							const bool differs = l != c[k] || rr != c[k] || band_class(ym[k], above, below) != c[k] || band_class(yp[k], above, below) != c[k] || band_class(zm[k], above, below) != c[k] || band_class(zp[k], above, below) != c[k];
+							need[k] = ((inRow >> k) & 1u) && (c[k] == 0 || differs);
+							any |= need[k];
+							if (((inRow >> k) & 1u) && !need[k] && c[k] > 0)
+								positive |= 1u << k;
+						}
+					}
+					if (L.fill)
+					{
+						if (!any && vector && inRow == 0xfu)
+						{
+							const float off = positive ? hi : lo; // all four on the same side: an edge between two settled nodes of different sides would have made both `need`
+							const float4 f4 = make_float4(v[0] - off, v[1] - off, v[2] - off, v[3] - off);
+							if (L.land)
+								*reinterpret_cast<float4 *>(L.land + idx) = f4;
+							if (L.navigation)
+								*reinterpret_cast<float4 *>(L.navigation + idx) = f4;
+						}
+						else
+						{
+#pragma unroll
+							for (int k = 0; k < BAND_NODES; k++)
+								if (((inRow >> k) & 1u) && !need[k])
+								{
+									const float f = v[k] - (((positive >> k) & 1u) ? hi : lo);
+									if (L.land)
+										L.land[idx + k] = f;
+									if (L.navigation)
+										L.navigation[idx + k] = f;
+								}
+						}
+					}
+				}
+				if (L.bitPitch)
+				{
+					// the sign bits of the settled nodes (the same for land and navigation): lane l holds the nibble of nodes 4 l .. 4 l + 3 of
+					// the warp's 128; three shuffles gather eight nibbles into lanes 0, 8, 16, 24.  The nodes to evaluate contribute their
+					// bit after the evaluation (drain below, atomicOr: same block, ordered by the barrier).
+					uint32_t word = positive;
+					word |= __shfl_down_sync(0xffffffffu, word, 1) << 4;
+					word |= __shfl_down_sync(0xffffffffu, word, 2) << 8;
+					word |= __shfl_down_sync(0xffffffffu, word, 4) << 16;
+					const uint32_t wx = (xs * BAND_STEP + warp * 32u * BAND_NODES) / 32u + (lane >> 3);
+					if ((lane & 7u) == 0 && wx * 32u < res)
+					{
+						const uint64_t at = (uint64_t)row * L.bitPitch + wx;
+						if (L.landSigns)
+							L.landSigns[at] = word;
+						if (L.navSigns)
+							L.navSigns[at] = word;
 					}
 				}
 				// push the nodes to evaluate into the ring
-				uint32_t votes[BAND_NODES], mine = 0;
-#pragma unroll
-				for (int k = 0; k < BAND_NODES; k++)
+				uint32_t votes[BAND_NODES] = { 0, 0, 0, 0 }, mine = 0;
+				if (__any_sync(0xffffffffu, any))
 				{
-					votes[k] = __ballot_sync(0xffffffffu, need[k]);
-					mine += __popc(votes[k]);
+#pragma unroll
+					for (int k = 0; k < BAND_NODES; k++)
+					{
+						votes[k] = __ballot_sync(0xffffffffu, need[k]);
+						mine += __popc(votes[k]);
+					}
 				}
 				if (lane == 0)
 					warpCount[warp] = mine;
@@ -200,13 +256,27 @@ namespace upg
 					before += k < warp ? n : 0u;
 					total += n;
 				}
-				uint32_t slot = head + count + before;
-#pragma unroll
-				for (int k = 0; k < BAND_NODES; k++)
+				if (mine)
 				{
-					if (need[k])
-						ring[(slot + __popc(votes[k] & ((1u << lane) - 1u))) & (BAND_RING - 1u)] = r * res + x + k;
-					slot += __popc(votes[k]);
+					uint32_t slot = head + count + before;
+#pragma unroll
+					for (int k = 0; k < BAND_NODES; k++)
+					{
+						if (need[k])
+							ring[(slot + __popc(votes[k] & ((1u << lane) - 1u))) & (BAND_RING - 1u)] = r * res + x + k;
+						slot += __popc(votes[k]);
+					}
+				}
+				// next scan position
+				if (++xs == xSteps)
+				{
+					xs = 0;
+					r++;
+					if (++y == res)
+					{
+						y = 0;
+						zl++;
+					}
 				}
 				count += total;
 				__syncthreads();
@@ -243,6 +313,25 @@ namespace upg
 						}
 						if (bad)
 							atomicOr(L.status, 1u);
+						if (L.bitPitch)
+						{
+							const uint64_t at = (uint64_t)erow * L.bitPitch + (ex >> 5);
+							const uint32_t bit = 1u << (ex & 31u);
+							if (L.landSigns)
+							{
+								if (land >= 0.0f)
+									atomicOr(L.landSigns + at, bit);
+								if (abs_(land) < L.nearTol)
+									atomicOr(L.landNear + at, bit);
+							}
+							if (L.navSigns)
+							{
+								if (nav >= 0.0f)
+									atomicOr(L.navSigns + at, bit);
+								if (abs_(nav) < L.nearTol)
+									atomicOr(L.navNear + at, bit);
+							}
+						}
 					}
 					head += n;
 					count -= n;
@@ -268,7 +357,7 @@ namespace upg
 	}
 
 	// land / navigation over z-slices [za, zb) given the water field of the same slices; asynchronous on `stream`
-	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream)
+	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits, const SignBits *navigationBits, bool fill)
 	{
 		const PlanetParams &P = planet->params;
 		const uint32_t res = (uint32_t)P.grid.res;
@@ -286,11 +375,23 @@ namespace upg
 		L.lo = (float)lo;
 		L.hi = (float)hi;
 		// the float subtraction of the field and the one of the classification round independently (relative 2^-24 of values up to
-		// the box diagonal ~3500 + |hi|): 1/64 is two orders of magnitude above that and ten times the near-zero threshold 1e-3
-		L.margin = 0.015625f;
+		// the box diagonal ~3500 + |hi|): 1/32 is two orders of magnitude above that and keeps every stored value at least 1/64 from zero,
+		// fifteen times the near-zero threshold 1e-3
+		L.margin = 0.03125f;
 		L.vector = res % 4 == 0 && ((uintptr_t)water & 15) == 0 && ((uintptr_t)land & 15) == 0 && ((uintptr_t)navigation & 15) == 0;
 		L.status = planet->status;
 		L.evaluated = evaluated;
+		L.fill = fill ? 1u : 0u;
+		L.landSigns = land && landBits ? landBits->signs : nullptr;
+		L.landNear = land && landBits ? landBits->near : nullptr;
+		L.navSigns = navigation && navigationBits ? navigationBits->signs : nullptr;
+		L.navNear = navigation && navigationBits ? navigationBits->near : nullptr;
+		L.bitPitch = L.landSigns ? landBits->pitch : L.navSigns ? navigationBits->pitch : 0u;
+		L.nearTol = NEAR_ZERO_TOLERANCE;
+		if (L.landSigns && L.navSigns && landBits->pitch != navigationBits->pitch)
+			return fail(UPG_ERR_ARGUMENT, "bit fields of different pitch");
+		if (!fill && ((land && !L.landSigns) || (navigation && !L.navSigns)))
+			return fail(UPG_ERR_ARGUMENT, "band sampling without fill values needs the bit fields");
 		switch (P.elevation)
 		{
 			case EL_SIMPLE:

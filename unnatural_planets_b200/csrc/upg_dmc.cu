@@ -197,55 +197,127 @@ namespace upg
 			}
 		}
 
+		// The same pass from the samplers' bit fields (SignBits, upg_internal.h): 1 bit instead of 4 bytes read per node.  One WARP walks
+		// one row of cells, a lane 32 consecutive cells: bits x0 .. x0 + 32 of the four sample rows that bound the cell row (a word and
+		// the first bit of the next; rows carry an all-zero padding word), 32 codes = 8 code words.  Nearly every lane sees four uniform
+		// bit strings (far from the surface) and stores eight constant words; per-row quad counts come from a warp reduction.
+		constexpr int DMC_BITS_WARPS = 8;
+		__global__ void __launch_bounds__(DMC_BITS_WARPS * 32) dmc_cell_codes_bits(const uint32_t *__restrict__ signs, const uint32_t *__restrict__ nearBits, uint32_t pitch, Dims d, uint8_t *__restrict__ codes, uint32_t *__restrict__ rowQuads, unsigned long long *__restrict__ nearZero)
+		{
+			const uint32_t row = blockIdx.x * DMC_BITS_WARPS + (threadIdx.x >> 5);
+			if (row >= (uint32_t)d.rows())
+				return;
+			const uint32_t lane = threadIdx.x & 31u;
+			const int32_t z = (int32_t)(row / (uint32_t)d.cy()), y = (int32_t)(row - (uint32_t)z * (uint32_t)d.cy());
+			const int32_t cx = d.cx();
+			const uint64_t at = ((uint64_t)z * d.ry + y) * pitch;
+			const uint32_t *b00 = signs + at;
+			const uint32_t *b01 = b00 + pitch; // y + 1
+			const uint32_t *b10 = b00 + (uint64_t)d.ry * pitch; // z + 1
+			const uint32_t *b11 = b10 + pitch;
+			uint32_t *codeWords = reinterpret_cast<uint32_t *>(codes + (uint64_t)row * (uint32_t)d.codePitch());
+			uint32_t nq = 0, nz = 0;
+			for (int32_t x0 = (int32_t)lane * 32; x0 < cx; x0 += 32 * 32)
+			{
+				const uint32_t w = (uint32_t)x0 >> 5;
+				const uint32_t cellsHere = (uint32_t)min(32, cx - x0);
+				// samples within tolerance of zero among the cell origins of this row (the statistic of the float pass)
+				nz += __popc(__ldg(nearBits + at + w) & (cellsHere == 32u ? 0xffffffffu : (1u << cellsHere) - 1u));
+				const uint32_t l00 = __ldg(b00 + w), l01 = __ldg(b01 + w), l10 = __ldg(b10 + w), l11 = __ldg(b11 + w);
+				const uint32_t h00 = __ldg(b00 + w + 1), h01 = __ldg(b01 + w + 1), h10 = __ldg(b10 + w + 1), h11 = __ldg(b11 + w + 1);
+				const uint32_t words = (cellsHere + 3u) >> 2;
+				const uint32_t all = l00 & l01 & l10 & l11, any = l00 | l01 | l10 | l11;
+				const uint32_t next = (h00 & h01 & h10 & h11 & 1u) | ((h00 | h01 | h10 | h11) & 1u) << 1; // 0: all clear, 3: all set
+				if (cellsHere == 32u && ((any == 0u && next == 0u) || (all == 0xffffffffu && next == 3u)))
+				{
+					const uint32_t fillWord = any ? 0xffffffffu : 0u; // every corner of every cell on the same side: no quad here
+#pragma unroll
+					for (uint32_t k = 0; k < 8; k++)
+						codeWords[(x0 >> 2) + k] = fillWord;
+					continue;
+				}
+				const uint64_t s00 = l00 | (uint64_t)(h00 & 1u) << 32, s01 = l01 | (uint64_t)(h01 & 1u) << 32;
+				const uint64_t s10 = l10 | (uint64_t)(h10 & 1u) << 32, s11 = l11 | (uint64_t)(h11 & 1u) << 32;
+				for (uint32_t k4 = 0; k4 < words; k4++)
+				{
+					uint32_t word = 0;
+#pragma unroll
+					for (uint32_t k = 0; k < 4; k++)
+					{
+						const uint32_t c = k4 * 4 + k;
+						if (c >= cellsHere)
+							break;
+						// corner id = x + 2y + 4z
+						const uint32_t code = (uint32_t)((s00 >> c) & 3u) | ((uint32_t)((s01 >> c) & 3u) << 2) | ((uint32_t)((s10 >> c) & 3u) << 4) | ((uint32_t)((s11 >> c) & 3u) << 6);
+						word |= code << (8 * k);
+						nq += __popc(quad_mask(d, x0 + (int32_t)c, y, z, code));
+					}
+					codeWords[(x0 >> 2) + k4] = word;
+				}
+			}
+			for (int o = 16; o > 0; o >>= 1)
+			{
+				nq += __shfl_down_sync(0xffffffffu, nq, o);
+				nz += __shfl_down_sync(0xffffffffu, nz, o);
+			}
+			if (lane == 0)
+			{
+				rowQuads[row] = nq;
+				if (nz)
+					atomicAdd(nearZero, (unsigned long long)nz);
+			}
+		}
+
 		// ---- pass 2: ordered quad compaction ----------------------------------------------------------------
 		// quadCell[q] = linear cell index of the anchoring grid point, quadInfo[q] = axis | firstOrder << 2
-		__global__ void __launch_bounds__(DMC_ROW_MAX_THREADS) dmc_emit_quads(Dims d, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ rowOffsets, const uint32_t *__restrict__ rowQuads, uint32_t *__restrict__ quadCell, uint8_t *__restrict__ quadInfo, uint32_t *__restrict__ quadBase)
+		// One WARP per row of cells (rows without quads -- three in four even on the rows that cross a planet, nearly all elsewhere -- cost
+		// one 4-byte read per warp), a lane four consecutive cells per step, the ordered offsets from a warp prefix: no block barrier.
+		constexpr int DMC_EMIT_WARPS = 8;
+		__global__ void __launch_bounds__(DMC_EMIT_WARPS * 32) dmc_emit_quads(Dims d, const uint8_t *__restrict__ codes, const uint32_t *__restrict__ rowOffsets, const uint32_t *__restrict__ rowQuads, uint32_t *__restrict__ quadCell, uint8_t *__restrict__ quadInfo, uint32_t *__restrict__ quadBase)
 		{
-			const uint32_t row = blockIdx.x;
-			if (rowQuads[row] == 0)
-				return; // nothing to emit in this row (the vast majority): 4 bytes read
+			const uint32_t row = blockIdx.x * DMC_EMIT_WARPS + (threadIdx.x >> 5);
+			if (row >= (uint32_t)d.rows() || rowQuads[row] == 0)
+				return;
+			const uint32_t lane = threadIdx.x & 31u;
 			const int32_t z = (int32_t)(row / (uint32_t)d.cy()), y = (int32_t)(row - (uint32_t)z * (uint32_t)d.cy());
 			const int32_t cx = d.cx();
 			const uint32_t *codeWords = reinterpret_cast<const uint32_t *>(codes + (uint64_t)row * (uint32_t)d.codePitch());
 			const uint32_t rowL = row * (uint32_t)cx; // linear index of the row's first cell
-			__shared__ uint32_t warpSum[DMC_ROW_MAX_THREADS / 32];
-			__shared__ uint32_t carry;
-			if (threadIdx.x == 0)
-				carry = rowOffsets[row];
-			__syncthreads();
-			const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = (blockDim.x + 31) / 32;
-			for (int32_t c0 = 0; c0 < cx; c0 += (int32_t)blockDim.x * 4)
+			uint32_t carry = rowOffsets[row];
+			for (int32_t c0 = 0; c0 < cx; c0 += 32 * 4)
 			{
-				const int32_t x0 = c0 + (int32_t)threadIdx.x * 4;
+				const int32_t x0 = c0 + (int32_t)lane * 4;
 				uint32_t word = 0, masks = 0, nq = 0;
 				if (x0 < cx)
 				{
 					word = __ldg(codeWords + (x0 >> 2));
-#pragma unroll
-					for (int k = 0; k < 4; k++)
+					// four cells all inside or all outside emit nothing (their shared edges do not cross either)
+					if (word != 0u && word != 0xffffffffu)
 					{
-						if (x0 + k >= cx)
-							break;
-						const uint32_t m = quad_mask(d, x0 + k, y, z, (word >> (8 * k)) & 0xffu);
-						masks |= m << (4 * k);
-						nq += __popc(m);
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+						{
+							if (x0 + k >= cx)
+								break;
+							const uint32_t m = quad_mask(d, x0 + k, y, z, (word >> (8 * k)) & 0xffu);
+							masks |= m << (4 * k);
+							nq += __popc(m);
+						}
 					}
 				}
-				// exclusive prefix inside the block, in x order
+				// exclusive prefix inside the warp, in x order
 				uint32_t incl = nq;
+#pragma unroll
 				for (int o = 1; o < 32; o <<= 1)
 				{
 					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
 					if (lane >= (uint32_t)o)
 						incl += t;
 				}
-				if (lane == 31)
-					warpSum[warp] = incl;
-				__syncthreads();
-				uint32_t base = carry;
-				for (uint32_t w = 0; w < warp; w++)
-					base += warpSum[w];
-				uint32_t q = base + incl - nq;
+				uint32_t q = carry + incl - nq;
+				carry += __shfl_sync(0xffffffffu, incl, 31);
+				if (!masks)
+					continue;
 #pragma unroll
 				for (int k = 0; k < 4; k++)
 				{
@@ -276,15 +348,6 @@ namespace upg
 						q++;
 					}
 				}
-				__syncthreads();
-				if (threadIdx.x == 0)
-				{
-					uint32_t total = 0;
-					for (uint32_t w = 0; w < warps; w++)
-						total += warpSum[w];
-					carry += total;
-				}
-				__syncthreads();
 			}
 		}
 
@@ -739,7 +802,7 @@ namespace upg
 
 	// Everything on `s`; the caller owns `dens` (rx*ry*rz floats on the device).  Outputs are device arrays allocated
 	// with cudaMallocAsync on `s` (released by dmc_release).
-	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset, int ownZ0, int ownZ1)
+	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset, int ownZ0, int ownZ1, const SignBits *bits)
 	{
 		out = DmcResult();
 		const Dims d{ rx, ry, rz, zOffset };
@@ -785,7 +848,10 @@ namespace upg
 		UPG_TRY(cudaMemsetAsync(nearZero, 0, sizeof(unsigned long long), s));
 		if (e == cudaSuccess)
 		{
-			dmc_cell_codes<<<blocks, rowThreads, 0, s>>>(dens, d, codes, blockQuads, nearZero, 1e-3f);
+			if (bits && bits->signs)
+				dmc_cell_codes_bits<<<(blocks + DMC_BITS_WARPS - 1) / DMC_BITS_WARPS, DMC_BITS_WARPS * 32, 0, s>>>(bits->signs, bits->near, bits->pitch, d, codes, blockQuads, nearZero);
+			else
+				dmc_cell_codes<<<blocks, rowThreads, 0, s>>>(dens, d, codes, blockQuads, nearZero, NEAR_ZERO_TOLERANCE);
 			UPG_LAUNCHED();
 		}
 		UPG_TRY(exclusive_scan_u32(blockQuads, blockOffsets, blocks, s));
@@ -808,7 +874,7 @@ namespace upg
 			UPG_TRY(dalloc(&vids, nSlots, s));
 			if (e == cudaSuccess)
 			{
-				dmc_emit_quads<<<blocks, rowThreads, 0, s>>>(d, codes, blockOffsets, blockQuads, quadCell, quadInfo, quadBase);
+				dmc_emit_quads<<<(blocks + DMC_EMIT_WARPS - 1) / DMC_EMIT_WARPS, DMC_EMIT_WARPS * 32, 0, s>>>(d, codes, blockOffsets, blockQuads, quadCell, quadInfo, quadBase);
 				UPG_LAUNCHED();
 			}
 			const uint32_t slotBlocks = (nSlots + DMC_BLOCK - 1) / DMC_BLOCK;

@@ -25,6 +25,12 @@ namespace upg
 		uint32_t z0; // first z-slice (grid mode)
 		int32_t field; // Field
 		uint32_t *status; // device status word
+		// row-wise water launches only (shape_rows_kernel): optional sign / near-zero bit fields of the samples, one bit per node,
+		// bit (x & 31) of word (row * bitPitch + (x >> 5)); see SignBits in upg_internal.h
+		uint32_t *signBits = nullptr;
+		uint32_t *nearBits = nullptr;
+		uint32_t bitPitch = 0;
+		float nearTol = 0;
 	};
 
 	// runtime field selection (uniform across the grid) over the compile-time shape / elevation pair
@@ -159,11 +165,30 @@ namespace upg
 			const uint32_t zl = row / res;
 			const float cy = coord[row - zl * res], cz = coord[L.z0 + zl];
 			float *out = L.out + (uint64_t)row * res;
-			for (uint32_t x = threadIdx.x; x < res; x += FIELD_BLOCK)
+			// every warp stays whole through the loop (x0 is warp uniform): its 32 samples are one word of the bit fields
+			for (uint32_t x0 = threadIdx.x & ~31u; x0 < res; x0 += FIELD_BLOCK)
 			{
-				const float v = shape_sdf<SHAPE>(P, v3(coord[x], cy, cz));
-				bad |= isnan_(v);
-				out[x] = v;
+				const uint32_t x = x0 + (threadIdx.x & 31u);
+				float v = -1.0f;
+				if (x < res)
+				{
+					v = shape_sdf<SHAPE>(P, v3(coord[x], cy, cz));
+					bad |= isnan_(v);
+					out[x] = v;
+				}
+				if (L.signBits)
+				{
+					// the extraction's inside test (`>= iso`, dualmc.tpp:12-32) and its near-zero statistic, taken here once
+					const uint32_t sign = __ballot_sync(0xffffffffu, x < res && v >= 0.0f);
+					const uint32_t near = __ballot_sync(0xffffffffu, x < res && abs_(v) < L.nearTol);
+					if ((threadIdx.x & 31u) == 0)
+					{
+						const uint64_t word = (uint64_t)row * L.bitPitch + (x0 >> 5);
+						L.signBits[word] = sign;
+						if (near)
+							L.nearBits[word] = near;
+					}
+				}
 			}
 		}
 		if (bad)

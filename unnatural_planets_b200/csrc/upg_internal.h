@@ -3,6 +3,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstddef>
+
 #include "upg_field.cuh"
 #include "upg_planet_host.h"
 
@@ -67,9 +69,22 @@ namespace upg
 		uint32_t firstVertex = 0, ownedVertices = 0, firstQuad = 0, ownedQuads = 0, firstTriangle = 0, ownedTriangles = 0;
 		uint64_t nearZeroSamples = 0; // samples with |value| < 1e-3: where topology parity is not promised
 	};
+	// What the dense passes of the extraction need of a sample field, as bits (one per node, rows of `pitch` words, bit x & 31 of word
+	// x >> 5, at least one all-zero padding word behind the last sample of a row): `signs` = sample >= 0 (getCellCode's inside test),
+	// `near` = |sample| < 1e-3 (DmcResult::nearZeroSamples).  Written by the samplers (shape_rows_kernel, band_sample_kernel) so that
+	// the cell-code pass reads 1 bit instead of 4 bytes per node and the band sampler need not store what nobody reads.
+	struct SignBits
+	{
+		uint32_t *signs = nullptr;
+		uint32_t *near = nullptr;
+		uint32_t pitch = 0;
+	};
+	inline uint32_t sign_bits_pitch(int res) { return (uint32_t)((res + 31) / 32 + 1); }
+	constexpr float NEAR_ZERO_TOLERANCE = 1e-3f;
+
 	// zOffset: global z of local slice 0; [ownZ0, ownZ1): global scan iterations (dualmc's z loop) whose quads / created vertices /
 	// triangles are reported (defaults = the whole volume)
-	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset = 0, int ownZ0 = 0, int ownZ1 = 0x7fffffff);
+	int dmc_extract(const float *dens, int rx, int ry, int rz, float boxSize, int fullRes, cudaStream_t s, DmcResult &out, int zOffset = 0, int ownZ0 = 0, int ownZ1 = 0x7fffffff, const SignBits *bits = nullptr);
 	void dmc_release(DmcResult &r, cudaStream_t s);
 
 	// K9 (upg_meshfix.cu): the clean-up chain of makeMesh / meshGenerateGeneric / meshGenerateBaseWater over device arrays; `stages` are
@@ -79,7 +94,23 @@ namespace upg
 	// K1b (upg_band.cu): land / navigation of slices [za, zb) from the water (= shape) field of the same slices, exact wherever the
 	// isosurface can see the value; asynchronous on `stream`.  `evaluated`: optional device counter of evaluated nodes.
 	bool band_sampling_applies(const Planet *planet);
-	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream);
+	// With `landBits` / `navigationBits` (zero-filled by the caller) the kernel also writes the sign / near-zero bits of both fields and,
+	// unless `fill`, stores sample VALUES only where it evaluated them (all that dmc_build reads).
+	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits = nullptr, const SignBits *navigationBits = nullptr, bool fill = true);
+
+	// cached pinned host blocks (upg_api.cu) and the staged upload of pageable host arrays built on them
+	cudaError_t pinned_block_acquire(size_t bytes, void **out, size_t *capacity);
+	void pinned_block_release(void *ptr, size_t capacity);
+	struct HostArray
+	{
+		void *dst; // device
+		const void *src; // host, pageable or pinned
+		size_t bytes;
+	};
+	int upload_host_arrays(const HostArray *arrays, int n, cudaStream_t stream, void **staging, size_t *stagingCapacity);
+
+	bool trace_enabled(); // UPG_TRACE=1
+	double now_ms();
 
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
 	int check_status(Planet *planet, cudaStream_t stream, const char *what);
