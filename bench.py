@@ -455,6 +455,74 @@ def run_ours(args, rank, world, local_rank):
             }
         del smeshes, src
 
+    # ---- leg 5: a batch of planets back to back (BASELINE configs[3]: random base shape per seed, every elevation mode) ----
+    batch_line = None
+    if args.batch > 0:
+        from unnatural_planets_b200 import ELEVATIONS, SHAPES, UpgError, synth
+
+        try:
+            del dmesh, outs
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        bres, btex = args.batch_grid, args.batch_texture
+        mine = list(range(rank, args.batch, world))  # replicas: planet i on rank i mod N, no communication
+        bhost = {"land": [torch.empty(btex * btex * 3, dtype=torch.uint8, pin_memory=True) for _ in range(3)], "water": [torch.empty(btex * btex * c, dtype=torch.uint8, pin_memory=True) for c in (4, 3, 3)]}
+
+        def batch_planet(i, timed):
+            seed = seed_for(1000 + i)
+            shape = SHAPES[seed[0] % len(SHAPES)]  # `--shape random` draws randomRange(0u, 34) (sources/modesConfiguration.cpp:121)
+            elev = ELEVATIONS[i % len(ELEVATIONS)]
+            t0 = time.perf_counter()
+            bp = Planet(shape=shape, elevation=elev, coloring=COLORING, grid=bres, device=local_rank, seed=seed)
+            try:
+                final = bp.field_meshes_clean(FIELDS)
+            except UpgError as ex:  # the reference throws for the same planets ("generated empty base land mesh", NaN sdf)
+                bp.close()
+                return {"i": i, "shape": shape, "elevation": elev, "error": ex.code}, time.perf_counter() - t0, 0.0, 0
+            t_mesh = time.perf_counter() - t0
+            # the generator would simplify, chunk and unwrap here (host geometry, out of scope): synthetic chart, outside the timing
+            t_bake, texels_b = 0.0, 0
+            for name, water in (("land", 0), ("water", 1)):
+                m = final[name]
+                if len(m["indices"]) == 0:
+                    continue
+                uv = synth.octahedral_uv(m["positions"])
+                idx = synth.drop_folded_triangles(uv, m["indices"])
+                o = bhost[name]
+                t1 = time.perf_counter()
+                capi.check(L.upg_bake_export(bp._h, water, m["positions"].ctypes.data_as(C.c_void_p), m["normals"].ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(uv), idx.ctypes.data_as(C.c_void_p), len(idx), btex, btex, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr())))
+                t_bake += time.perf_counter() - t1
+                texels_b += int(L.upg_bake_last_covered_texels())
+            info = {"i": i, "shape": shape, "elevation": elev, "land_triangles": int(len(final["land"]["indices"]) // 3), "mesh_ms": round(t_mesh * 1e3, 2), "bake_ms": round(t_bake * 1e3, 2)}
+            bp.close()
+            return info, t_mesh, t_bake, texels_b
+
+        if mine:
+            batch_planet(mine[0], False)  # warms the pools for this grid / texture size
+        barrier()
+        infos, sum_mesh, sum_bake, sum_texels = [], 0.0, 0.0, 0
+        for i in mine:
+            info, tm, tb, tx = batch_planet(i, True)
+            infos.append(info)
+            sum_mesh += tm
+            sum_bake += tb
+            sum_texels += tx
+        bt = torch.tensor([sum_mesh, sum_bake], dtype=torch.float64, device=dev)
+        bc = torch.tensor([float(sum_texels), float(sum(1 for x in infos if "error" in x))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bc, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            shapes_seen = sorted({x["shape"] for x in infos})
+            batch_line = {
+                "what": "BASELINE configs[3]: %d planets back to back, seed i -> shape = seed %% 34 (the reference's `random`), elevation = mode i %% 6, %d^3 grid, %d^2 land + water export bake; per planet: upg_planet_create + upg_field_meshes_clean + 2 x upg_bake_export, host buffers, wall clock of the C calls (synthetic UV chart on the host outside the timing); planets are replicas across ranks" % (args.batch, bres, btex),
+                "planets": args.batch, "grid": bres, "texture": btex, "failed": int(bc[1]),
+                "generation_ms_per_planet": (float(bt[0]) + float(bt[1])) * 1e3 / max(1, len(mine)), "planets_per_s": args.batch / max(1e-9, float(bt[0]) + float(bt[1])),
+                "meshes_ms_total": float(bt[0]) * 1e3, "bake_ms_total": float(bt[1]) * 1e3, "baked_texels": int(bc[0]),
+                "rank0_shapes": shapes_seen, "rank0_planets": infos,
+            }
+
     texels = covered["land"] + covered["water"]
     times = torch.tensor([ms_total, e2e_s * 1e3, bake_ms, bake_e2e_s * 1e3, mesh_s * 1e3, mesh_raw_s * 1e3], dtype=torch.float64, device=dev)
     counts = torch.tensor([float(texels)], dtype=torch.float64, device=dev)
@@ -525,6 +593,7 @@ def run_ours(args, rank, world, local_rank):
         "texel_bake": texel_bake,
         "planet": planet_line,
         "sharded_planet": sharded_line,
+        "batch": batch_line,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), file=_STDOUT, flush=True)
@@ -547,6 +616,9 @@ def main():
     ap.add_argument("--grid", type=int, default=1000, help="samples per axis of the meshing grid (BASELINE configs[2]: 1000)")
     ap.add_argument("--texture", type=int, default=4096, help="bake resolution (BASELINE configs[2]: 4096)")
     ap.add_argument("--sharded-grid", type=int, default=1024, help="grid of the one-planet-over-all-ranks leg (BASELINE configs[4]: 1024; 0 = skip)")
+    ap.add_argument("--batch", type=int, default=64, help="planets of the back-to-back leg (BASELINE configs[3]: 64; 0 = skip)")
+    ap.add_argument("--batch-grid", type=int, default=500, help="grid of the batch planets (the reference's constant)")
+    ap.add_argument("--batch-texture", type=int, default=2048, help="bake resolution of the batch planets")
     ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -43,6 +43,29 @@ namespace
 		static float run(int, const PlanetParams &, V3) { return NAN; }
 	};
 
+	// elevation through the column path of the dense kernel (csrc/upg_field.cuh: sdf_column_kernel): the first Value fBm from a
+	// ValueFbmColumn that lives as long as the (x, y) column
+	template<int E>
+	struct ElevColumnDispatch
+	{
+		static float run(int elev, const PlanetParams &P, V3 p, ValueFbmColumn<4> &c)
+		{
+			if (elev == E)
+			{
+				float first = 0;
+				if (ElevationStartsWithValueFbm<E>::value)
+					first = value_fbm_column<4>(P.el.n[0], p.x, p.y, p.z, c);
+				return elevation_raw_given<E>(P, p, first);
+			}
+			return ElevColumnDispatch<E + 1>::run(elev, P, p, c);
+		}
+	};
+	template<>
+	struct ElevColumnDispatch<EL_COUNT>
+	{
+		static float run(int, const PlanetParams &, V3, ValueFbmColumn<4> &) { return NAN; }
+	};
+
 	float eval_field(const PlanetParams &P, int field, V3 pos)
 	{
 		switch (field)
@@ -121,6 +144,50 @@ extern "C"
 	void upgh_elevation_interval10(int elevation, double *lo10, double *hi10)
 	{
 		elevation_interval10(elevation, lo10, hi10);
+	}
+	// terrainSdfElevationRaw over the grid, evaluated column by column like sdf_column_kernel does; zOrder: 0 ascending, 1 descending,
+	// 2 = a zig-zag with repeats (the cache must not care)
+	void upgh_grid_elevation_columns(const upgh_planet *p, int z0, int z1, int zOrder, float *out)
+	{
+		const GridConsts &g = p->params.grid;
+		const uint32_t res = (uint32_t)g.res;
+		const int n = z1 - z0;
+		int stride = 7; // of the zig-zag: coprime with n, so that every slice is visited once
+		for (bool ok = false; !ok; stride += ok ? 0 : 2)
+		{
+			int a = stride, b = n;
+			while (b)
+			{
+				const int t = a % b;
+				a = b;
+				b = t;
+			}
+			ok = a == 1;
+		}
+		for (uint32_t y = 0; y < res; y++)
+			for (uint32_t x = 0; x < res; x++)
+			{
+				ValueFbmColumn<4> c;
+				for (int k = 0; k < n; k++)
+				{
+					int zi = zOrder == 0 ? k : zOrder == 1 ? n - 1 - k : ((k * stride) % n);
+					const uint32_t z = (uint32_t)(z0 + zi);
+					out[((uint64_t)zi * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, z)), c);
+				}
+			}
+	}
+	// the same for the first `rows` grid rows of every slice only, ascending z (big grids on the host)
+	void upgh_grid_elevation_columns_rows(const upgh_planet *p, int z0, int z1, int rows, float *out)
+	{
+		const GridConsts &g = p->params.grid;
+		const uint32_t res = (uint32_t)g.res;
+		for (uint32_t y = 0; y < (uint32_t)rows; y++)
+			for (uint32_t x = 0; x < res; x++)
+			{
+				ValueFbmColumn<4> c;
+				for (int z = z0; z < z1; z++)
+					out[((uint64_t)(z - z0) * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, (uint32_t)z)), c);
+			}
 	}
 	void upgh_grid_coords(const upgh_planet *p, float *out)
 	{

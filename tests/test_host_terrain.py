@@ -113,6 +113,30 @@ def test_elevation_interval_bounds_every_mode(hostlib, elev):
         assert hi - lo < 12 * (seen_hi - seen_lo), (elev, lo, seen_lo, seen_hi, hi)
 
 
+@pytest.mark.parametrize("elev,res", [("lakes", 40), ("islands", 33), ("legacy", 28), ("craters", 12), ("lakes", 1000)])
+def test_column_evaluation_is_bit_identical(hostlib, elev, res):
+    """the dense kernel walks the grid in z columns and keeps the first Value fBm of lakes / islands / legacy between samples
+    (ValueFbmColumn, csrc/upg_noise.cuh): same bits as the sample-by-sample evaluation, in any z order"""
+    import ctypes as C
+
+    hp = HostPlanet(hostlib, "sphere", elev, res=res)
+    if res > 100:
+        # a slab of the bench grid, where an octave stays up to 192 samples between two lattice planes; two grid rows of every slice
+        z0, z1, rows = 300, 700, 2
+        c = hp.coords()
+        zz, yy, xx = np.meshgrid(c[z0:z1], c[:rows], c, indexing="ij")
+        want = hp.points("elevraw", np.stack([xx.ravel(), yy.ravel(), zz.ravel()], axis=1)).reshape(z1 - z0, rows, res)
+        got = np.zeros((z1 - z0, res, res), dtype=np.float32)
+        hostlib.upgh_grid_elevation_columns_rows(C.c_void_p(hp.h), z0, z1, rows, got.ctypes.data_as(C.c_void_p))
+        assert same_bits(got[:, :rows, :], want).all()
+        return
+    want = hp.grid("elevraw")
+    for order in (0, 1, 2):
+        got = np.zeros((res, res, res), dtype=np.float32)
+        hostlib.upgh_grid_elevation_columns(C.c_void_p(hp.h), 0, res, order, got.ctypes.data_as(C.c_void_p))
+        assert same_bits(got, want).all(), (elev, order)
+
+
 def test_rng_known_answers(hostlib):
     # externals/cage/sources/test-core/random.cpp:37-79 pins randomRange3i(10, 1000) == (730, 955, 866) for this state;
     # the raw stream below was produced by cage's RandomGenerator itself

@@ -613,7 +613,7 @@ namespace upg
 {
 	// Pinned host blocks are expensive to create (cudaMallocHost of ~100 MB costs tens of milliseconds, more than the sampling
 	// of a 500^3 field), and the generator asks for one mesh after another: blocks handed back by upg_mesh_free are kept
-	// (up to 1 GiB in total) and reused for the next mesh of a similar size.
+	// (up to 2 GiB in total) and reused for the next mesh of a similar size.
 	namespace
 	{
 		struct PinnedBlock
@@ -622,17 +622,33 @@ namespace upg
 			size_t bytes;
 		};
 		std::mutex g_pinnedMutex;
-		PinnedBlock g_pinnedFree[16];
+		PinnedBlock g_pinnedFree[32];
 		int g_pinnedCount = 0;
 		size_t g_pinnedBytes = 0;
 
+		// Requests are rounded up to 2^k or 1.5 * 2^k (at least 1 MiB) so that the meshes of successive planets, which never have the
+		// same size twice, land on the same few block sizes: a batch of 64 different planets paid up to 960 ms per planet in
+		// cudaMallocHost / cudaFreeHost before this rounding (bench.py batch leg), against ~10 ms of GPU work.
+		size_t pinned_bucket(size_t bytes)
+		{
+			size_t b = (size_t)1 << 20;
+			while (b < bytes)
+			{
+				if (b + b / 2 >= bytes)
+					return b + b / 2;
+				b <<= 1;
+			}
+			return b;
+		}
+
 		cudaError_t pinned_acquire(size_t bytes, void **out, size_t *capacity)
 		{
+			const size_t bucket = pinned_bucket(bytes);
 			{
 				std::lock_guard<std::mutex> lock(g_pinnedMutex);
 				int best = -1;
 				for (int i = 0; i < g_pinnedCount; i++)
-					if (g_pinnedFree[i].bytes >= bytes && g_pinnedFree[i].bytes <= bytes * 2 + (1u << 20) && (best < 0 || g_pinnedFree[i].bytes < g_pinnedFree[best].bytes))
+					if (g_pinnedFree[i].bytes >= bytes && g_pinnedFree[i].bytes <= bucket * 2 && (best < 0 || g_pinnedFree[i].bytes < g_pinnedFree[best].bytes))
 						best = i;
 				if (best >= 0)
 				{
@@ -643,15 +659,15 @@ namespace upg
 					return cudaSuccess;
 				}
 			}
-			*capacity = bytes;
-			return cudaMallocHost(out, bytes);
+			*capacity = bucket;
+			return cudaMallocHost(out, bucket);
 		}
 
 		void pinned_release(void *ptr, size_t bytes)
 		{
 			{
 				std::lock_guard<std::mutex> lock(g_pinnedMutex);
-				if (g_pinnedCount < 16 && g_pinnedBytes + bytes <= ((size_t)1 << 30))
+				if (g_pinnedCount < 32 && g_pinnedBytes + bytes <= ((size_t)2 << 30))
 				{
 					g_pinnedFree[g_pinnedCount++] = PinnedBlock{ ptr, bytes };
 					g_pinnedBytes += bytes;

@@ -141,6 +141,80 @@ namespace upg
 		L.out[idx] = v;
 	}
 
+	// K1 over whole z-slices for the elevation modes that start with a Value fBm of the position (lakes, islands, legacy): a thread owns
+	// one (x, y) COLUMN of the grid and walks COLUMN_Z slices of it, so that the fBm's per-octave interpolation planes live in
+	// registers between samples (ValueFbmColumn, upg_noise.cuh: bit-identical, 8 hashes + 7 lerps per octave become 1 lerp) and the
+	// x / y coordinates, their IEEE divisions and the index arithmetic are paid once per column.  z is uniform over the block, so
+	// "the column left its lattice cell" is a uniform branch.  A warp's 32 stores per slice are consecutive in x as before.
+#ifndef UPG_COLUMN_Z
+#define UPG_COLUMN_Z 32
+#endif
+	constexpr int COLUMN_Z = UPG_COLUMN_Z;
+#ifndef UPG_COLUMN_MIN_BLOCKS
+#define UPG_COLUMN_MIN_BLOCKS 4 // resident blocks per SM the register allocation aims at (A/B in profiles/)
+#endif
+	template<int SHAPE, int ELEV>
+	__global__ void __launch_bounds__(FIELD_BLOCK, UPG_COLUMN_MIN_BLOCKS) sdf_column_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
+	{
+		__shared__ float coordZ[COLUMN_Z];
+		const uint32_t res = (uint32_t)P.grid.res;
+		const uint32_t zcount = (uint32_t)(L.count / ((uint64_t)res * res));
+		const uint32_t zBegin = blockIdx.z * COLUMN_Z;
+		const uint32_t zEnd = min(zBegin + (uint32_t)COLUMN_Z, zcount);
+		grad_table_init<FIELD_BLOCK>();
+		if (threadIdx.x < zEnd - zBegin)
+			coordZ[threadIdx.x] = grid_coord(P.grid, L.z0 + zBegin + threadIdx.x);
+		__syncthreads();
+		const uint32_t x = blockIdx.x * FIELD_BLOCK + threadIdx.x, y = blockIdx.y;
+		if (x >= res)
+			return;
+		const float px = grid_coord(P.grid, x), py = grid_coord(P.grid, y);
+		const int field = L.field;
+		ValueFbmColumn<4> column;
+		bool bad = false;
+		uint64_t idx = ((uint64_t)zBegin * res + y) * res + x;
+		const uint64_t slice = (uint64_t)res * res;
+		for (uint32_t zl = zBegin; zl < zEnd; zl++, idx += slice)
+		{
+			const V3 pos = v3(px, py, coordZ[zl - zBegin]);
+			float base = 0;
+			if (field != FD_ELEVATION_RAW)
+				base = shape_sdf<SHAPE>(P, pos);
+			const float first = value_fbm_column<4>(P.el.n[0], pos.x, pos.y, pos.z, column);
+			const float elev = elevation_raw_given<ELEV>(P, pos, first);
+			// the expressions of sdf_sample_kernel
+			if (field == FD_ALL)
+			{
+				const float e10 = elev / 10.0f;
+				const float land = base - e10;
+				const float nav = base - fmax_(e10, 0.0f);
+				if (L.out)
+				{
+					L.out[idx] = land;
+					bad |= isnan_(land);
+				}
+				if (L.outWater)
+				{
+					L.outWater[idx] = base;
+					bad |= isnan_(base);
+				}
+				if (L.outNavigation)
+				{
+					L.outNavigation[idx] = nav;
+					bad |= isnan_(nav);
+				}
+			}
+			else
+			{
+				const float v = field == FD_ELEVATION_RAW ? elev : field == FD_NAVIGATION ? base - fmax_(elev / 10.0f, 0.0f) : base - elev / 10.0f;
+				bad |= isnan_(v);
+				L.out[idx] = v;
+			}
+		}
+		if (bad)
+			atomicOr(L.status, 1u);
+	}
+
 	// The water field (= the bare shape, terrainSdfWater) of whole grid rows: the shape functions cost a few dozen instructions, so
 	// the index arithmetic of the generic kernel above (a 64-bit division and three IEEE divisions per sample) would dominate.  Here
 	// the grid -> world coordinates come from a per-block table (same grid_coord(), same bits) and a block walks SHAPE_ROWS rows.

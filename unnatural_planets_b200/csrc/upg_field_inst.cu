@@ -19,7 +19,10 @@ namespace upg
 		constexpr int LO = (SH_COUNT * UPG_PART) / PARTS;
 		constexpr int HI = (SH_COUNT * (UPG_PART + 1)) / PARTS;
 
-		template<int S>
+		// ELEV and PART are part of the type on purpose: nvcc names this anonymous namespace after the SOURCE FILE, which the 24 translation
+		// units share, and emits the members as weak symbols -- without the two arguments the linker would merge the 24 different run()
+		// bodies into whichever came first (it did, as soon as run() grew too big to be inlined: every planet sampled with elevation "none").
+		template<int S, int ELEV = UPG_ELEV, int PART = UPG_PART>
 		struct Dispatch
 		{
 			static bool run(int shape, const PlanetParams &P, const FieldLaunch &L, cudaStream_t stream)
@@ -35,15 +38,28 @@ namespace upg
 						return true;
 					}
 #endif
+					// whole slices of land / navigation / raw elevation under a mode that starts with a Value fBm: the column kernel
+					const uint64_t slice = (uint64_t)P.grid.res * (uint64_t)P.grid.res;
+#ifndef UPG_NO_COLUMN
+					if constexpr (ElevationStartsWithValueFbm<UPG_ELEV>::value)
+					{
+						if (!L.positions && L.count % slice == 0 && (L.field == FD_ALL || L.field == FD_LAND || L.field == FD_NAVIGATION || L.field == FD_ELEVATION_RAW))
+						{
+							const dim3 grid((unsigned)((P.grid.res + FIELD_BLOCK - 1) / FIELD_BLOCK), (unsigned)P.grid.res, (unsigned)((L.count / slice + COLUMN_Z - 1) / COLUMN_Z));
+							sdf_column_kernel<S, UPG_ELEV><<<grid, FIELD_BLOCK, 0, stream>>>(P, L);
+							return true;
+						}
+					}
+#endif
 					const uint64_t blocks = (L.count + FIELD_BLOCK - 1) / FIELD_BLOCK;
 					sdf_sample_kernel<S, UPG_ELEV><<<(unsigned)blocks, FIELD_BLOCK, 0, stream>>>(P, L);
 					return true;
 				}
-				return Dispatch<S + 1>::run(shape, P, L, stream);
+				return Dispatch<S + 1, ELEV, PART>::run(shape, P, L, stream);
 			}
 		};
 		template<>
-		struct Dispatch<HI>
+		struct Dispatch<HI, UPG_ELEV, UPG_PART>
 		{
 			static bool run(int, const PlanetParams &, const FieldLaunch &, cudaStream_t) { return false; }
 		};
@@ -53,6 +69,6 @@ namespace upg
 	{
 		if (shape < LO || shape >= HI)
 			return false;
-		return Dispatch<LO>::run(shape, P, L, (cudaStream_t)stream);
+		return Dispatch<LO, UPG_ELEV, UPG_PART>::run(shape, P, L, (cudaStream_t)stream);
 	}
 }

@@ -627,6 +627,71 @@ namespace upg
 		return noise3<TYPE, FRACTAL, OCTAVES, OUTLINED>(n, p.x, p.y, p.z);
 	}
 
+	// ---- Value fBm along a column of samples ---------------------------------------------------------------------------
+	// single_value() interpolates x first, then y, then z: its last step is nlerp(yf0, yf1, zs) with yf0 / yf1 functions of (x, y) and
+	// of the lattice planes z0 / z0 + 1 alone.  Samples that share x and y and step through z (a column of the meshing grid) therefore
+	// share yf0 / yf1 for as long as they stay between the same two planes -- 24 to 192 consecutive samples for the octaves of the
+	// `lakes` land noise on a 1000^3 grid.  The state below keeps both per octave; a sample then costs one floor, one Hermite weight
+	// and one nlerp per octave instead of eight hashes and seven nlerps, and every operation that is executed is the one
+	// single_value() executes, on the same operands: bit-identical sums (tests/test_host_terrain.py).
+	template<int OCTAVES>
+	struct ValueFbmColumn
+	{
+		int32_t z0[OCTAVES]; // lattice plane below the last sample, per octave
+		float yf0[OCTAVES], yf1[OCTAVES]; // single_value()'s yf0 / yf1 (unscaled) for those planes
+		bool fresh = true; // nothing cached yet
+	};
+
+	// yf of single_value() for one lattice plane (zp = z lattice index * PRIME_Z)
+	UPG_HD float value_plane(int32_t seed, float x, float y, int32_t zp)
+	{
+		int32_t x0 = fast_floor(x), y0 = fast_floor(y);
+		const float xs = interp_hermite(x - (float)x0);
+		const float ys = interp_hermite(y - (float)y0);
+		x0 = imul(x0, PRIME_X);
+		y0 = imul(y0, PRIME_Y);
+		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y);
+		const int32_t s0 = seed ^ y0 ^ zp, s1 = seed ^ y1 ^ zp;
+		const float xf0 = nlerp(value_bits_from_hash(imul(s0 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s0 ^ x1, 0x27d4eb2d)), xs);
+		const float xf1 = nlerp(value_bits_from_hash(imul(s1 ^ x0, 0x27d4eb2d)), value_bits_from_hash(imul(s1 ^ x1, 0x27d4eb2d)), xs);
+		return nlerp(xf0, xf1, ys);
+	}
+
+	// == noise3<NT_VALUE, FT_FBM, OCTAVES>(n, x, y, z), for successive samples of one (x, y) column in any z order
+	template<int OCTAVES>
+	UPG_HD float value_fbm_column(const NoiseInst &n, float x, float y, float z, ValueFbmColumn<OCTAVES> &c)
+	{
+		x *= n.frequency;
+		y *= n.frequency;
+		z *= n.frequency;
+		int32_t seed = n.seed;
+		float sum = 0;
+		float amp = n.bounding;
+#pragma unroll
+		for (int o = 0; o < OCTAVES; o++)
+		{
+			const int32_t z0 = fast_floor(z);
+			if (c.fresh || z0 != c.z0[o])
+			{
+				const int32_t zp = imul(z0, PRIME_Z);
+				// one plane up: the old upper plane is the new lower one
+				c.yf0[o] = (!c.fresh && z0 == iadd(c.z0[o], 1)) ? c.yf1[o] : value_plane(seed, x, y, zp);
+				c.yf1[o] = value_plane(seed, x, y, iadd(zp, PRIME_Z));
+				c.z0[o] = z0;
+			}
+			const float zs = interp_hermite(z - (float)z0);
+			const float v = nlerp(c.yf0[o], c.yf1[o], zs) * VALUE_SCALE;
+			seed = iadd(seed, 1);
+			sum += fractal_term<FT_FBM>(v) * amp;
+			x *= n.lacunarity;
+			y *= n.lacunarity;
+			z *= n.lacunarity;
+			amp *= n.gain;
+		}
+		c.fresh = false;
+		return sum;
+	}
+
 	// cellular variant (needs the jitter table and the distance / return kind)
 	template<int DIST, int OP, int FRACTAL, int OCTAVES>
 	UPG_HD float noise3_cellular(const float *rv, const NoiseInst &n, float x, float y, float z)

@@ -638,8 +638,16 @@ namespace upg
 		return land + smooth_max(0, fmax_(ridge, terraces), 50);
 	}
 
+	// the modes whose FIRST noise is a four-octave Value fBm of the sample position itself (the column kernel caches it, upg_field.cuh)
 	template<int ELEV>
-	UPG_HD float elevation_raw(const PlanetParams &P, V3 pos)
+	struct ElevationStartsWithValueFbm
+	{
+		static constexpr bool value = ELEV == EL_LEGACY || ELEV == EL_LAKES || ELEV == EL_ISLANDS;
+	};
+
+	// elevation_raw with that first noise value handed in (`first` is ignored by the other modes)
+	template<int ELEV>
+	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first)
 	{
 		const ElevationConsts &E = P.el;
 		switch (ELEV)
@@ -655,7 +663,7 @@ namespace upg
 			}
 			case EL_LEGACY:
 			{
-				const float scale = noise3<NT_VALUE, FT_FBM, 4>(E.n[0], pos) * 0.0005f + 0.0015f;
+				const float scale = first * 0.0005f + 0.0015f;
 				float a = noise3<NT_VALUE, FT_FBM, 4>(E.n[1], pos * scale);
 				a += 0.11f;
 				if (a < 0)
@@ -667,7 +675,7 @@ namespace upg
 			case EL_LAKES:
 			case EL_ISLANDS:
 			{
-				float land = noise3<NT_VALUE, FT_FBM, 4>(E.n[0], pos) * 0.5f + 0.5f;
+				float land = first * 0.5f + 0.5f;
 				land = saturate_(land);
 				land = 1 - powf(land, ELEV == EL_LAKES ? 1.24f : 0.83f);
 				land = land * 2 - 1;
@@ -687,6 +695,15 @@ namespace upg
 			}
 		}
 		return 0;
+	}
+
+	template<int ELEV>
+	UPG_HD float elevation_raw(const PlanetParams &P, V3 pos)
+	{
+		float first = 0;
+		if (ElevationStartsWithValueFbm<ELEV>::value)
+			first = noise3<NT_VALUE, FT_FBM, 4>(P.el.n[0], pos);
+		return elevation_raw_given<ELEV>(P, pos, first);
 	}
 
 	// ---- field compositions (sources/modesConfiguration.cpp:227-279), meshElevationRatio = 10 ------
