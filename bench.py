@@ -47,7 +47,7 @@ FLOPS_PER_TEXEL_LAND = 7200.0
 # (profiles/); None until a capture of this kernel exists
 def _k1_traffic():
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "k1_fused_ncu.json")))["dram_bytes_per_grid_node"])
+        return float(json.load(open(os.path.join(ROOT, "profiles", "k1_column_ncu.json")))["dram_bytes_per_grid_node"])
     except Exception:
         return None
 
@@ -545,7 +545,7 @@ def run_ours(args, rank, world, local_rank):
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     peak_source = "FP32 FMA ceiling measured in this run by upg_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 SIMT figure)"
     roofline = {
-        "bound": "fp32", "kernel": "sdf_sample_kernel<sphere,lakes> (fused land + water + navigation launch)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if peak else None, "traffic": K1_TRAFFIC_BYTES_PER_NODE * n if K1_TRAFFIC_BYTES_PER_NODE else None, "peak_source": peak_source,
         "kernel_ms": fused_ms, "flops_per_grid_node": FLOPS_PER_SAMPLE_LAND, "samples_per_grid_node": len(FIELDS),
         "single_field_kernel_ms": single_ms,
