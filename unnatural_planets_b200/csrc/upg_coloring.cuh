@@ -398,8 +398,13 @@ namespace upg
 	// generateDirt (:338-402)
 	UPG_LAYER void generate_dirt(const ColoringConsts &C, Tile &t)
 	{
+		// bf = (a factor in [0, 1]) * steepness: when the steepness mask alone is under the threshold so is bf, and the three Perlin octaves
+		// behind the other factor are not needed (same early return as the reference's, taken earlier)
+		const float steepness = steepness_mask(t.slope, 20, 5);
+		if (steepness < 1e-7f)
+			return;
 		float height = noise3<NT_PERLIN, FT_FBM, 3, true>(C.dirtHeight, t.position) * 0.2f + 0.5f;
-		const float bf = sharp_edge(saturate_(height - t.height + 0.4f)) * steepness_mask(t.slope, 20, 5);
+		const float bf = sharp_edge(saturate_(height - t.height + 0.4f)) * steepness;
 		if (bf < 1e-7f)
 			return;
 		V3 color = v3(168, 94, 28) / 255;
@@ -593,6 +598,11 @@ namespace upg
 	UPG_LAYER void generate_snow(const ColoringConsts &C, Tile &t)
 	{
 		float bf = sharp_edge(range_mask(t.elevation + noise3<NT_VALUE, FT_NONE, 3, true>(C.snowElevOffset, t.position) * 20, 220, 240) * steepness_mask(t.slope, 25, 5));
+		// The reference evaluates the thickness noise (three ValueCubic octaves, 192 lattice taps) before it tests bf.  The factor applied
+		// below lies in [0, 1], so a bf under the threshold here stays under it: the same early return, taken before the noise -- which is
+		// nearly always, snow needs 220 m of elevation (identical tiles: tests/test_host_coloring.py).  A NaN bf compares false and goes on.
+		if (bf < 1e-7f)
+			return;
 		const float thickness = noise3<NT_CUBIC, FT_FBM, 3, true>(C.snowThickness, t.position) * 0.5f + 0.5f;
 		bf *= saturate_(thickness * 0.5f + 0.7f);
 		if (bf < 1e-7f)
