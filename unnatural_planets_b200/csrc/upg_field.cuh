@@ -150,8 +150,11 @@ namespace upg
 #define UPG_COLUMN_Z 32
 #endif
 	constexpr int COLUMN_Z = UPG_COLUMN_Z;
+#ifndef UPG_COLUMN_PERLIN
+#define UPG_COLUMN_PERLIN 1 // also cache the Perlin mountain mask along the column
+#endif
 #ifndef UPG_COLUMN_MIN_BLOCKS
-#define UPG_COLUMN_MIN_BLOCKS 4 // resident blocks per SM the register allocation aims at (A/B in profiles/)
+#define UPG_COLUMN_MIN_BLOCKS 5 // resident blocks per SM the register allocation aims at (A/B in profiles/)
 #endif
 	template<int SHAPE, int ELEV>
 	__global__ void __launch_bounds__(FIELD_BLOCK, UPG_COLUMN_MIN_BLOCKS) sdf_column_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
@@ -171,6 +174,9 @@ namespace upg
 		const float px = grid_coord(P.grid, x), py = grid_coord(P.grid, y);
 		const int field = L.field;
 		ValueFbmColumn<4> column;
+#if UPG_COLUMN_PERLIN
+		PerlinColumn maskColumn; // the mountain mask of lakes / islands (elevation_mountains)
+#endif
 		bool bad = false;
 		uint64_t idx = ((uint64_t)zBegin * res + y) * res + x;
 		const uint64_t slice = (uint64_t)res * res;
@@ -181,7 +187,11 @@ namespace upg
 			if (field != FD_ELEVATION_RAW)
 				base = shape_sdf<SHAPE>(P, pos);
 			const float first = value_fbm_column<4>(P.el.n[0], pos.x, pos.y, pos.z, column);
+#if UPG_COLUMN_PERLIN
+			const float elev = elevation_raw_given<ELEV>(P, pos, first, &maskColumn);
+#else
 			const float elev = elevation_raw_given<ELEV>(P, pos, first);
+#endif
 			// the expressions of sdf_sample_kernel
 			if (field == FD_ALL)
 			{

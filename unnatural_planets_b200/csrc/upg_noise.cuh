@@ -151,18 +151,23 @@ namespace upg
 			upg_grad_lds[i] = upg_grad_const[i >> 3];
 #endif
 	}
-	UPG_HD float grad_dot(int32_t h, float xd, float yd, float zd)
+	// the gradient a lattice hash selects
+	UPG_HD void grad_vec(int32_t h, float &gx, float &gy, float &gz)
 	{
 #if defined(__CUDA_ARCH__)
 		const uint32_t t = ((uint32_t)h ^ ((uint32_t)(h >> 15))) & (63u << 2);
 		const float4 g = upg_grad_lds[t * 2u + (threadIdx.x & 7u)];
-		return (xd * g.x + yd * g.y) + zd * g.z;
+		gx = g.x, gy = g.y, gz = g.z;
 #else
 		h ^= h >> 15;
-		float gx, gy, gz;
 		grad_entry(((uint32_t)h >> 2) & 63u, gx, gy, gz);
-		return (xd * gx + yd * gy) + zd * gz;
 #endif
+	}
+	UPG_HD float grad_dot(int32_t h, float xd, float yd, float zd)
+	{
+		float gx, gy, gz;
+		grad_vec(h, gx, gy, gz);
+		return (xd * gx + yd * gy) + zd * gz;
 	}
 	UPG_HD float grad_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) { return grad_dot(lattice_hash(seed, xp, yp, zp), xd, yd, zd); }
 
@@ -690,6 +695,74 @@ namespace upg
 		}
 		c.fresh = false;
 		return sum;
+	}
+
+	// ---- Perlin along a column of samples ----------------------------------------------------------------------------------
+	// single_perlin()'s corner term is (xd * gx + yd * gy) + zd * gz.  Along a z column the hash, the gradient and the bracket are fixed for
+	// as long as the samples stay between two lattice planes; what remains per sample is zd * gz + bracket for the eight corners, the
+	// seven lerps (x and y weights are fixed too) and one quintic weight.  Same operations on the same operands as single_perlin().
+	struct PerlinColumn
+	{
+		int32_t z0; // lattice plane below the last sample
+		float xy[8], gz[8]; // bracket and z component per corner: 0..3 lower plane (x0y0, x1y0, x0y1, x1y1), 4..7 upper plane
+		float xs, ys; // quintic weights of x and y
+		bool fresh = true;
+	};
+
+	UPG_HD void perlin_plane(int32_t seed, float x, float y, int32_t zp, float *xy4, float *gz4, float &xs, float &ys)
+	{
+		int32_t x0 = fast_floor(x), y0 = fast_floor(y);
+		const float xd0 = x - (float)x0, yd0 = y - (float)y0;
+		const float xd1 = xd0 - 1, yd1 = yd0 - 1;
+		xs = interp_quintic(xd0);
+		ys = interp_quintic(yd0);
+		x0 = imul(x0, PRIME_X);
+		y0 = imul(y0, PRIME_Y);
+		const int32_t x1 = iadd(x0, PRIME_X), y1 = iadd(y0, PRIME_Y);
+		const int32_t s0 = seed ^ y0 ^ zp, s1 = seed ^ y1 ^ zp;
+		float gx, gy;
+		grad_vec(imul(s0 ^ x0, 0x27d4eb2d), gx, gy, gz4[0]);
+		xy4[0] = xd0 * gx + yd0 * gy;
+		grad_vec(imul(s0 ^ x1, 0x27d4eb2d), gx, gy, gz4[1]);
+		xy4[1] = xd1 * gx + yd0 * gy;
+		grad_vec(imul(s1 ^ x0, 0x27d4eb2d), gx, gy, gz4[2]);
+		xy4[2] = xd0 * gx + yd1 * gy;
+		grad_vec(imul(s1 ^ x1, 0x27d4eb2d), gx, gy, gz4[3]);
+		xy4[3] = xd1 * gx + yd1 * gy;
+	}
+
+	// == single_perlin(seed, x, y, z) for successive samples of one (x, y) column in any z order
+	UPG_HD float perlin_column(int32_t seed, float x, float y, float z, PerlinColumn &c)
+	{
+		const int32_t z0 = fast_floor(z);
+		if (c.fresh || z0 != c.z0)
+		{
+			const int32_t zp = imul(z0, PRIME_Z);
+			if (!c.fresh && z0 == iadd(c.z0, 1))
+			{
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					c.xy[k] = c.xy[4 + k];
+					c.gz[k] = c.gz[4 + k];
+				}
+			}
+			else
+				perlin_plane(seed, x, y, zp, c.xy, c.gz, c.xs, c.ys);
+			perlin_plane(seed, x, y, iadd(zp, PRIME_Z), c.xy + 4, c.gz + 4, c.xs, c.ys);
+			c.z0 = z0;
+			c.fresh = false;
+		}
+		const float zd0 = z - (float)z0;
+		const float zd1 = zd0 - 1;
+		const float zs = interp_quintic(zd0);
+		const float xf00 = nlerp(c.xy[0] + zd0 * c.gz[0], c.xy[1] + zd0 * c.gz[1], c.xs);
+		const float xf10 = nlerp(c.xy[2] + zd0 * c.gz[2], c.xy[3] + zd0 * c.gz[3], c.xs);
+		const float xf01 = nlerp(c.xy[4] + zd1 * c.gz[4], c.xy[5] + zd1 * c.gz[5], c.xs);
+		const float xf11 = nlerp(c.xy[6] + zd1 * c.gz[6], c.xy[7] + zd1 * c.gz[7], c.xs);
+		const float yf0 = nlerp(xf00, xf10, c.ys);
+		const float yf1 = nlerp(xf01, xf11, c.ys);
+		return nlerp(yf0, yf1, zs) * 0.964921414852142333984375f;
 	}
 
 	// cellular variant (needs the jitter table and the distance / return kind)

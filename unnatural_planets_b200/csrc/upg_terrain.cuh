@@ -600,13 +600,15 @@ namespace upg
 	}
 
 	// ---- elevation modes (sources/elevationModes.cpp) ------------------------------------------------
-	UPG_HD float elevation_mountains(const ElevationConsts &E, V3 pos, float land)
+	// `maskColumn`: the column kernel's cache of the mask noise (PerlinColumn, upg_noise.cuh), or null = evaluate it from scratch
+	UPG_HD float elevation_mountains(const ElevationConsts &E, V3 pos, float land, PerlinColumn *maskColumn = nullptr)
 	{
 		const float cover = 1 - saturate_(land * -0.1f);
 		if (cover < 1e-7f)
 			return land;
 
-		const float mask = noise3<NT_PERLIN, FT_NONE, 3>(E.n[1], pos);
+		// noise3<NT_PERLIN, FT_NONE>: frequency scale, then the single generator
+		const float mask = maskColumn ? perlin_column(E.n[1].seed, pos.x * E.n[1].frequency, pos.y * E.n[1].frequency, pos.z * E.n[1].frequency, *maskColumn) : noise3<NT_PERLIN, FT_NONE, 3>(E.n[1], pos);
 		const float rm = smoothstep_(saturate_(mask * +7 - 0.3f));
 		const float tm = smoothstep_(saturate_(mask * -7 - 1.5f));
 
@@ -647,7 +649,7 @@ namespace upg
 
 	// elevation_raw with that first noise value handed in (`first` is ignored by the other modes)
 	template<int ELEV>
-	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first)
+	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first, PerlinColumn *maskColumn = nullptr)
 	{
 		const ElevationConsts &E = P.el;
 		switch (ELEV)
@@ -681,7 +683,7 @@ namespace upg
 				land = land * 2 - 1;
 				land = land / (abs_(land) + 0.17f) + 0.15f;
 				land *= 150;
-				return elevation_mountains(E, pos, land);
+				return elevation_mountains(E, pos, land, maskColumn);
 			}
 			case EL_CRATERS:
 			{
