@@ -246,6 +246,12 @@ int upg_isosurface(const float *host_samples, int rx, int ry, int rz, float box_
 
 void upg_mesh_free(upg_mesh *mesh);
 
+/* Host memory (pageable or pinned) -> device memory of `device`, complete when the call returns: the multi-threaded staged copy the
+ * host-buffer entry points use for their mesh arguments (pageable memory moves at ~11 GB/s through cudaMemcpy, at link speed through
+ * this), for callers that feed the *_device entry points from host arrays (unnatural_planets_b200/sharded.py).  Several arrays in one
+ * call share the staging: `count` triples of (device_dst[i], host_src[i], bytes[i]), count <= 16. */
+int upg_upload(int device, void *const *device_dst, const void *const *host_src, const uint64_t *bytes, int count, void *cuda_stream);
+
 /*
  * ---- texel baking (K5..K7) ------------------------------------------------------------------------------------
  */

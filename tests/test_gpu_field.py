@@ -232,3 +232,16 @@ def test_band_sampling_subsets_slices_and_scratch_shape_field(shape, elev, res):
         assert 0 < n <= (z1 - z0) * res * res  # (the mandelbulb at this size lies inside the band everywhere)
     with pytest.raises(UpgError):
         p.fields_samples_band_device(z0, z1, 0, 0, 0, s.cuda_stream)
+
+
+def test_staged_upload_round_trip():
+    # upg_upload: pageable host arrays of mixed types and sizes (small ones take the plain copy, big ones the staged slices)
+    from unnatural_planets_b200.planet import upload
+
+    rng = np.random.default_rng(5)
+    arrays = [rng.standard_normal((3_000_001, 3)).astype(np.float32), rng.integers(0, 2**32, size=7_000_003, dtype=np.uint32), np.arange(5, dtype=np.float32), np.zeros((0, 3), dtype=np.float32)]
+    got = upload(arrays, device=0)
+    for a, t in zip(arrays, got):
+        assert t.shape == a.shape
+        back = t.cpu().numpy()
+        assert (back.view(np.uint32) == a.view(np.uint32)).all()

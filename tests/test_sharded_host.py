@@ -63,6 +63,9 @@ def _worker(rank, world, port, out_path):
 
         tens = {k: (torch.from_numpy(a.view(np.int32).copy()) if a.dtype == np.uint32 else torch.from_numpy(a.copy())) if isinstance(a, np.ndarray) else a for k, a in parts[rank].items()}
         mesh2 = sharded.assemble_mesh_tensors(tens, dst=0, keys=[k for k, _ in sharded.MESH_KEYS])
+        # several fields in one exchange (what ShardedPlanet.field_meshes does): a second "field" with the arrays scaled / shifted
+        tens_b = {k: (t * 3 if k in ("positions", "normals", "dmc_vertices") else t) for k, t in tens.items()}
+        both = sharded.assemble_meshes_tensors({"land": tens, "water": tens_b}, ["land", "water"], dst=0, keys=[k for k, _ in sharded.MESH_KEYS])
         # row tiles of a 37-row image (ragged split)
         h, w = 37, 5
         img = [np.arange(h * w * c, dtype=np.uint32).reshape(h, w, c).astype(np.uint8) for c in (3, 2, 1)]
@@ -74,11 +77,13 @@ def _worker(rank, world, port, out_path):
             ok = (mesh["dmc_vertices"] == v).all() and (mesh["dmc_quads"] == whole_quads).all() and (mesh["positions"] == v * np.float32(2)).all()
             ok = ok and (mesh["indices"] == whole_quads[:, :3].reshape(-1)).all() and mesh["near_zero_samples"] == sum(range(1, world + 1))
             ok = ok and all((mesh2[k] == mesh[k]).all() and mesh2[k].dtype == mesh[k].dtype and mesh2[k].shape == mesh[k].shape for k in ("positions", "normals", "dmc_vertices", "indices", "dmc_quads")) and mesh2["near_zero_samples"] == mesh["near_zero_samples"]
+            ok = ok and all((both["land"][k] == mesh[k]).all() and both["land"][k].dtype == mesh[k].dtype and both["land"][k].shape == mesh[k].shape for k in ("positions", "normals", "dmc_vertices", "indices", "dmc_quads"))
+            ok = ok and (both["water"]["positions"] == mesh["positions"] * np.float32(3)).all() and (both["water"]["dmc_quads"] == mesh["dmc_quads"]).all() and both["water"]["near_zero_samples"] == mesh["near_zero_samples"]
             ok = ok and all((a == b).all() for a, b in zip(rows, img)) and [len(x) for x in lens] == [4, 0][:world]
             negative = any((p["dmc_quads"].view(np.int32) < 0).any() for p in parts[1:])
             np.save(out_path, np.array([int(ok), int(negative)]))
         else:
-            assert mesh is None and mesh2 is None and rows is None and lens is None
+            assert mesh is None and mesh2 is None and both is None and rows is None and lens is None
     finally:
         dist.destroy_process_group()
 

@@ -123,6 +123,7 @@ def load_library():
     L.upg_field_samples.argtypes = [vp, i32, i32, i32, fp]
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_fields_samples_device.argtypes = [vp, i32, i32, fp, fp, fp, vp]
+    L.upg_upload.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), i32, vp]
     L.upg_fields_samples_band_device.argtypes = [vp, i32, i32, fp, fp, fp, vp, C.POINTER(C.c_uint64)]
     L.upg_field_meshes.argtypes = [vp, C.c_uint, C.POINTER(Mesh)]
     L.upg_field_meshes_slab.argtypes = [vp, C.c_uint, i32, i32, C.POINTER(Mesh)]

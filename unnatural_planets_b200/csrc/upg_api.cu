@@ -1303,6 +1303,27 @@ extern "C"
 		return rc;
 	}
 
+	int upg_upload(int device, void *const *device_dst, const void *const *host_src, const uint64_t *bytes, int count, void *cuda_stream)
+	{
+		if (!device_dst || !host_src || !bytes || count < 0 || count > 16)
+			return fail(UPG_ERR_ARGUMENT, "bad argument");
+		cudaError_t e = cudaSetDevice(device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		HostArray arrays[16];
+		for (int i = 0; i < count; i++)
+			arrays[i] = HostArray{ device_dst[i], host_src[i], (size_t)bytes[i] };
+		void *staging = nullptr;
+		size_t capacity = 0;
+		int rc = upload_host_arrays(arrays, count, (cudaStream_t)cuda_stream, &staging, &capacity);
+		e = cudaStreamSynchronize((cudaStream_t)cuda_stream);
+		if (staging)
+			pinned_block_release(staging, capacity);
+		if (rc == UPG_OK && e != cudaSuccess)
+			rc = cuda_fail(e, "upg_upload");
+		return rc;
+	}
+
 	void upg_mesh_free(upg_mesh *mesh)
 	{
 		if (!mesh)

@@ -67,6 +67,24 @@ def stitch_slabs(slabs):
     return out
 
 
+def upload(arrays, device=0, stream=0):
+    """host numpy arrays -> CUDA tensors on `device` through the library's staged multi-threaded copy (upg_upload): pageable memory at
+    link speed instead of cudaMemcpy's ~11 GB/s.  uint32 arrays arrive as int32 tensors (same bits)."""
+    import torch
+
+    L = capi.load_library()
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    dev = torch.device("cuda", device)
+    outs = [torch.empty(a.shape, dtype=torch.from_numpy(a[:0].view(np.int32) if a.dtype == np.uint32 else a[:0]).dtype, device=dev) for a in arrays]
+    n = len(arrays)
+    dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    src = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    nbytes = (C.c_uint64 * n)(*[a.nbytes for a in arrays])
+    torch.cuda.current_stream(dev).synchronize()  # the tensors above were allocated on torch's stream
+    capi.check(L.upg_upload(device, dst, src, nbytes, n, C.c_void_p(stream)))
+    return outs
+
+
 def raster(uv, idx, w, h, device=0):
     """K5 alone (upg_raster): owner image (0xffffffff = uncovered), barycentric weights of the winning visit, visit count."""
     L = capi.load_library()
