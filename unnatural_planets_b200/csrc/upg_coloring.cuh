@@ -347,8 +347,10 @@ namespace upg
 		const float depth = sqr_(noise3<NT_CUBIC, FT_NONE, 3, true>(C.bedrockDepth, t.position) * 0.5f + 0.501f) * 2;
 		const float freq = noise3<NT_CUBIC, FT_NONE, 3, true>(C.bedrockFreq, t.position) * 0.15f + 1;
 		const V3 pf = t.position * freq;
-		const float cracks = saturate_(powf(noise3_cellular<CD_HYBRID, CO_SUBTRACT, FT_NONE, 3>(rv, C.bedrockCracks, pf.x, pf.y, pf.z) * 0.5f + 0.5f, 0.7f));
-		const float value = noise3_cellular<CD_HYBRID, CO_CELL, FT_NONE, 3>(rv, C.bedrockValue, pf.x, pf.y, pf.z);
+		// cracksNoise and valueNoise share their seed and frequency (:221-240): one scan of the 27 cells serves both (noise3_cellular_pair)
+		float cracksNoise, value;
+		noise3_cellular_pair<CD_HYBRID, CO_SUBTRACT, CO_CELL, FT_NONE, 3>(rv, C.bedrockCracks, pf.x, pf.y, pf.z, cracksNoise, value);
+		const float cracks = saturate_(powf(cracksNoise * 0.5f + 0.5f, 0.7f));
 		const float saturation = saturate_(noise3<NT_CUBIC, FT_FBM, 2, true>(C.bedrockSaturation, t.position) * 0.35f + 0.3f);
 		const V3 hsv = v3(0.07f, saturation, saturate_(value * 0.1f + 0.7f) * (cracks * 0.4f + 0.6f));
 		t.albedo = hsv_to_rgb(hsv);
@@ -470,8 +472,10 @@ namespace upg
 		V3 color = v3(114, 187, 77) / 255;
 		color = color_hue_shift(color, hueShift);
 		const V3 p = t.position;
-		const float patchesMask = sharp_edge(noise3_cellular<CD_HYBRID, CO_CELL, FT_NONE, 3>(rv, C.grassPatchesCells, p.x, p.y, p.z) * 0.5f + 0.2f);
-		const float patches = powf(noise3_cellular<CD_HYBRID, CO_SUBTRACT, FT_NONE, 3>(rv, C.grassPatchesDist, p.x, p.y, p.z) * 0.5f + 0.5f, 0.5f) * patchesMask * (1 - dryness * 0.8f);
+		float patchCell, patchDist; // one seed, one frequency (:480-509): one scan
+		noise3_cellular_pair<CD_HYBRID, CO_CELL, CO_SUBTRACT, FT_NONE, 3>(rv, C.grassPatchesCells, p.x, p.y, p.z, patchCell, patchDist);
+		const float patchesMask = sharp_edge(patchCell * 0.5f + 0.2f);
+		const float patches = powf(patchDist * 0.5f + 0.5f, 0.5f) * patchesMask * (1 - dryness * 0.8f);
 		color = color * (1 - patches * 0.09f);
 		const float scratches = saturate_(noise3_cellular<CD_HYBRID, CO_MULTIPLY, FT_NONE, 3>(rv, C.grassScratches, p.x, p.y, p.z) - 0.2f) * (1 - dryness * 0.5f);
 		color = color * (1 - scratches * 0.1f);
@@ -580,8 +584,10 @@ namespace upg
 		}
 		const float freq = noise3<NT_VALUE, FT_FBM, 3, true>(C.iceFreq, t.position) * 0.08f + 1;
 		const V3 pf = t.position * freq;
-		const float thickness = sharp_edge(saturate_(noise3_cellular<CD_HYBRID, CO_CELL, FT_FBM, 2>(rv, C.iceThickness, pf.x, pf.y, pf.z) * 0.5f + 0.8f), 0.1f) * 0.6f + 0.4f;
-		const float crack = 1 - powf(noise3_cellular<CD_HYBRID, CO_SUBTRACT, FT_FBM, 2>(rv, C.iceCracks, pf.x, pf.y, pf.z) * 0.5f + 0.5f, 0.3f);
+		float thicknessNoise, crackNoise; // one seed, one frequency, two octaves each (:767-790): one scan per octave
+		noise3_cellular_pair<CD_HYBRID, CO_CELL, CO_SUBTRACT, FT_FBM, 2>(rv, C.iceThickness, pf.x, pf.y, pf.z, thicknessNoise, crackNoise);
+		const float thickness = sharp_edge(saturate_(thicknessNoise * 0.5f + 0.8f), 0.1f) * 0.6f + 0.4f;
+		const float crack = 1 - powf(crackNoise * 0.5f + 0.5f, 0.3f);
 		V3 color = max3(v3(122, 162, 164) / 255 - crack * 0.3f, 0);
 		color = interpolate_color(t.albedo, color, thickness);
 		float roughness = 0.15f + crack * 0.6f;

@@ -145,7 +145,8 @@ namespace upg
 	// one (x, y) COLUMN of the grid and walks COLUMN_Z slices of it, so that the fBm's per-octave interpolation planes live in
 	// registers between samples (ValueFbmColumn, upg_noise.cuh: bit-identical, 8 hashes + 7 lerps per octave become 1 lerp) and the
 	// x / y coordinates, their IEEE divisions and the index arithmetic are paid once per column.  z is uniform over the block, so
-	// "the column left its lattice cell" is a uniform branch.  A warp's 32 stores per slice are consecutive in x as before.
+	// "the column left its lattice cell" is a uniform branch.
+	constexpr int COLUMN_TILE_X = 32, COLUMN_TILE_Y = FIELD_BLOCK / COLUMN_TILE_X; // columns per block
 #ifndef UPG_COLUMN_Z
 #define UPG_COLUMN_Z 32
 #endif
@@ -168,8 +169,18 @@ namespace upg
 		if (threadIdx.x < zEnd - zBegin)
 			coordZ[threadIdx.x] = grid_coord(P.grid, L.z0 + zBegin + threadIdx.x);
 		__syncthreads();
-		const uint32_t x = blockIdx.x * FIELD_BLOCK + threadIdx.x, y = blockIdx.y;
-		if (x >= res)
+		// a block owns COLUMN_TILE_X x COLUMN_TILE_Y columns and a warp an 8 x 4 tile of them: the mountain masks are coherent in SPACE, so a
+		// compact warp footprint (32 x 16 world units instead of 128 x 4 on the 1000^3 grid) crosses their borders less often, and a
+		// warp's 32 stores per slice are still four full 32-byte sectors
+		const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if UPG_COLUMN_LINE // A/B: a warp = 32 consecutive x of one row
+		const uint32_t x = blockIdx.x * COLUMN_TILE_X + lane;
+		const uint32_t y = blockIdx.y * COLUMN_TILE_Y + warp;
+#else
+		const uint32_t x = blockIdx.x * COLUMN_TILE_X + (warp & 3u) * 8u + (lane & 7u);
+		const uint32_t y = blockIdx.y * COLUMN_TILE_Y + (warp >> 2) * 4u + (lane >> 3);
+#endif
+		if (x >= res || y >= res)
 			return;
 		const float px = grid_coord(P.grid, x), py = grid_coord(P.grid, y);
 		const int field = L.field;

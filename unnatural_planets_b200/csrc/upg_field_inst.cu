@@ -45,7 +45,7 @@ namespace upg
 					{
 						if (!L.positions && L.count % slice == 0 && (L.field == FD_ALL || L.field == FD_LAND || L.field == FD_NAVIGATION || L.field == FD_ELEVATION_RAW))
 						{
-							const dim3 grid((unsigned)((P.grid.res + FIELD_BLOCK - 1) / FIELD_BLOCK), (unsigned)P.grid.res, (unsigned)((L.count / slice + COLUMN_Z - 1) / COLUMN_Z));
+							const dim3 grid((unsigned)((P.grid.res + COLUMN_TILE_X - 1) / COLUMN_TILE_X), (unsigned)((P.grid.res + COLUMN_TILE_Y - 1) / COLUMN_TILE_Y), (unsigned)((L.count / slice + COLUMN_Z - 1) / COLUMN_Z));
 							sdf_column_kernel<S, UPG_ELEV><<<grid, FIELD_BLOCK, 0, stream>>>(P, L);
 							return true;
 						}

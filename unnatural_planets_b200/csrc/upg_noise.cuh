@@ -465,8 +465,14 @@ namespace upg
 	// Cellular: 27 neighbouring cells, one jittered feature point each.  `rv` = the 256 x float4 jitter
 	// direction table handed to the planet at creation (see upg.h: upstream's table is not
 	// reconstructible, the oracle declares a substitute and the product receives it as data).
-	template<int DIST, int OP>
-	UPG_HD float single_cellular(const float *rv, int32_t seed, float x, float y, float z)
+	// the 27-cell scan of SingleCellular: two smallest distances and the hash of the closest feature point
+	struct CellularScan
+	{
+		float d0, d1;
+		int32_t closest;
+	};
+	template<int DIST>
+	UPG_HD CellularScan cellular_scan(const float *rv, int32_t seed, float x, float y, float z)
 	{
 		const int32_t xr = fast_round(x), yr = fast_round(y), zr = fast_round(z);
 		float d0 = 1e10f, d1 = 1e10f;
@@ -510,7 +516,14 @@ namespace upg
 			}
 			xp = iadd(xp, PRIME_X);
 		}
+		return CellularScan{ d0, d1, closest };
+	}
 
+	// the return kinds of SingleCellular over one scan
+	template<int DIST, int OP>
+	UPG_HD float cellular_result(CellularScan c)
+	{
+		float d0 = c.d0, d1 = c.d1;
 		if (DIST == CD_EUCLIDEAN && OP >= CO_DISTANCE)
 		{
 			d0 = sqrtf(d0);
@@ -521,7 +534,7 @@ namespace upg
 		switch (OP)
 		{
 			case CO_CELL:
-				return (float)closest * (1 / 2147483648.0f);
+				return (float)c.closest * (1 / 2147483648.0f);
 			case CO_DISTANCE:
 				return d0 - 1;
 			case CO_DISTANCE2:
@@ -537,6 +550,12 @@ namespace upg
 			default:
 				return 0;
 		}
+	}
+
+	template<int DIST, int OP>
+	UPG_HD float single_cellular(const float *rv, int32_t seed, float x, float y, float z)
+	{
+		return cellular_result<DIST, OP>(cellular_scan<DIST>(rv, seed, x, y, z));
 	}
 
 	// ---- dispatch + fractal drivers -----------------------------------------------------------------
@@ -569,10 +588,16 @@ namespace upg
 	{
 		return noise_single<TYPE>(seed, x, y, z);
 	}
-	template<int DIST, int OP>
-	UPG_OUTLINED float single_cellular_outlined(const float *rv, int32_t seed, float x, float y, float z)
+	// one body per distance function; the return kind is a handful of instructions at the call site
+	template<int DIST>
+	UPG_OUTLINED CellularScan cellular_scan_outlined(const float *rv, int32_t seed, float x, float y, float z)
 	{
-		return single_cellular<DIST, OP>(rv, seed, x, y, z);
+		return cellular_scan<DIST>(rv, seed, x, y, z);
+	}
+	template<int DIST, int OP>
+	UPG_HD float single_cellular_outlined(const float *rv, int32_t seed, float x, float y, float z)
+	{
+		return cellular_result<DIST, OP>(cellular_scan_outlined<DIST>(rv, seed, x, y, z));
 	}
 
 	UPG_HD float ping_pong(float t)
@@ -789,6 +814,42 @@ namespace upg
 			amp *= n.gain;
 		}
 		return sum;
+	}
+
+	// TWO cellular noises that share seed, frequency, fractal parameters and position but differ in the return kind -- the reference
+	// builds such pairs from one `static const uint32 seed` (bedrock cracks / value, grass patches, ice: sources/coloringModes.cpp:221-240,
+	// 480-509, 767-790) -- scan the same 27 cells per octave: one scan serves both.  a = noise3_cellular<DIST, OP_A, ...>(rv, n, ...),
+	// b = noise3_cellular<DIST, OP_B, ...>(rv, n, ...), bit for bit.
+	template<int DIST, int OP_A, int OP_B, int FRACTAL, int OCTAVES>
+	UPG_HD void noise3_cellular_pair(const float *rv, const NoiseInst &n, float x, float y, float z, float &a, float &b)
+	{
+		x *= n.frequency;
+		y *= n.frequency;
+		z *= n.frequency;
+		if (FRACTAL == FT_NONE)
+		{
+			const CellularScan c = cellular_scan_outlined<DIST>(rv, n.seed, x, y, z);
+			a = cellular_result<DIST, OP_A>(c);
+			b = cellular_result<DIST, OP_B>(c);
+			return;
+		}
+		int32_t seed = n.seed;
+		float sumA = 0, sumB = 0;
+		float amp = n.bounding;
+#pragma unroll 1
+		for (int o = 0; o < OCTAVES; o++)
+		{
+			const CellularScan c = cellular_scan_outlined<DIST>(rv, seed, x, y, z);
+			seed = iadd(seed, 1);
+			sumA += fractal_term<FRACTAL>(cellular_result<DIST, OP_A>(c)) * amp;
+			sumB += fractal_term<FRACTAL>(cellular_result<DIST, OP_B>(c)) * amp;
+			x *= n.lacunarity;
+			y *= n.lacunarity;
+			z *= n.lacunarity;
+			amp *= n.gain;
+		}
+		a = sumA;
+		b = sumB;
 	}
 
 	// GetNoise(x, 0) for the Value kind, no fractal (sources/coloringModes.cpp:36-48)
