@@ -148,7 +148,7 @@ namespace upg
 	// "the column left its lattice cell" is a uniform branch.
 	constexpr int COLUMN_TILE_X = 32, COLUMN_TILE_Y = FIELD_BLOCK / COLUMN_TILE_X; // columns per block
 #ifndef UPG_COLUMN_Z
-#define UPG_COLUMN_Z 32
+#define UPG_COLUMN_Z 64
 #endif
 	constexpr int COLUMN_Z = UPG_COLUMN_Z;
 #ifndef UPG_COLUMN_PERLIN
