@@ -66,6 +66,11 @@ def _worker(rank, world, port, out_path):
         # several fields in one exchange (what ShardedPlanet.field_meshes does): a second "field" with the arrays scaled / shifted
         tens_b = {k: (t * 3 if k in ("positions", "normals", "dmc_vertices") else t) for k, t in tens.items()}
         both = sharded.assemble_meshes_tensors({"land": tens, "water": tens_b}, ["land", "water"], dst=0, keys=[k for k, _ in sharded.MESH_KEYS])
+        # a mesh only rank 1 holds reaches every rank (ShardedPlanet.bake(src=...)): one payload broadcast
+        held = [np.arange(21, dtype=np.float32).reshape(7, 3) * np.float32(0.5), np.arange(14, dtype=np.float32).reshape(7, 2), np.array([4000000000, 1, 2, 3, 4, 5], dtype=np.uint32)]
+        got_b = sharded.broadcast_arrays(held if rank == 1 else None, src=1)
+        assert len(got_b) == 3 and got_b[0].shape == (7, 3) and got_b[1].shape == (7, 2) and got_b[2].shape == (6,)
+        assert (got_b[0].numpy() == held[0]).all() and (got_b[1].numpy() == held[1]).all() and (got_b[2].numpy().view(np.uint32) == held[2]).all()
         # row tiles of a 37-row image (ragged split)
         h, w = 37, 5
         img = [np.arange(h * w * c, dtype=np.uint32).reshape(h, w, c).astype(np.uint8) for c in (3, 2, 1)]

@@ -758,7 +758,12 @@ namespace upg
 					failed.store(1);
 			}
 		};
+		// up to six copy threads, fewer when the host cores are shared by one process per GPU (bench.py --gpus 8: 8 ranks x 2 bakes)
 		unsigned workers = std::thread::hardware_concurrency();
+		int devices = 1;
+		if (cudaGetDeviceCount(&devices) != cudaSuccess || devices < 1)
+			devices = 1;
+		workers /= (unsigned)devices;
 		workers = workers > 6 ? 6 : workers < 1 ? 1 : workers;
 		if (workers > slices.size())
 			workers = (unsigned)slices.size();
