@@ -95,13 +95,13 @@ namespace upg
 		uint32_t st = 0;
 		cudaError_t e = cudaMemcpyAsync(&st, planet->status, sizeof(st), cudaMemcpyDeviceToHost, stream);
 		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(stream);
+			e = stream_sync(stream);
 		if (e != cudaSuccess)
 			return cuda_fail(e, what);
 		if (st & 1u)
 		{
 			cudaMemsetAsync(planet->status, 0, sizeof(uint32_t), stream);
-			cudaStreamSynchronize(stream);
+			stream_sync(stream);
 			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in %s", what);
 		}
 		return UPG_OK;
@@ -469,7 +469,7 @@ extern "C"
 			unsigned long long n = 0;
 			e = cudaMemcpyAsync(&n, counter, sizeof(n), cudaMemcpyDeviceToHost, stream);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(stream);
+				e = stream_sync(stream);
 			if (e != cudaSuccess && rc == UPG_OK)
 				rc = cuda_fail(e, "upg_fields_samples_band_device");
 			if (band)
@@ -538,9 +538,9 @@ extern "C"
 				e = cudaEventRecord(drained[b], cs.copy);
 		}
 		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs.copy);
+			e = stream_sync(cs.copy);
 		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs.compute);
+			e = stream_sync(cs.compute);
 		for (int i = 0; i < 2; i++)
 		{
 			if (buf[i])
@@ -594,7 +594,7 @@ extern "C"
 		if (e == cudaSuccess && rc == UPG_OK)
 			e = cudaMemcpyAsync(host_out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost, cs.compute);
 		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(cs.compute);
+			e = stream_sync(cs.compute);
 		if (dpos)
 			cudaFreeAsync(dpos, cs.compute);
 		if (dout)
@@ -778,6 +778,58 @@ namespace upg
 		return UPG_OK;
 	}
 
+	namespace
+	{
+		struct SleepingEvent
+		{
+			cudaEvent_t event = nullptr;
+			int device = -1;
+			~SleepingEvent()
+			{
+				if (event)
+					cudaEventDestroy(event);
+			}
+		};
+		bool blocking_sync_wanted()
+		{
+			if (const char *env = std::getenv("UPG_BLOCKING_SYNC"))
+				return env[0] != '0';
+			int devices = 1;
+			if (cudaGetDeviceCount(&devices) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return false;
+			}
+			return devices >= 4;
+		}
+	}
+
+	cudaError_t stream_sync(cudaStream_t s)
+	{
+		static const bool blocking = blocking_sync_wanted();
+		if (!blocking)
+			return cudaStreamSynchronize(s);
+		thread_local SleepingEvent ev;
+		int device = 0;
+		cudaError_t e = cudaGetDevice(&device);
+		if (e != cudaSuccess)
+			return e;
+		if (!ev.event || ev.device != device)
+		{
+			if (ev.event)
+				cudaEventDestroy(ev.event);
+			ev.event = nullptr;
+			e = cudaEventCreateWithFlags(&ev.event, cudaEventBlockingSync | cudaEventDisableTiming);
+			if (e != cudaSuccess)
+				return e;
+			ev.device = device;
+		}
+		e = cudaEventRecord(ev.event, s);
+		if (e != cudaSuccess)
+			return e;
+		return cudaEventSynchronize(ev.event);
+	}
+
 	// UPG_TRACE=1: wall-clock phases of the host-buffer entry points on stderr (profiling aid)
 	bool trace_enabled()
 	{
@@ -828,7 +880,7 @@ namespace upg
 		if (e == cudaSuccess && nq)
 			e = cudaMemcpyAsync(out->dmc_quads, r.quads + q0, sizeof(uint32_t) * nq * 4, cudaMemcpyDeviceToHost, s);
 		if (e == cudaSuccess)
-			e = cudaStreamSynchronize(s);
+			e = stream_sync(s);
 		if (e != cudaSuccess)
 		{
 			pinned_release(block, capacity);
@@ -877,7 +929,7 @@ extern "C"
 			rc = sample_one_for_extraction(p, field, 0, res, dens, cs.compute, &bits, &bitBlock);
 		if (trace)
 		{
-			cudaStreamSynchronize(cs.compute);
+			stream_sync(cs.compute);
 			t1 = now_ms();
 		}
 		DmcResult r;
@@ -891,7 +943,7 @@ extern "C"
 			rc = fail(UPG_ERR_EMPTY_MESH, "generated empty mesh");
 		if (trace)
 		{
-			cudaStreamSynchronize(cs.compute);
+			stream_sync(cs.compute);
 			t2 = now_ms();
 		}
 		if (rc == UPG_OK)
@@ -901,7 +953,7 @@ extern "C"
 		dmc_release(r, cs.compute);
 		if (dens)
 			cudaFreeAsync(dens, cs.compute);
-		cudaStreamSynchronize(cs.compute);
+		stream_sync(cs.compute);
 		cs.close();
 		return rc;
 	}
@@ -1037,7 +1089,7 @@ extern "C"
 							r = dmc_extract(dens[f], res, res, zb - za, p->boxSize, res, ws.compute, d, za, slabCount > 0 ? z0 : 0, slabCount > 0 ? z1 : 0x7fffffff, bits3[f].signs ? &bits3[f] : nullptr);
 						if (trace)
 						{
-							cudaStreamSynchronize(ws.compute);
+							stream_sync(ws.compute);
 							w1 = now_ms();
 						}
 						if (r == UPG_OK && stages)
@@ -1056,14 +1108,14 @@ extern "C"
 							r = fail(UPG_ERR_EMPTY_MESH, "generated empty base %s mesh", f == FD_LAND ? "land" : f == FD_WATER ? "water" : "navigation");
 						if (trace)
 						{
-							cudaStreamSynchronize(ws.compute);
+							stream_sync(ws.compute);
 							w2 = now_ms();
 						}
 						if (r == UPG_OK && out3)
 							r = mesh_to_host(d, ws.compute, &out3[f]);
 						else if (r == UPG_OK)
 						{
-							ee = cudaStreamSynchronize(ws.compute);
+							ee = stream_sync(ws.compute);
 							if (ee != cudaSuccess)
 								r = cuda_fail(ee, "extraction");
 							else
@@ -1073,7 +1125,7 @@ extern "C"
 							std::fprintf(stderr, "[upg]   field %d: extract %.2f ms, clean-up %.2f ms, download %.2f ms (%u vertices, %u triangles)\n", f, w1 - w0, w2 - w1, now_ms() - w2, d.vertexCount, d.triangleCount);
 						dmc_release(d, ws.compute);
 						if (ws.compute)
-							cudaStreamSynchronize(ws.compute);
+							stream_sync(ws.compute);
 						ws.close();
 						rcs[f] = r;
 						if (r != UPG_OK)
@@ -1096,7 +1148,7 @@ extern "C"
 				cudaFreeAsync(dens[f], cs.compute);
 		if (bitBlock)
 			cudaFreeAsync(bitBlock, cs.compute);
-		cudaStreamSynchronize(cs.compute);
+		stream_sync(cs.compute);
 		cs.close();
 		if (rc != UPG_OK)
 			for (int f = 0; f < 3; f++)
@@ -1205,7 +1257,7 @@ extern "C"
 			cudaFreeAsync(dn, s);
 		if (di)
 			cudaFreeAsync(di, s);
-		cudaStreamSynchronize(s);
+		stream_sync(s);
 		cs.close();
 		return rc;
 	}
@@ -1269,7 +1321,7 @@ extern "C"
 		dmc_release(r, cs.compute);
 		if (dens)
 			cudaFreeAsync(dens, cs.compute);
-		cudaStreamSynchronize(cs.compute);
+		stream_sync(cs.compute);
 		cs.close();
 		return rc;
 	}
@@ -1303,7 +1355,7 @@ extern "C"
 		dmc_release(r, cs.compute);
 		if (dens)
 			cudaFreeAsync(dens, cs.compute);
-		cudaStreamSynchronize(cs.compute);
+		stream_sync(cs.compute);
 		cs.close();
 		return rc;
 	}
@@ -1321,7 +1373,7 @@ extern "C"
 		void *staging = nullptr;
 		size_t capacity = 0;
 		int rc = upload_host_arrays(arrays, count, (cudaStream_t)cuda_stream, &staging, &capacity);
-		e = cudaStreamSynchronize((cudaStream_t)cuda_stream);
+		e = stream_sync((cudaStream_t)cuda_stream);
 		if (staging)
 			pinned_block_release(staging, capacity);
 		if (rc == UPG_OK && e != cudaSuccess)

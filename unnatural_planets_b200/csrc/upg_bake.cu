@@ -706,7 +706,7 @@ namespace upg
 			{
 				for (int i = 0; i < count; i++)
 					cudaFreeAsync(ptrs[i], s);
-				cudaStreamSynchronize(s);
+				stream_sync(s);
 			}
 		};
 
@@ -836,7 +836,7 @@ extern "C"
 			if (e == cudaSuccess && rc == UPG_OK)
 				e = cudaMemcpyAsync(host_out, dout, sizeof(upg_tile) * n, cudaMemcpyDeviceToHost, cs.compute);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(cs.compute);
+				e = stream_sync(cs.compute);
 			if (rc == UPG_OK && e != cudaSuccess)
 				rc = cuda_fail(e, "upg_tiles");
 			if (rc == UPG_OK)
@@ -897,7 +897,7 @@ extern "C"
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(&visits, dvisits, sizeof(visits), cudaMemcpyDeviceToHost, cs.compute);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(cs.compute);
+				e = stream_sync(cs.compute);
 			if (callbacks)
 				*callbacks = visits;
 			if (e != cudaSuccess)
@@ -959,7 +959,7 @@ extern "C"
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(image, src, sizeof(float) * n, cudaMemcpyDeviceToHost, cs.compute);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(cs.compute);
+				e = stream_sync(cs.compute);
 			if (e != cudaSuccess)
 				rc = cuda_fail(e, "upg_dilate");
 		}
@@ -1048,7 +1048,7 @@ extern "C"
 				if (e == cudaSuccess)
 					e = cudaMemcpyAsync(&covered, dcount, sizeof(covered), cudaMemcpyDeviceToHost, s);
 				if (e == cudaSuccess)
-					e = cudaStreamSynchronize(s);
+					e = stream_sync(s);
 				if (e == cudaSuccess && covered)
 				{
 					count_in_range_kernel<<<blocks_for(covered, 256), 256, 0, s>>>(list, covered, (row0 - bandBegin) * w, (row1 - bandBegin) * w, dvisits + 1);
@@ -1099,7 +1099,7 @@ extern "C"
 
 			if (trace)
 			{
-				cudaStreamSynchronize(s);
+				stream_sync(s);
 				tr[2] = now_ms();
 			}
 			// K7 over the band (its outer 7 rows are apron unless they are the image border), then the caller's rows
@@ -1113,7 +1113,7 @@ extern "C"
 				e = dilate7(imgHeight, w, bandH, 1, qHeight, s);
 			if (trace)
 			{
-				cudaStreamSynchronize(s);
+				stream_sync(s);
 				tr[3] = now_ms();
 			}
 			if (e == cudaSuccess && rc == UPG_OK)
@@ -1143,7 +1143,7 @@ extern "C"
 					e = cudaMemcpyAsync(dNormal, T.normal, keep * 3, cudaMemcpyDefault, s);
 			}
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(s);
+				e = stream_sync(s);
 			if (trace)
 				std::fprintf(stderr, "[upg]   bake core %s %ux%u rows [%u, %u): raster + compaction %.2f ms, colouring %.2f ms (%u texels), dilation %.2f ms, tail + copies out %.2f ms\n", water ? "water" : "land", w, h, row0, row1, tr[1] - tr[0], tr[2] - tr[1], covered, tr[3] - tr[2], now_ms() - tr[3]);
 			t_lastCovered = coveredRows;
@@ -1214,7 +1214,7 @@ extern "C"
 			if (e == cudaSuccess && heightMap)
 				e = cudaMemcpyAsync(normal, T.normal, n * 3, cudaMemcpyDeviceToHost, s);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(s);
+				e = stream_sync(s);
 			if (e != cudaSuccess)
 				rc = cuda_fail(e, "upg_texture_tail");
 		}
@@ -1260,7 +1260,7 @@ extern "C"
 			const double t0 = trace ? now_ms() : 0;
 			if (trace)
 			{
-				cudaStreamSynchronize(s);
+				stream_sync(s);
 				std::fprintf(stderr, "[upg] bake (host buffers): mesh upload %.2f ms (%.1f MB, waited %.2f ms after enqueueing)\n", now_ms() - tUp, (32.0 * nverts + 4.0 * nidx) * 1e-6, now_ms() - t0);
 			}
 			// the outputs are host memory: the core's final copies are cudaMemcpyDefault, so they land there directly
@@ -1268,7 +1268,7 @@ extern "C"
 				rc = bake_core(planet, water, dpos, dnrm, duv, nverts, didx, nidx, w, h, row0, row1, albedo, special, heightMap, pbr, normalMap, 1.f, s);
 			if (staging)
 			{
-				cudaStreamSynchronize(s);
+				stream_sync(s);
 				pinned_block_release(staging, stagingCapacity);
 			}
 			if (trace)

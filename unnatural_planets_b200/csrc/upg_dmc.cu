@@ -794,7 +794,7 @@ namespace upg
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(&b, scanned + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(s);
+				e = stream_sync(s);
 			*total = a + b;
 			return e;
 		}
@@ -861,7 +861,7 @@ namespace upg
 			unsigned long long nz = 0;
 			e = cudaMemcpyAsync(&nz, nearZero, sizeof(nz), cudaMemcpyDeviceToHost, s);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(s);
+				e = stream_sync(s);
 			out.nearZeroSamples = nz;
 		}
 
@@ -948,7 +948,7 @@ namespace upg
 					UPG_LAUNCHED();
 				}
 				UPG_TRY(cudaMemcpyAsync(h, ranges, sizeof(h), cudaMemcpyDeviceToHost, s));
-				UPG_TRY(cudaStreamSynchronize(s));
+				UPG_TRY(stream_sync(s));
 				if (ranges)
 					cudaFreeAsync(ranges, s);
 				if (e == cudaSuccess)

@@ -109,6 +109,12 @@ namespace upg
 	};
 	int upload_host_arrays(const HostArray *arrays, int n, cudaStream_t stream, void **staging, size_t *stagingCapacity);
 
+	// Waits for a stream.  cudaStreamSynchronize spins; with one process per GPU (bench.py --gpus 8: eight ranks, each with its three
+	// extraction threads and two bake threads) the spinning threads outnumber the host cores and starve the threads that launch work,
+	// so when several GPUs are visible the wait goes through an event created with cudaEventBlockingSync and the thread sleeps instead.
+	// UPG_BLOCKING_SYNC=0 / 1 overrides the choice.
+	cudaError_t stream_sync(cudaStream_t s);
+
 	bool trace_enabled(); // UPG_TRACE=1
 	double now_ms();
 

@@ -636,7 +636,7 @@ namespace upg
 			if (e == cudaSuccess)
 				e = cudaMemcpyAsync(&b, out + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, pool.s);
 			if (e == cudaSuccess)
-				e = cudaStreamSynchronize(pool.s);
+				e = stream_sync(pool.s);
 			*total = a + b;
 			return e;
 		}
@@ -787,7 +787,7 @@ namespace upg
 			MF_TRY(scan_u32(pool, newOut, newOff, tris, &created));
 			uint32_t hostCounters[4] = { 0, 0, 0, 0 };
 			MF_TRY(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, s));
-			MF_TRY(cudaStreamSynchronize(s));
+			MF_TRY(stream_sync(s));
 			if (e == cudaSuccess && hostCounters[1])
 				rc = fail(UPG_ERR_INVALID_VALUE, "clipping one triangle against the box produced more than %d pieces", CLIP_MAX_TRIS);
 			if (e == cudaSuccess && rc == UPG_OK && (uint64_t)verts + created >= LOCAL_BIT)
@@ -835,7 +835,7 @@ namespace upg
 					MF_LAUNCHED();
 				}
 				MF_TRY(cudaMemcpyAsync(hostCounters, counters, sizeof(hostCounters), cudaMemcpyDeviceToHost, s));
-				MF_TRY(cudaStreamSynchronize(s));
+				MF_TRY(stream_sync(s));
 				if (e == cudaSuccess && hostCounters[2])
 				{
 					flatten_kernel<<<blocks_of(w.verts), MF_BLOCK, 0, s>>>(parent, w.verts);
