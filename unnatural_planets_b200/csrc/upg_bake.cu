@@ -196,11 +196,24 @@ namespace upg
 		// covered texels of the band that fall into the caller's rows (the band adds a 7-row apron for the dilation)
 		__global__ void __launch_bounds__(256) count_in_range_kernel(const uint32_t *__restrict__ list, uint32_t n, uint32_t lo, uint32_t hi, unsigned long long *__restrict__ out)
 		{
-			const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-			const bool in = i < n && list[i] >= lo && list[i] < hi;
-			const unsigned m = __ballot_sync(0xffffffffu, in);
-			if ((threadIdx.x & 31) == 0 && m)
-				atomicAdd(out, (unsigned long long)__popc(m));
+			// grid-stride, one atomic per block (one per warp made half a million same-address atomics of a 4096^2 bake: 0.36 ms)
+			__shared__ uint32_t warpSum[8];
+			uint32_t mine = 0;
+			for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+				mine += (list[i] >= lo && list[i] < hi) ? 1u : 0u;
+			for (int o = 16; o > 0; o >>= 1)
+				mine += __shfl_down_sync(0xffffffffu, mine, o);
+			if ((threadIdx.x & 31) == 0)
+				warpSum[threadIdx.x >> 5] = mine;
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				uint32_t total = 0;
+				for (int k = 0; k < 8; k++)
+					total += warpSum[k];
+				if (total)
+					atomicAdd(out, (unsigned long long)total);
+			}
 		}
 
 		struct IsCovered
@@ -1049,9 +1062,12 @@ extern "C"
 					e = cudaMemcpyAsync(&covered, dcount, sizeof(covered), cudaMemcpyDeviceToHost, s);
 				if (e == cudaSuccess)
 					e = stream_sync(s);
-				if (e == cudaSuccess && covered)
+				if (e == cudaSuccess && covered && row0 == bandBegin && row1 == bandEnd)
+					coveredRows = covered; // the band is the caller's rows (whole images): nothing to separate
+				else if (e == cudaSuccess && covered)
 				{
-					count_in_range_kernel<<<blocks_for(covered, 256), 256, 0, s>>>(list, covered, (row0 - bandBegin) * w, (row1 - bandBegin) * w, dvisits + 1);
+					const unsigned countBlocks = blocks_for(covered, 256) < 1184u ? blocks_for(covered, 256) : 1184u; // 148 SMs x 8 blocks
+					count_in_range_kernel<<<countBlocks, 256, 0, s>>>(list, covered, (row0 - bandBegin) * w, (row1 - bandBegin) * w, dvisits + 1);
 					e = cudaGetLastError();
 					if (e == cudaSuccess)
 						e = cudaMemcpyAsync(&coveredRows, dvisits + 1, sizeof(coveredRows), cudaMemcpyDeviceToHost, s);
