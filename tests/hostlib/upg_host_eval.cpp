@@ -48,22 +48,22 @@ namespace
 	template<int E>
 	struct ElevColumnDispatch
 	{
-		static float run(int elev, const PlanetParams &P, V3 p, ValueFbmColumn<4> &c, PerlinColumn &m)
+		static float run(int elev, const PlanetParams &P, V3 p, ValueFbmColumn<4> &c, PerlinColumn &m, PerlinFbmColumn<3> &tc)
 		{
 			if (elev == E)
 			{
 				float first = 0;
 				if (ElevationStartsWithValueFbm<E>::value)
 					first = value_fbm_column<4>(P.el.n[0], p.x, p.y, p.z, c);
-				return elevation_raw_given<E>(P, p, first, &m);
+				return elevation_raw_given<E>(P, p, first, &m, &tc);
 			}
-			return ElevColumnDispatch<E + 1>::run(elev, P, p, c, m);
+			return ElevColumnDispatch<E + 1>::run(elev, P, p, c, m, tc);
 		}
 	};
 	template<>
 	struct ElevColumnDispatch<EL_COUNT>
 	{
-		static float run(int, const PlanetParams &, V3, ValueFbmColumn<4> &, PerlinColumn &) { return NAN; }
+		static float run(int, const PlanetParams &, V3, ValueFbmColumn<4> &, PerlinColumn &, PerlinFbmColumn<3> &) { return NAN; }
 	};
 
 	float eval_field(const PlanetParams &P, int field, V3 pos)
@@ -169,11 +169,12 @@ extern "C"
 			{
 				ValueFbmColumn<4> c;
 				PerlinColumn m;
+				PerlinFbmColumn<3> tc;
 				for (int k = 0; k < n; k++)
 				{
 					int zi = zOrder == 0 ? k : zOrder == 1 ? n - 1 - k : ((k * stride) % n);
 					const uint32_t z = (uint32_t)(z0 + zi);
-					out[((uint64_t)zi * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, z)), c, m);
+					out[((uint64_t)zi * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, z)), c, m, tc);
 				}
 			}
 	}
@@ -187,8 +188,9 @@ extern "C"
 			{
 				ValueFbmColumn<4> c;
 				PerlinColumn m;
+				PerlinFbmColumn<3> tc;
 				for (int z = z0; z < z1; z++)
-					out[((uint64_t)(z - z0) * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, (uint32_t)z)), c, m);
+					out[((uint64_t)(z - z0) * res + y) * res + x] = ElevColumnDispatch<0>::run(p->params.elevation, p->params, v3(grid_coord(g, x), grid_coord(g, y), grid_coord(g, (uint32_t)z)), c, m, tc);
 			}
 	}
 	void upgh_grid_coords(const upgh_planet *p, float *out)

@@ -154,6 +154,9 @@ namespace upg
 #ifndef UPG_COLUMN_PERLIN
 #define UPG_COLUMN_PERLIN 1 // also cache the Perlin mountain mask along the column
 #endif
+#ifndef UPG_COLUMN_TERRACES
+#define UPG_COLUMN_TERRACES 0 // A/B: also cache the terrace octaves (57 more floats per thread)
+#endif
 #ifndef UPG_COLUMN_MIN_BLOCKS
 #define UPG_COLUMN_MIN_BLOCKS 5 // resident blocks per SM the register allocation aims at (A/B in profiles/)
 #endif
@@ -188,6 +191,9 @@ namespace upg
 #if UPG_COLUMN_PERLIN
 		PerlinColumn maskColumn; // the mountain mask of lakes / islands (elevation_mountains)
 #endif
+#if UPG_COLUMN_TERRACES
+		PerlinFbmColumn<3> terraceColumn; // the three Perlin octaves behind the terrace mask
+#endif
 		bool bad = false;
 		uint64_t idx = ((uint64_t)zBegin * res + y) * res + x;
 		const uint64_t slice = (uint64_t)res * res;
@@ -198,7 +204,9 @@ namespace upg
 			if (field != FD_ELEVATION_RAW)
 				base = shape_sdf<SHAPE>(P, pos);
 			const float first = value_fbm_column<4>(P.el.n[0], pos.x, pos.y, pos.z, column);
-#if UPG_COLUMN_PERLIN
+#if UPG_COLUMN_PERLIN && UPG_COLUMN_TERRACES
+			const float elev = elevation_raw_given<ELEV>(P, pos, first, &maskColumn, &terraceColumn);
+#elif UPG_COLUMN_PERLIN
 			const float elev = elevation_raw_given<ELEV>(P, pos, first, &maskColumn);
 #else
 			const float elev = elevation_raw_given<ELEV>(P, pos, first);

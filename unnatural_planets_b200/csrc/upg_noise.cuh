@@ -790,6 +790,35 @@ namespace upg
 		return nlerp(yf0, yf1, zs) * 0.964921414852142333984375f;
 	}
 
+	// == noise3<NT_PERLIN, FT_FBM, OCTAVES>(n, x, y, z) for successive samples of one (x, y) column: one PerlinColumn per octave
+	template<int OCTAVES>
+	struct PerlinFbmColumn
+	{
+		PerlinColumn octave[OCTAVES];
+	};
+	template<int OCTAVES>
+	UPG_HD float perlin_fbm_column(const NoiseInst &n, float x, float y, float z, PerlinFbmColumn<OCTAVES> &c)
+	{
+		x *= n.frequency;
+		y *= n.frequency;
+		z *= n.frequency;
+		int32_t seed = n.seed;
+		float sum = 0;
+		float amp = n.bounding;
+#pragma unroll
+		for (int o = 0; o < OCTAVES; o++)
+		{
+			const float v = perlin_column(seed, x, y, z, c.octave[o]);
+			seed = iadd(seed, 1);
+			sum += fractal_term<FT_FBM>(v) * amp;
+			x *= n.lacunarity;
+			y *= n.lacunarity;
+			z *= n.lacunarity;
+			amp *= n.gain;
+		}
+		return sum;
+	}
+
 	// cellular variant (needs the jitter table and the distance / return kind)
 	template<int DIST, int OP, int FRACTAL, int OCTAVES>
 	UPG_HD float noise3_cellular(const float *rv, const NoiseInst &n, float x, float y, float z)

@@ -601,7 +601,7 @@ namespace upg
 
 	// ---- elevation modes (sources/elevationModes.cpp) ------------------------------------------------
 	// `maskColumn`: the column kernel's cache of the mask noise (PerlinColumn, upg_noise.cuh), or null = evaluate it from scratch
-	UPG_HD float elevation_mountains(const ElevationConsts &E, V3 pos, float land, PerlinColumn *maskColumn = nullptr)
+	UPG_HD float elevation_mountains(const ElevationConsts &E, V3 pos, float land, PerlinColumn *maskColumn = nullptr, PerlinFbmColumn<3> *terraceColumn = nullptr)
 	{
 		const float cover = 1 - saturate_(land * -0.1f);
 		if (cover < 1e-7f)
@@ -630,7 +630,7 @@ namespace upg
 		float terraces = 0.0f;
 		if (tm != 0.0f)
 		{
-			terraces = noise3<NT_PERLIN, FT_FBM, 3>(E.n[3], pos);
+			terraces = terraceColumn ? perlin_fbm_column<3>(E.n[3], pos.x, pos.y, pos.z, *terraceColumn) : noise3<NT_PERLIN, FT_FBM, 3>(E.n[3], pos);
 			terraces = fmax_(terraces + 0.1f, 0.0f) * 2.5f;
 			terraces = terrace(terraces, 4);
 			terraces *= tm * cover;
@@ -649,7 +649,7 @@ namespace upg
 
 	// elevation_raw with that first noise value handed in (`first` is ignored by the other modes)
 	template<int ELEV>
-	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first, PerlinColumn *maskColumn = nullptr)
+	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first, PerlinColumn *maskColumn = nullptr, PerlinFbmColumn<3> *terraceColumn = nullptr)
 	{
 		const ElevationConsts &E = P.el;
 		switch (ELEV)
@@ -683,7 +683,7 @@ namespace upg
 				land = land * 2 - 1;
 				land = land / (abs_(land) + 0.17f) + 0.15f;
 				land *= 150;
-				return elevation_mountains(E, pos, land, maskColumn);
+				return elevation_mountains(E, pos, land, maskColumn, terraceColumn);
 			}
 			case EL_CRATERS:
 			{
