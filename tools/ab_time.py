@@ -48,4 +48,6 @@ for name, water in (("land", 0), ("water", 1)):
     out["bake_%s_ms" % name] = round(ms, 3)
     out["mtexels_per_s_%s" % name] = round(p.last_covered_texels / ms / 1e3, 1)
     out["checksum_%s" % name] = int(o[0].to(torch.int64).sum().item())
+    # position-weighted sums of the three images: equal outputs <=> equal numbers (for A/B builds that must stay bit-identical)
+    out["digest_%s" % name] = [int((x.to(torch.int64) * (torch.arange(x.numel(), device=dev) % 65521 + 1)).sum().item()) for x in o]
 print(out)

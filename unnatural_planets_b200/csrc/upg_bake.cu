@@ -18,6 +18,7 @@
 //                         apron, mostly L2 hits) + CH B written per texel instead of 7 x 8*CH B for seven global rounds.
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <cuda_runtime.h>
 
@@ -219,7 +220,29 @@ namespace upg
 		struct IsCovered
 		{
 			const uint32_t *owner;
-			__device__ __forceinline__ bool operator()(uint32_t i) const { return owner[i] != NO_OWNER; }
+			__device__ __forceinline__ bool operator()(uint32_t i) const { return i != 0xffffffffu && owner[i] != NO_OWNER; }
+		};
+
+		// The compacted list keeps the order in which the texels are offered to the selection.  Offering them tile by tile
+		// (TEXEL_TILE_W x TEXEL_TILE_H texels, row-major inside a tile) gives the 32 texels of a colouring warp a compact footprint
+		// on the surface -- ~8 x 4 world units instead of a 32 x 1 sliver -- so they meet the biome / slope masks of the layers and
+		// the lattice cells of the noises (single_cubic's warp-cooperative rows) together more often.  Texels are independent and
+		// written by id: the images do not depend on this order.  Slot -> texel id, 0xffffffff for the padding past the band's edges.
+#if !defined(UPG_TEXEL_TILE_W)
+#define UPG_TEXEL_TILE_W 8
+#define UPG_TEXEL_TILE_H 4
+#endif
+		constexpr uint32_t TEXEL_TILE_W = UPG_TEXEL_TILE_W, TEXEL_TILE_H = UPG_TEXEL_TILE_H;
+		struct TileOrder
+		{
+			uint32_t w, h, tilesX;
+			__host__ __device__ __forceinline__ uint32_t operator()(uint32_t slot) const
+			{
+				const uint32_t tile = slot / (TEXEL_TILE_W * TEXEL_TILE_H), in = slot % (TEXEL_TILE_W * TEXEL_TILE_H);
+				const uint32_t x = (tile % tilesX) * TEXEL_TILE_W + in % TEXEL_TILE_W;
+				const uint32_t y = (tile / tilesX) * TEXEL_TILE_H + in / TEXEL_TILE_W;
+				return x < w && y < h ? y * w + x : 0xffffffffu;
+			}
 		};
 
 		// K6a.  Probe layout: probes[(k * n + i) * 3 ..], k = 0..7 the slope ring, k = 8 the tile position.
@@ -993,6 +1016,9 @@ extern "C"
 			return fail(UPG_ERR_ARGUMENT, "generating texture requires triangles mesh");
 		if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull || row0 > row1 || row1 > h)
 			return fail(UPG_ERR_ARGUMENT, "bad texture resolution %u x %u or rows [%u, %u)", w, h, row0, row1);
+		// the compaction walks the image padded to whole texel tiles (TileOrder)
+		if (((uint64_t)w + TEXEL_TILE_W - 1) / TEXEL_TILE_W * (((uint64_t)h + TEXEL_TILE_H - 1) / TEXEL_TILE_H) * (TEXEL_TILE_W * TEXEL_TILE_H) > 0x7fffffffull)
+			return fail(UPG_ERR_ARGUMENT, "bad texture resolution %u x %u", w, h);
 		cudaError_t e = cudaSetDevice(p->device);
 		if (e != cudaSuccess)
 			return cuda_fail(e, "cudaSetDevice");
@@ -1042,22 +1068,25 @@ extern "C"
 				raster_owner_kernel<<<blocks_for(M.triangles, BAKE_BLOCK), BAKE_BLOCK, 0, s>>>(M, owner, dvisits);
 				e = cudaGetLastError();
 			}
-			// covered texels in raster order
+			// covered texels, tile by tile (TileOrder)
 			uint32_t covered = 0;
 			unsigned long long coveredRows = 0;
 			if (e == cudaSuccess)
 			{
 				size_t tmpBytes = 0;
-				thrust::counting_iterator<uint32_t> ids(0);
+				const TileOrder order{ w, bandH, (w + TEXEL_TILE_W - 1) / TEXEL_TILE_W };
+				const uint64_t slots64 = (uint64_t)order.tilesX * ((bandH + TEXEL_TILE_H - 1) / TEXEL_TILE_H) * (TEXEL_TILE_W * TEXEL_TILE_H);
+				const int slots = (int)slots64; // < 2^31: checked on entry
+				auto ids = thrust::make_transform_iterator(thrust::counting_iterator<uint32_t>(0), order);
 				IsCovered pred{ owner };
-				e = cub::DeviceSelect::If(nullptr, tmpBytes, ids, list, dcount, (int)texels, pred, s);
+				e = cub::DeviceSelect::If(nullptr, tmpBytes, ids, list, dcount, slots, pred, s);
 				void *tmp = nullptr;
 				if (e == cudaSuccess)
 					tmp = mem.alloc<char>(tmpBytes);
 				if (e == cudaSuccess)
 					e = mem.err;
 				if (e == cudaSuccess)
-					e = cub::DeviceSelect::If(tmp, tmpBytes, ids, list, dcount, (int)texels, pred, s);
+					e = cub::DeviceSelect::If(tmp, tmpBytes, ids, list, dcount, slots, pred, s);
 				if (e == cudaSuccess)
 					e = cudaMemcpyAsync(&covered, dcount, sizeof(covered), cudaMemcpyDeviceToHost, s);
 				if (e == cudaSuccess)

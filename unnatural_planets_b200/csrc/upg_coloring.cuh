@@ -31,6 +31,17 @@
 #define UPG_LAYER_SYNC() ((void)0)
 #endif
 
+// A layer's early return (`if (bf < 1e-7) return;`) taken by SOME lanes of a warp saves nothing -- the warp walks the rest of the layer
+// anyway -- but leaves it with a partial mask, and the warp-cooperative noise paths (upg_noise.cuh: single_cubic) need whole warps.
+// The layers below therefore keep a per-lane `on` flag, leave early only when NO lane of the warp is on (UPG_WARP_ANY, a vote), let the
+// off lanes compute values nobody reads, and apply their result under `if (on)`.  On the host the vote is the flag itself: the
+// reference's control flow.
+#if defined(__CUDA_ARCH__)
+#define UPG_WARP_ANY(flag) (__any_sync(__activemask(), (flag)) != 0)
+#else
+#define UPG_WARP_ANY(flag) (flag)
+#endif
+
 #if defined(__CUDACC__)
 // the layers are real (non-inlined) device functions: the colouring kernel stays a few thousand instructions per layer
 // instead of one giant inlined body; they only exist in the translation unit that launches the kernel
@@ -403,11 +414,13 @@ namespace upg
 		// bf = (a factor in [0, 1]) * steepness: when the steepness mask alone is under the threshold so is bf, and the three Perlin octaves
 		// behind the other factor are not needed (same early return as the reference's, taken earlier)
 		const float steepness = steepness_mask(t.slope, 20, 5);
-		if (steepness < 1e-7f)
+		bool on = !(steepness < 1e-7f);
+		if (!UPG_WARP_ANY(on))
 			return;
 		float height = noise3<NT_PERLIN, FT_FBM, 3, true>(C.dirtHeight, t.position) * 0.2f + 0.5f;
 		const float bf = sharp_edge(saturate_(height - t.height + 0.4f)) * steepness;
-		if (bf < 1e-7f)
+		on = on && !(bf < 1e-7f);
+		if (!UPG_WARP_ANY(on))
 			return;
 		V3 color = v3(168, 94, 28) / 255;
 		{
@@ -427,6 +440,8 @@ namespace upg
 			color = lerp3(color, v3(0.1f, 0.1f, 0.1f), cracks);
 			roughness = lerp_(roughness, 0.9f, cracks);
 		}
+		if (!on)
+			return;
 		t.albedo = lerp3(t.albedo, color, bf);
 		t.roughness = lerp_(t.roughness, roughness, bf);
 		t.metallic = lerp_(t.metallic, metallic, bf);
@@ -437,7 +452,8 @@ namespace upg
 	UPG_LAYER void generate_sand(const ColoringConsts &C, Tile &t)
 	{
 		const float bf = range_mask(t.temperature, 24, 28) * steepness_mask(t.slope, 19, 10);
-		if (bf < 1e-7f)
+		const bool on = !(bf < 1e-7f);
+		if (!UPG_WARP_ANY(on))
 			return;
 		const float heightScale = noise3<NT_SIMPLEX, FT_FBM, 3, true>(C.sandHeightScale, t.position) * 0.3f + 1;
 		const float height = (noise3<NT_SIMPLEX, FT_RIDGED, 3, true>(C.sandHeight, t.position * heightScale) * 0.2f) * (range_mask(t.precipitation, 100, 50) * 0.4f + 0.6f) + 0.5f;
@@ -454,6 +470,8 @@ namespace upg
 		color = hsv_to_rgb(rgb_to_hsv(color) * v3(1, 0.7f, 0.8f));
 		const float roughness = (heightScale - 1) * 0.7f + 0.55f + hueShift;
 		const float metallic = 0;
+		if (!on)
+			return;
 		t.albedo = lerp3(t.albedo, color, bf);
 		t.roughness = lerp_(t.roughness, roughness, bf);
 		t.metallic = lerp_(t.metallic, metallic, bf);
@@ -607,11 +625,13 @@ namespace upg
 		// The reference evaluates the thickness noise (three ValueCubic octaves, 192 lattice taps) before it tests bf.  The factor applied
 		// below lies in [0, 1], so a bf under the threshold here stays under it: the same early return, taken before the noise -- which is
 		// nearly always, snow needs 220 m of elevation (identical tiles: tests/test_host_coloring.py).  A NaN bf compares false and goes on.
-		if (bf < 1e-7f)
+		bool on = !(bf < 1e-7f);
+		if (!UPG_WARP_ANY(on))
 			return;
 		const float thickness = noise3<NT_CUBIC, FT_FBM, 3, true>(C.snowThickness, t.position) * 0.5f + 0.5f;
 		bf *= saturate_(thickness * 0.5f + 0.7f);
-		if (bf < 1e-7f)
+		on = on && !(bf < 1e-7f);
+		if (!on)
 			return;
 		const V3 color = v3(230, 230, 230) / 255;
 		const float roughness = thickness * 0.3f + 0.2f;

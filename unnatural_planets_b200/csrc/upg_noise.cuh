@@ -240,6 +240,21 @@ namespace upg
 		return nlerp(yf0, yf1, zs) * 0.964921414852142333984375f;
 	}
 
+	// Warp-cooperative form of the x stage (device only, UPG_CUBIC_COOP).  The colouring kernel evaluates ValueCubic at frequencies
+	// whose lattice cells are 70 - 450 world units wide while the 32 texels of a warp are neighbours ~1 unit apart: nearly every
+	// warp sits in ONE cell, so its 64 lattice values -- and therefore the four polynomial coefficients p, (a - b) - p, c - a, b that
+	// cubic_lerp() derives from each row of four of them -- are the same for all 32 lanes.  Lanes 0..15 compute one row each
+	// (4 hashes instead of 64 per lane) into a per-warp shared-memory block, every lane reads the rows back as broadcast LDS.128
+	// and evaluates ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit.  Warps that
+	// are not whole (a layer's early return) or straddle a cell boundary take the per-lane path below.
+#if !defined(UPG_CUBIC_COOP)
+#define UPG_CUBIC_COOP 2
+#endif
+#if defined(__CUDACC__) && UPG_CUBIC_COOP
+	constexpr int CUBIC_COOP_MAX_WARPS = 32; // 1-D blocks of up to 1024 threads
+	static __shared__ float4 upg_cubic_rows[CUBIC_COOP_MAX_WARPS][16];
+#endif
+
 	UPG_HD float single_cubic(int32_t seed, float x, float y, float z)
 	{
 		int32_t x1 = fast_floor(x), y1 = fast_floor(y), z1 = fast_floor(z);
@@ -249,6 +264,61 @@ namespace upg
 		z1 = imul(z1, PRIME_Z);
 		const int32_t xi0 = isub(x1, PRIME_X), xi2 = iadd(x1, PRIME_X), xi3 = iadd(x1, ishl(PRIME_X, 1));
 		const int32_t yb = isub(y1, PRIME_Y), zb = isub(z1, PRIME_Z);
+#if defined(__CUDA_ARCH__) && UPG_CUBIC_COOP
+		if (__activemask() == 0xffffffffu)
+		{
+			const uint32_t full = 0xffffffffu;
+			const uint32_t lane = threadIdx.x & 31u;
+			float4 *rows = upg_cubic_rows[threadIdx.x >> 5];
+			const float tt = xs * xs, ttt = tt * xs;
+			float result = 0;
+			// one round per distinct lattice cell among the lanes (the primes are odd: equal products <=> equal cells); a warp's
+			// texels are an 8 x 4 tile ~1 world unit apart (upg_bake.cu: TileOrder), so nearly always one round, two or three at the
+			// highest frequencies.  `todo` is warp-uniform.
+			uint32_t todo = full;
+			do
+			{
+				const int leader = __ffs((int)todo) - 1;
+				const int32_t ux = __shfl_sync(full, x1, leader), uy = __shfl_sync(full, y1, leader), uz = __shfl_sync(full, z1, leader);
+				const bool mine = (x1 == ux) & (y1 == uy) & (z1 == uz);
+				const uint32_t group = __ballot_sync(full, mine);
+#if UPG_CUBIC_COOP == 1 // A/B: whole warps in one cell only, everything else per lane
+				if (group != full)
+					break;
+#endif
+				if (lane < 16u)
+				{
+					const int32_t s = seed ^ iadd(isub(uy, PRIME_Y), imul((int32_t)(lane & 3u), PRIME_Y)) ^ iadd(isub(uz, PRIME_Z), imul((int32_t)(lane >> 2), PRIME_Z));
+					const float a = value_bits_from_hash(imul(s ^ isub(ux, PRIME_X), 0x27d4eb2d)), b = value_bits_from_hash(imul(s ^ ux, 0x27d4eb2d));
+					const float c = value_bits_from_hash(imul(s ^ iadd(ux, PRIME_X), 0x27d4eb2d)), d = value_bits_from_hash(imul(s ^ iadd(ux, ishl(PRIME_X, 1)), 0x27d4eb2d));
+					const float p = (d - c) - (a - b);
+					rows[lane] = make_float4(p, (a - b) - p, c - a, b);
+				}
+				__syncwarp();
+				if (mine)
+				{
+					float zr[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+					{
+						float yr[4];
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+						{
+							const float4 q = rows[k * 4 + j];
+							yr[j] = ttt * q.x + tt * q.y + xs * q.z + q.w;
+						}
+						zr[k] = cubic_lerp(yr[0], yr[1], yr[2], yr[3], ys);
+					}
+					result = (cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * VALUE_SCALE) * (1 / (1.5f * 1.5f * 1.5f));
+				}
+				__syncwarp(); // the rows are rewritten by the next round / octave
+				todo &= ~group;
+			} while (todo);
+			if (!todo)
+				return result;
+		}
+#endif
 		float zr[4];
 		int32_t zp = zb;
 #pragma unroll
