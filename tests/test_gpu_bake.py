@@ -238,6 +238,30 @@ def test_bake_rows_equal_whole_image(water):
         assert (np.concatenate([q[k] for q in parts], axis=0) == whole[k]).all()
 
 
+@pytest.mark.parametrize("size", [(190, 187), (61, 33), (7, 3)])
+def test_bake_ragged_sizes(size):
+    # image sizes that are not multiples of the 8 x 4 texel tiles the covered texels are compacted in (upg_bake.cu: TileOrder):
+    # coverage and images equal the reference's, and row bands still reassemble to the whole image bit for bit
+    w, h = size
+    cfg = ("sphere", "lakes", "default", True, True)
+    pos, nrm, uv, idx = bc.atlas_mesh()
+    p = make_planet(cfg)
+    whole = p.bake(0, pos, nrm, uv, idx, w, h)
+    total = p.last_covered_texels
+    cuts = sorted({0, 1, h // 3, h // 3 + 2, h})
+    parts, covered = [], 0
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        parts.append(p.bake_rows(0, pos, nrm, uv, idx, w, h, r0, r1))
+        covered += p.last_covered_texels
+    assert covered == total
+    for k in range(3):
+        assert (np.concatenate([q[k] for q in parts], axis=0) == whole[k]).all()
+    ref = ref_planet(cfg)
+    want = ref.bake_seeded(0, pos, nrm, uv, idx, w, h)
+    assert total == ref.last_covered_texels
+    check_bake(whole, want, ("ragged", size), frac=0.99 if w * h < 4096 else 0.998)
+
+
 def test_bake_empty_mesh_and_errors():
     p = make_planet(("sphere", "lakes", "default", False, False))
     a, s, h = p.bake(0, np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), np.zeros((3, 2), np.float32), np.zeros(0, np.uint32), 32, 32)

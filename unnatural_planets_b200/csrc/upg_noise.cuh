@@ -241,12 +241,13 @@ namespace upg
 	}
 
 	// Warp-cooperative form of the x stage (device only, UPG_CUBIC_COOP).  The colouring kernel evaluates ValueCubic at frequencies
-	// whose lattice cells are 70 - 450 world units wide while the 32 texels of a warp are neighbours ~1 unit apart: nearly every
-	// warp sits in ONE cell, so its 64 lattice values -- and therefore the four polynomial coefficients p, (a - b) - p, c - a, b that
-	// cubic_lerp() derives from each row of four of them -- are the same for all 32 lanes.  Lanes 0..15 compute one row each
-	// (4 hashes instead of 64 per lane) into a per-warp shared-memory block, every lane reads the rows back as broadcast LDS.128
-	// and evaluates ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit.  Warps that
-	// are not whole (a layer's early return) or straddle a cell boundary take the per-lane path below.
+	// whose lattice cells are 6 - 1000 world units wide while the 32 texels of a warp are an 8 x 4 tile of neighbours ~1 unit apart
+	// (upg_bake.cu: TileOrder): the lanes of a warp sit in one cell, or in two or three, so the 64 lattice values -- and therefore
+	// the four polynomial coefficients p, (a - b) - p, c - a, b that cubic_lerp() derives from each row of four of them -- are the
+	// same for all lanes of a cell.  Per distinct cell, lanes 0..15 compute one row each (4 hashes instead of 64 per lane) into a
+	// per-warp shared-memory block, and the lanes of that cell read the rows back as broadcast LDS.128 and evaluate
+	// ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit (225 instructions per
+	// round against 650 per lane; profiles/r01_zl_summary.md).  Warps that are not whole take the per-lane path below.
 #if !defined(UPG_CUBIC_COOP)
 #define UPG_CUBIC_COOP 2
 #endif
