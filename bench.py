@@ -55,6 +55,19 @@ def _k1_traffic():
 K1_TRAFFIC_BYTES_PER_NODE = _k1_traffic()
 
 
+def _k1_issue():
+    """issue-slot view of the same committed capture: the arithmetic is un-contracted (no FMA), so every flop of the reference's
+    expression costs one issue slot where the FMA peak counts two, and the hash lattice costs INT32 slots on top"""
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "k1_column_ncu.json")))
+        per_node = c["smsp__inst_executed.sum"] * 32.0 / c["grid_nodes"]  # issue slots x 32 lanes, whether or not every lane is active
+        return {"issue_active_frac": c["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0, "thread_instructions_per_grid_node": per_node,
+                "frac_ceiling_at_full_issue": FLOPS_PER_SAMPLE_LAND / (2.0 * per_node),
+                "source": "profiles/k1_column_ncu.json (ncu --set full of this kernel); frac_ceiling = flops_per_grid_node / (2 x instructions per node): what roofline.frac would be with every issue slot busy"}
+    except Exception:
+        return None
+
+
 def workload(args):
     return "BASELINE configs[2]: --shape sphere (elevation lakes, colouring default, default seed), 3 fields (land, water, navigation) x %d^3 grid, %d x %d land + water bake" % (args.grid, args.texture, args.texture)
 
@@ -557,7 +570,7 @@ def run_ours(args, rank, world, local_rank):
         "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if peak else None, "traffic": K1_TRAFFIC_BYTES_PER_NODE * n if K1_TRAFFIC_BYTES_PER_NODE else None, "peak_source": peak_source,
         "kernel_ms": fused_ms, "flops_per_grid_node": FLOPS_PER_SAMPLE_LAND, "samples_per_grid_node": len(FIELDS),
-        "single_field_kernel_ms": single_ms,
+        "single_field_kernel_ms": single_ms, "issue_slots": _k1_issue(),
         "hbm": {"achieved_gbs": 4.0 * len(FIELDS) * n / (fused_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "12 B written per grid node (3 fields); the kernel is FP32/INT32 issue bound"},
     }
     bake_achieved = FLOPS_PER_TEXEL_LAND * covered["land"] / (bake_land_ms * 1e-3) / 1e12
