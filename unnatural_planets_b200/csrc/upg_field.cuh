@@ -180,8 +180,12 @@ namespace upg
 		const uint32_t x = blockIdx.x * COLUMN_TILE_X + lane;
 		const uint32_t y = blockIdx.y * COLUMN_TILE_Y + warp;
 #else
-		const uint32_t x = blockIdx.x * COLUMN_TILE_X + (warp & 3u) * 8u + (lane & 7u);
-		const uint32_t y = blockIdx.y * COLUMN_TILE_Y + (warp >> 2) * 4u + (lane >> 3);
+#ifndef UPG_COLUMN_WARP_W
+#define UPG_COLUMN_WARP_W 8 // A/B: 16 = 16 x 2 tiles (64-byte store segments, more mask borders crossed)
+#endif
+		constexpr uint32_t WW = UPG_COLUMN_WARP_W, WH = 32u / WW, WPR = COLUMN_TILE_X / WW; // warp tile, warps per block row
+		const uint32_t x = blockIdx.x * COLUMN_TILE_X + (warp % WPR) * WW + (lane % WW);
+		const uint32_t y = blockIdx.y * COLUMN_TILE_Y + (warp / WPR) * WH + (lane / WW);
 #endif
 		if (x >= res || y >= res)
 			return;

@@ -171,7 +171,19 @@ namespace upg
 	}
 	UPG_HD float grad_coord(int32_t seed, int32_t xp, int32_t yp, int32_t zp, float xd, float yd, float zd) { return grad_dot(lattice_hash(seed, xp, yp, zp), xd, yd, zd); }
 
-	UPG_HD int32_t fast_floor(float f) { return f >= 0 ? (int32_t)f : (int32_t)f - 1; }
+	// The library's FastFloor / FastRound (note floor(-2.0) = -3 and the NaN case: the comparison is false, so the second branch).  On
+	// the device the select is a predicated add: convert, compare "less or unordered", decrement -- three instructions where the
+	// compiler's rendering of the ternary took five (5.5 % of the dense sampling kernel's instructions were these, profiles/r01_zl).
+	UPG_HD int32_t fast_floor(float f)
+	{
+#if defined(__CUDA_ARCH__)
+		int32_t i;
+		asm("{\n\t.reg .pred p;\n\tcvt.rzi.s32.f32 %0, %1;\n\tsetp.ltu.f32 p, %1, 0f00000000;\n\t@p add.s32 %0, %0, -1;\n\t}" : "=r"(i) : "f"(f));
+		return i;
+#else
+		return f >= 0 ? (int32_t)f : (int32_t)f - 1;
+#endif
+	}
 	UPG_HD int32_t fast_round(float f) { return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f); }
 	UPG_HD float nlerp(float a, float b, float t) { return a + t * (b - a); }
 	UPG_HD float interp_hermite(float t) { return t * t * (3 - 2 * t); }
