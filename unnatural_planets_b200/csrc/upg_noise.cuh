@@ -259,12 +259,14 @@ namespace upg
 	// same for all lanes of a cell.  Per distinct cell, lanes 0..15 compute one row each (4 hashes instead of 64 per lane) into a
 	// per-warp shared-memory block, and the lanes of that cell read the rows back as broadcast LDS.128 and evaluate
 	// ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit (225 instructions per
-	// round against 650 per lane; profiles/r01_zl_summary.md).  Warps that are not whole take the per-lane path below.
+	// round against 650 per lane; profiles/r01_zl_summary.md).  Warps that are not whole, and lanes still unserved after
+	// CUBIC_COOP_MAX_ROUNDS rounds, take the per-lane path below.
 #if !defined(UPG_CUBIC_COOP)
 #define UPG_CUBIC_COOP 2
 #endif
 #if defined(__CUDACC__) && UPG_CUBIC_COOP
 	constexpr int CUBIC_COOP_MAX_WARPS = 32; // 1-D blocks of up to 1024 threads
+	constexpr int CUBIC_COOP_MAX_ROUNDS = 8; // a round costs ~1/3 of the per-lane evaluation; bake warps need 1 - 6 (A/B 4 / 8 / unbounded in profiles/r01_zl_summary.md)
 	static __shared__ float4 upg_cubic_rows[CUBIC_COOP_MAX_WARPS][16];
 #endif
 
@@ -289,6 +291,7 @@ namespace upg
 			// texels are an 8 x 4 tile ~1 world unit apart (upg_bake.cu: TileOrder), so nearly always one round, two or three at the
 			// highest frequencies.  `todo` is warp-uniform.
 			uint32_t todo = full;
+			int rounds = 0;
 			do
 			{
 				const int leader = __ffs((int)todo) - 1;
@@ -327,8 +330,9 @@ namespace upg
 				}
 				__syncwarp(); // the rows are rewritten by the next round / octave
 				todo &= ~group;
-			} while (todo);
-			if (!todo)
+			} while (todo && ++rounds < CUBIC_COOP_MAX_ROUNDS);
+			// lanes still waiting after that many rounds (incoherent positions: upg_tiles on arbitrary points) go per lane below
+			if (!((todo >> lane) & 1u))
 				return result;
 		}
 #endif
