@@ -767,12 +767,24 @@ namespace upg
 		workers = workers > 6 ? 6 : workers < 1 ? 1 : workers;
 		if (workers > slices.size())
 			workers = (unsigned)slices.size();
+		// Staged uploads take turns (per process: the copy threads and the host -> device link are shared by every call).  Two bakes
+		// arriving together -- the generator's chunk tasks -- otherwise split the link, BOTH meshes arrive late, the colourings run back
+		// to back on the GPU after that and both sets of images come back at the end.  One after the other, the first call's colouring
+		// starts after half the time, the second upload hides behind it, and the first download hides behind the second colouring.
+		// UPG_UPLOAD_TURNS=0 switches it off (A/B in profiles/).
+		static std::mutex uploadTurn;
+		static const bool turns = !(std::getenv("UPG_UPLOAD_TURNS") && std::getenv("UPG_UPLOAD_TURNS")[0] == '0');
+		std::unique_lock<std::mutex> turn(uploadTurn, std::defer_lock);
+		if (turns)
+			turn.lock();
 		std::vector<std::thread> pool;
 		for (unsigned t = 1; t < workers; t++)
 			pool.emplace_back(work);
 		work();
 		for (auto &t : pool)
 			t.join();
+		if (turns)
+			turn.unlock();
 		if (failed.load())
 			return cuda_fail(cudaGetLastError(), "upload (staged)");
 		return UPG_OK;

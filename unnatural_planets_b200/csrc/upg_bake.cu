@@ -42,6 +42,11 @@ namespace upg
 			uint32_t triangles;
 			uint32_t width, height;
 			uint32_t bandBegin, bandEnd; // rows [bandBegin, bandEnd) are kept (row-tile sharding); the owner image is band sized
+			// index validation happens here, where the indices are read anyway: a serial host loop over the 8.7 M indices of a 1000^3 base
+			// mesh cost 6 ms per bake call.  0 = not checked (the caller did); else triangles with an index >= vertices are skipped and
+			// the largest offending index + 1 lands in *badIndex
+			uint32_t vertices = 0;
+			uint32_t *badIndex = nullptr;
 		};
 
 		// Vec2i * Real (meshAlgorithms.cpp:52-55): per component sint32(int * float)
@@ -124,7 +129,18 @@ namespace upg
 		{
 			const uint32_t tri = blockIdx.x * BAKE_BLOCK + threadIdx.x;
 			unsigned long long mine = 0;
-			if (tri < M.triangles)
+			bool valid = tri < M.triangles;
+			if (valid && M.vertices)
+			{
+				const uint32_t i0 = M.indices[tri * 3 + 0], i1 = M.indices[tri * 3 + 1], i2 = M.indices[tri * 3 + 2];
+				const uint32_t top = max(i0, max(i1, i2));
+				if (top >= M.vertices)
+				{
+					atomicMax(M.badIndex, top == 0xffffffffu ? top : top + 1);
+					valid = false;
+				}
+			}
+			if (valid)
 			{
 				scan_triangle(M, tri,
 					[&](int x, int y)
@@ -799,7 +815,8 @@ namespace upg
 
 		thread_local uint64_t t_lastCovered = 0;
 
-		int check_mesh(const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h)
+		// `indices` = also walk the index array on the host (upg_raster, small parity inputs); the bake validates them on the device
+		int check_mesh(const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, bool indices)
 		{
 			if (!uvs || !idx)
 				return fail(UPG_ERR_ARGUMENT, "generating texture requires uvs and indices");
@@ -807,7 +824,7 @@ namespace upg
 				return fail(UPG_ERR_ARGUMENT, "generating texture requires triangles mesh");
 			if (w == 0 || h == 0 || (uint64_t)w * h > 0x7fffffffull)
 				return fail(UPG_ERR_ARGUMENT, "bad texture resolution %u x %u", w, h);
-			for (uint32_t i = 0; i < nidx; i++)
+			for (uint32_t i = 0; indices && i < nidx; i++)
 				if (idx[i] >= nverts)
 					return fail(UPG_ERR_ARGUMENT, "index %u out of range (%u vertices)", idx[i], nverts);
 			return UPG_OK;
@@ -886,7 +903,7 @@ extern "C"
 	{
 		if (!owner || !weights)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
-		int rc = check_mesh(uvs, nverts, idx, nidx, w, h);
+		int rc = check_mesh(uvs, nverts, idx, nidx, w, h, true);
 		if (rc)
 			return rc;
 		cudaError_t e = cudaSetDevice(device);
@@ -1044,6 +1061,7 @@ extern "C"
 			uint32_t *list = mem.alloc<uint32_t>(texels);
 			uint32_t *dcount = mem.alloc<uint32_t>(1);
 			unsigned long long *dvisits = mem.alloc<unsigned long long>(2);
+			uint32_t *dbad = mem.alloc<uint32_t>(1);
 			float *imgAlbedo = mem.alloc<float>(texels * ach);
 			float *imgSpecial = mem.alloc<float>(texels * 2);
 			float *imgHeight = mem.alloc<float>(texels);
@@ -1054,6 +1072,8 @@ extern "C"
 				e = cudaMemsetAsync(owner, 0, sizeof(uint32_t) * texels, s);
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(dvisits, 0, sizeof(unsigned long long) * 2, s);
+			if (e == cudaSuccess)
+				e = cudaMemsetAsync(dbad, 0, sizeof(uint32_t), s);
 			// imageFill(NaN) (sources/textures.cpp:47-63): all-ones is a quiet NaN
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(imgAlbedo, 0xff, sizeof(float) * texels * ach, s);
@@ -1062,7 +1082,7 @@ extern "C"
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(imgHeight, 0xff, sizeof(float) * texels, s);
 
-			RasterMesh M{ duv, didx, nidx / 3, w, h, bandBegin, bandEnd };
+			RasterMesh M{ duv, didx, nidx / 3, w, h, bandBegin, bandEnd, nverts, dbad };
 			if (e == cudaSuccess && M.triangles)
 			{
 				raster_owner_kernel<<<blocks_for(M.triangles, BAKE_BLOCK), BAKE_BLOCK, 0, s>>>(M, owner, dvisits);
@@ -1087,10 +1107,19 @@ extern "C"
 					e = mem.err;
 				if (e == cudaSuccess)
 					e = cub::DeviceSelect::If(tmp, tmpBytes, ids, list, dcount, slots, pred, s);
+				uint32_t bad = 0;
 				if (e == cudaSuccess)
 					e = cudaMemcpyAsync(&covered, dcount, sizeof(covered), cudaMemcpyDeviceToHost, s);
 				if (e == cudaSuccess)
+					e = cudaMemcpyAsync(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost, s);
+				if (e == cudaSuccess)
 					e = stream_sync(s);
+				if (e == cudaSuccess && bad)
+				{
+					// nothing downstream may touch the mesh through these indices
+					rc = fail(UPG_ERR_ARGUMENT, "index %u out of range (%u vertices)", bad == 0xffffffffu ? bad : bad - 1, nverts);
+					covered = 0;
+				}
 				if (e == cudaSuccess && covered && row0 == bandBegin && row1 == bandEnd)
 					coveredRows = covered; // the band is the caller's rows (whole images): nothing to separate
 				else if (e == cudaSuccess && covered)
@@ -1272,7 +1301,7 @@ extern "C"
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !positions || !normals || !albedo)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
-		int rc = check_mesh(uvs, nverts, idx, nidx, w, h);
+		int rc = check_mesh(uvs, nverts, idx, nidx, w, h, false);
 		if (rc)
 			return rc;
 		cudaError_t e = cudaSetDevice(p->device);
