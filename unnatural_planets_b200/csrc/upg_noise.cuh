@@ -258,16 +258,18 @@ namespace upg
 	// the four polynomial coefficients p, (a - b) - p, c - a, b that cubic_lerp() derives from each row of four of them -- are the
 	// same for all lanes of a cell.  Per distinct cell, lanes 0..15 compute one row each (4 hashes instead of 64 per lane) into a
 	// per-warp shared-memory block, and the lanes of that cell read the rows back as broadcast LDS.128 and evaluate
-	// ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit (225 instructions per
-	// round against 650 per lane; profiles/r01_zl_summary.md).  Warps that are not whole, and lanes still unserved after
-	// CUBIC_COOP_MAX_ROUNDS rounds, take the per-lane path below.
+	// ((ttt * p + tt * q) + t * r) + b: the expression and operation order of cubic_lerp(), bit for bit (~50 instructions per
+	// distinct cell + ~200 once, against 650 per lane; profiles/r01_zl_summary.md).  Warps that are not whole, and lanes whose cell
+	// found none of the CUBIC_COOP_CELLS slots, take the per-lane path below.
 #if !defined(UPG_CUBIC_COOP)
-#define UPG_CUBIC_COOP 2
+#define UPG_CUBIC_COOP 1
 #endif
 #if defined(__CUDACC__) && UPG_CUBIC_COOP
-	constexpr int CUBIC_COOP_MAX_WARPS = 32; // 1-D blocks of up to 1024 threads
-	constexpr int CUBIC_COOP_MAX_ROUNDS = 8; // a round costs ~1/3 of the per-lane evaluation; bake warps need 1 - 6 (A/B 4 / 8 / unbounded in profiles/r01_zl_summary.md)
-	static __shared__ float4 upg_cubic_rows[CUBIC_COOP_MAX_WARPS][16];
+	// one block of 16 rows per distinct cell of the warp (CUBIC_COOP_CELLS of them: 2 KB per warp); warps beyond CUBIC_COOP_WARPS of a
+	// block go per lane.  The colouring kernel runs 12 warps per block (upg_bake.cu: COLOR_BLOCK).
+	constexpr int CUBIC_COOP_WARPS = 12;
+	constexpr int CUBIC_COOP_CELLS = 8; // the 8 x 4 texel tiles of a bake need 1 - 6 at the frequencies of the colouring noises
+	static __shared__ float4 upg_cubic_rows[CUBIC_COOP_WARPS][CUBIC_COOP_CELLS][16];
 #endif
 
 	UPG_HD float single_cubic(int32_t seed, float x, float y, float z)
@@ -280,59 +282,59 @@ namespace upg
 		const int32_t xi0 = isub(x1, PRIME_X), xi2 = iadd(x1, PRIME_X), xi3 = iadd(x1, ishl(PRIME_X, 1));
 		const int32_t yb = isub(y1, PRIME_Y), zb = isub(z1, PRIME_Z);
 #if defined(__CUDA_ARCH__) && UPG_CUBIC_COOP
-		if (__activemask() == 0xffffffffu)
+		if (__activemask() == 0xffffffffu && (threadIdx.x >> 5) < (uint32_t)CUBIC_COOP_WARPS)
 		{
 			const uint32_t full = 0xffffffffu;
 			const uint32_t lane = threadIdx.x & 31u;
-			float4 *rows = upg_cubic_rows[threadIdx.x >> 5];
-			const float tt = xs * xs, ttt = tt * xs;
-			float result = 0;
-			// one round per distinct lattice cell among the lanes (the primes are odd: equal products <=> equal cells); a warp's
-			// texels are an 8 x 4 tile ~1 world unit apart (upg_bake.cu: TileOrder), so nearly always one round, two or three at the
-			// highest frequencies.  `todo` is warp-uniform.
+			float4(*cells)[16] = upg_cubic_rows[threadIdx.x >> 5];
+			// STAGE: one round per distinct lattice cell among the lanes (the primes are odd: equal products <=> equal cells); `todo` and
+			// `cell` are warp-uniform.  Lanes 0..15 hash one row of the leader's cell each; the lanes of that cell note its slot.
 			uint32_t todo = full;
-			int rounds = 0;
+			int cell = 0, mySlot = -1;
 			do
 			{
 				const int leader = __ffs((int)todo) - 1;
 				const int32_t ux = __shfl_sync(full, x1, leader), uy = __shfl_sync(full, y1, leader), uz = __shfl_sync(full, z1, leader);
 				const bool mine = (x1 == ux) & (y1 == uy) & (z1 == uz);
 				const uint32_t group = __ballot_sync(full, mine);
-#if UPG_CUBIC_COOP == 1 // A/B: whole warps in one cell only, everything else per lane
-				if (group != full)
-					break;
-#endif
+				if (mine)
+					mySlot = cell;
 				if (lane < 16u)
 				{
 					const int32_t s = seed ^ iadd(isub(uy, PRIME_Y), imul((int32_t)(lane & 3u), PRIME_Y)) ^ iadd(isub(uz, PRIME_Z), imul((int32_t)(lane >> 2), PRIME_Z));
 					const float a = value_bits_from_hash(imul(s ^ isub(ux, PRIME_X), 0x27d4eb2d)), b = value_bits_from_hash(imul(s ^ ux, 0x27d4eb2d));
 					const float c = value_bits_from_hash(imul(s ^ iadd(ux, PRIME_X), 0x27d4eb2d)), d = value_bits_from_hash(imul(s ^ iadd(ux, ishl(PRIME_X, 1)), 0x27d4eb2d));
 					const float p = (d - c) - (a - b);
-					rows[lane] = make_float4(p, (a - b) - p, c - a, b);
+					cells[cell][lane] = make_float4(p, (a - b) - p, c - a, b);
 				}
-				__syncwarp();
-				if (mine)
-				{
-					float zr[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++)
-					{
-						float yr[4];
-#pragma unroll
-						for (int j = 0; j < 4; j++)
-						{
-							const float4 q = rows[k * 4 + j];
-							yr[j] = ttt * q.x + tt * q.y + xs * q.z + q.w;
-						}
-						zr[k] = cubic_lerp(yr[0], yr[1], yr[2], yr[3], ys);
-					}
-					result = (cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * VALUE_SCALE) * (1 / (1.5f * 1.5f * 1.5f));
-				}
-				__syncwarp(); // the rows are rewritten by the next round / octave
 				todo &= ~group;
-			} while (todo && ++rounds < CUBIC_COOP_MAX_ROUNDS);
-			// lanes still waiting after that many rounds (incoherent positions: upg_tiles on arbitrary points) go per lane below
-			if (!((todo >> lane) & 1u))
+			} while (todo && ++cell < CUBIC_COOP_CELLS);
+			__syncwarp();
+			// EVALUATE once: every served lane reads the 16 rows of its cell (lanes of one cell: one broadcast) -- cubic_lerp()'s
+			// ((ttt * p + tt * q) + t * r) + b per row, then the y and z stages as below
+			float result = 0;
+			if (mySlot >= 0)
+			{
+				const float4 *rows = cells[mySlot];
+				const float tt = xs * xs, ttt = tt * xs;
+				float zr[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					float yr[4];
+#pragma unroll
+					for (int j = 0; j < 4; j++)
+					{
+						const float4 q = rows[k * 4 + j];
+						yr[j] = ttt * q.x + tt * q.y + xs * q.z + q.w;
+					}
+					zr[k] = cubic_lerp(yr[0], yr[1], yr[2], yr[3], ys);
+				}
+				result = (cubic_lerp(zr[0], zr[1], zr[2], zr[3], zs) * VALUE_SCALE) * (1 / (1.5f * 1.5f * 1.5f));
+			}
+			__syncwarp(); // the rows are rewritten by the next octave
+			// lanes whose cell found no slot (incoherent positions: upg_tiles on arbitrary points) go per lane below
+			if (mySlot >= 0)
 				return result;
 		}
 #endif
