@@ -148,13 +148,15 @@ namespace upg
 			}
 		}
 
-		UPG_HD double max_chroma_for_lh(double l, double h)
+		// `sn` / `cs` hand sin / cos of the hue back to hsluv2rgb, whose lch2luv step needs the same two values (hsluv.c computes them twice)
+		UPG_HD double max_chroma_for_lh(double l, double h, double &sn, double &cs)
 		{
 			double minLen = DBL_MAX;
 			const double hrad = h * 0.01745329251994329577;
 			Bounds bounds[6];
 			get_bounds(l, bounds);
-			const double sn = sin(hrad), cs = cos(hrad);
+			sn = sin(hrad);
+			cs = cos(hrad);
 			for (int i = 0; i < 6; i++)
 			{
 				const double len = bounds[i].b / (sn - bounds[i].a * cs);
@@ -215,7 +217,10 @@ namespace upg
 			if (L > 99.9999999 || L < 0.00000001)
 				S = 0.0;
 			else
-				S = C / max_chroma_for_lh(L, H) * 100.0;
+			{
+				double sn, cs;
+				S = C / max_chroma_for_lh(L, H, sn, cs) * 100.0;
+			}
 			if (C < 0.00000001)
 				H = 0.0;
 			return D3{ H, S, L };
@@ -226,17 +231,31 @@ namespace upg
 			const double kappa = 903.29629629629629629630;
 			const double refU = 0.19783000664283680764, refV = 0.46831999493879100370;
 			// hsluv2lch
-			double c;
+			double c, sn = 0.0, cs = 1.0;
+			bool trig = false; // sn / cs hold sin / cos of h * pi / 180
 			if (l > 99.9999999 || l < 0.00000001)
 				c = 0.0;
 			else
-				c = max_chroma_for_lh(l, h) / 100.0 * s;
+			{
+				c = max_chroma_for_lh(l, h, sn, cs) / 100.0 * s;
+				trig = true;
+			}
 			if (s < 0.00000001)
+			{
 				h = 0.0;
+				sn = 0.0; // sin(0.0), cos(0.0): exact in every libm
+				cs = 1.0;
+				trig = true;
+			}
 			// lch2luv
-			const double hrad = h * 0.01745329251994329577;
-			const double u = cos(hrad) * c;
-			const double v = sin(hrad) * c;
+			if (!trig)
+			{
+				const double hrad = h * 0.01745329251994329577;
+				sn = sin(hrad);
+				cs = cos(hrad);
+			}
+			const double u = cs * c;
+			const double v = sn * c;
 			// luv2xyz
 			double X, Y, Z;
 			if (l <= 0.00000001)
