@@ -362,11 +362,28 @@ extern "C"
 			L.bitPitch = bits3[FD_WATER].pitch;
 			L.nearTol = NEAR_ZERO_TOLERANCE;
 		}
-		const int rc = launch_field(p, L, stream);
-		if (rc != UPG_OK)
-			return rc;
+		// the water launch also leaves the minimum / maximum of every row: the band sampler skips the rows whose neighbourhood is settled
+		float2 *rowMinMax = nullptr;
+		if (bits3 && cudaMallocAsync(&rowMinMax, sizeof(float2) * (uint64_t)(zb - za) * res, stream) != cudaSuccess)
+		{
+			cudaGetLastError();
+			rowMinMax = nullptr; // optional
+		}
+		// all-ones = NaN = "not settled": a row the water launch should ever leave unwritten is scanned node by node
+		if (rowMinMax && cudaMemsetAsync(rowMinMax, 0xff, sizeof(float2) * (uint64_t)(zb - za) * res, stream) != cudaSuccess)
+		{
+			cudaGetLastError();
+			cudaFreeAsync(rowMinMax, stream);
+			rowMinMax = nullptr;
+		}
+		L.rowMinMax = rowMinMax;
+		int rc = launch_field(p, L, stream);
 		// with bit fields the extraction reads the signs from them and values only where the elevation was evaluated: no fill stores
-		return band_sample(p, za, zb, water, land, navigation, evaluatedDevice, stream, bits3 ? &bits3[FD_LAND] : nullptr, bits3 ? &bits3[FD_NAVIGATION] : nullptr, bits3 == nullptr);
+		if (rc == UPG_OK)
+			rc = band_sample(p, za, zb, water, land, navigation, evaluatedDevice, stream, bits3 ? &bits3[FD_LAND] : nullptr, bits3 ? &bits3[FD_NAVIGATION] : nullptr, bits3 == nullptr, rowMinMax);
+		if (rowMinMax)
+			cudaFreeAsync(rowMinMax, stream);
+		return rc;
 	}
 
 	// zero-filled sign / near-zero bit fields (SignBits) of the fields in `mask` for `slices` z-slices: one stream-ordered allocation

@@ -38,6 +38,7 @@ namespace upg
 		struct BandLaunch
 		{
 			const float *water; // device, rows x res floats: the shape value of every node
+			const float2 *rowMinMax; // optional: (min, max) of every row of `water` (shape_rows_kernel); NaN when the row holds one
 			float *land; // may be null
 			float *navigation; // may be null
 			uint32_t rows; // zcount * res
@@ -131,6 +132,39 @@ namespace upg
 			{
 				const uint32_t x = xs * BAND_STEP + tid * BAND_NODES;
 				const uint32_t row = row0 + r;
+				// Whole rows first.  Every value the node-level test below looks at -- a node, its x neighbours, the same x in the rows y +- 1
+				// and z +- 1 -- lies in five rows; when the minimum over those rows is above the band (or the maximum below it) every node
+				// of this row is settled on that side with no neighbour of another class: exactly what the node-level test would find,
+				// for a handful of instructions per step instead of hundreds.  Block-uniform (every thread reads the same five pairs), so
+				// the barriers inside the skipped part are skipped by all.  Three quarters of the rows of a 1000^3 sphere go this way.
+				int rowSide = 0; // +1 / -1: settled row
+				if (L.rowMinMax && !L.fill)
+				{
+					const float2 m0 = L.rowMinMax[row];
+					const float2 mYm = y > 0 ? L.rowMinMax[row - 1] : m0, mYp = y + 1 < res ? L.rowMinMax[row + 1] : m0;
+					const float2 mZm = zl > 0 ? L.rowMinMax[row - res] : m0, mZp = zl + 1 < L.zcount ? L.rowMinMax[row + res] : m0;
+					const float mn = band_min3(band_min3(m0.x, mYm.x, mYp.x), mZm.x, mZp.x);
+					const float mx = band_max3(band_max3(m0.y, mYm.y, mYp.y), mZm.y, mZp.y);
+					rowSide = mn > above ? 1 : mx < below ? -1 : 0;
+				}
+				uint32_t total = 0;
+				if (rowSide != 0)
+				{
+					// the sign words of this step's nodes: all ones on the positive side (nodes beyond the row stay 0), the zero fill otherwise
+					const uint32_t wx = xs * (BAND_STEP / 32u) + tid;
+					if (rowSide > 0 && L.bitPitch && tid < BAND_STEP / 32u && wx * 32u < res)
+					{
+						const uint32_t bits = res - wx * 32u;
+						const uint32_t word = bits >= 32u ? 0xffffffffu : (1u << bits) - 1u;
+						const uint64_t at = (uint64_t)row * L.bitPitch + wx;
+						if (L.landSigns)
+							L.landSigns[at] = word;
+						if (L.navSigns)
+							L.navSigns[at] = word;
+					}
+				}
+				else
+				{
 				bool need[BAND_NODES] = { false, false, false, false };
 				uint32_t positive = 0; // bit k: node k is settled on the positive side
 				bool any = false;
@@ -248,7 +282,7 @@ namespace upg
 				if (lane == 0)
 					warpCount[warp] = mine;
 				__syncthreads();
-				uint32_t before = 0, total = 0;
+				uint32_t before = 0;
 #pragma unroll
 				for (uint32_t k = 0; k < BAND_WARPS; k++)
 				{
@@ -267,6 +301,7 @@ namespace upg
 						slot += __popc(votes[k]);
 					}
 				}
+				} // node-level scan of this step
 				// next scan position
 				if (++xs == xSteps)
 				{
@@ -357,7 +392,7 @@ namespace upg
 	}
 
 	// land / navigation over z-slices [za, zb) given the water field of the same slices; asynchronous on `stream`
-	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits, const SignBits *navigationBits, bool fill)
+	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits, const SignBits *navigationBits, bool fill, const float2 *rowMinMax)
 	{
 		const PlanetParams &P = planet->params;
 		const uint32_t res = (uint32_t)P.grid.res;
@@ -367,6 +402,7 @@ namespace upg
 		elevation_interval10(P.elevation, &lo, &hi);
 		BandLaunch L;
 		L.water = water;
+		L.rowMinMax = rowMinMax;
 		L.land = land;
 		L.navigation = navigation;
 		L.zcount = (uint32_t)(zb - za);

@@ -31,6 +31,9 @@ namespace upg
 		uint32_t *nearBits = nullptr;
 		uint32_t bitPitch = 0;
 		float nearTol = 0;
+		// row-wise water launches only: optional minimum / maximum of every grid row (x = min, y = max; NaN when the row holds one):
+		// the band sampler skips the rows whose whole neighbourhood lies on one side of the elevation band (upg_band.cu)
+		float2 *rowMinMax = nullptr;
 	};
 
 	// runtime field selection (uniform across the grid) over the compile-time shape / elevation pair
@@ -260,8 +263,14 @@ namespace upg
 		__shared__ float coord[SHAPE_MAX_RES];
 		const uint32_t res = (uint32_t)P.grid.res;
 		grad_table_init<FIELD_BLOCK>(); // the asteroid shape samples a noise
+		// per-row minimum / maximum (L.rowMinMax): every warp leaves its part of a row as order-preserving integer keys (one redux.sync
+		// each), the parts are combined once all rows of the block are done
+		__shared__ uint32_t partMin[SHAPE_ROWS][FIELD_BLOCK / 32], partMax[SHAPE_ROWS][FIELD_BLOCK / 32];
+		__shared__ uint32_t rowHasNan; // bit r: row r of the block holds a NaN
 		for (uint32_t i = threadIdx.x; i < res; i += FIELD_BLOCK)
 			coord[i] = grid_coord(P.grid, i);
+		if (threadIdx.x == 0)
+			rowHasNan = 0;
 		__syncthreads();
 		const uint32_t rows = (uint32_t)(L.count / res);
 		const uint32_t row0 = blockIdx.x * SHAPE_ROWS;
@@ -272,6 +281,8 @@ namespace upg
 			const uint32_t zl = row / res;
 			const float cy = coord[row - zl * res], cz = coord[L.z0 + zl];
 			float *out = L.out + (uint64_t)row * res;
+			float rowMin = __int_as_float(0x7f800000), rowMax = __int_as_float(0xff800000); // +inf / -inf
+			bool rowNan = false;
 			// every warp stays whole through the loop (x0 is warp uniform): its 32 samples are one word of the bit fields
 			for (uint32_t x0 = threadIdx.x & ~31u; x0 < res; x0 += FIELD_BLOCK)
 			{
@@ -282,6 +293,9 @@ namespace upg
 					v = shape_sdf<SHAPE>(P, v3(coord[x], cy, cz));
 					bad |= isnan_(v);
 					out[x] = v;
+					rowMin = fminf(rowMin, v);
+					rowMax = fmaxf(rowMax, v);
+					rowNan |= isnan_(v); // fminf / fmaxf drop NaNs: a row with a NaN sample must never be skipped
 				}
 				if (L.signBits)
 				{
@@ -296,6 +310,38 @@ namespace upg
 							L.nearBits[word] = near;
 					}
 				}
+			}
+			if (L.rowMinMax) // uniform
+			{
+				// float -> unsigned key of the same order, one redux.sync per bound
+				const uint32_t ua = __float_as_uint(rowMin), ub = __float_as_uint(rowMax);
+				const uint32_t ka = __reduce_min_sync(0xffffffffu, (ua & 0x80000000u) ? ~ua : (ua | 0x80000000u));
+				const uint32_t kb = __reduce_max_sync(0xffffffffu, (ub & 0x80000000u) ? ~ub : (ub | 0x80000000u));
+				const bool anyNan = __any_sync(0xffffffffu, rowNan);
+				if ((threadIdx.x & 31u) == 0)
+				{
+					partMin[row - row0][threadIdx.x >> 5] = ka;
+					partMax[row - row0][threadIdx.x >> 5] = kb;
+					if (anyNan)
+						atomicOr(&rowHasNan, 1u << (row - row0));
+				}
+			}
+		}
+		if (L.rowMinMax)
+		{
+			__syncthreads();
+			if (threadIdx.x < rowEnd - row0)
+			{
+				uint32_t ka = partMin[threadIdx.x][0], kb = partMax[threadIdx.x][0];
+				for (int w = 1; w < FIELD_BLOCK / 32; w++)
+				{
+					ka = min(ka, partMin[threadIdx.x][w]);
+					kb = max(kb, partMax[threadIdx.x][w]);
+				}
+				const float lo = __uint_as_float((ka & 0x80000000u) ? (ka & 0x7fffffffu) : ~ka), hi = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb);
+				const float nan = __int_as_float(0x7fc00000);
+				const bool hasNan = (rowHasNan >> threadIdx.x) & 1u;
+				L.rowMinMax[row0 + threadIdx.x] = hasNan ? make_float2(nan, nan) : make_float2(lo, hi);
 			}
 		}
 		if (bad)

@@ -96,7 +96,7 @@ namespace upg
 	bool band_sampling_applies(const Planet *planet);
 	// With `landBits` / `navigationBits` (zero-filled by the caller) the kernel also writes the sign / near-zero bits of both fields and,
 	// unless `fill`, stores sample VALUES only where it evaluated them (all that dmc_build reads).
-	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits = nullptr, const SignBits *navigationBits = nullptr, bool fill = true);
+	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits = nullptr, const SignBits *navigationBits = nullptr, bool fill = true, const float2 *rowMinMax = nullptr);
 
 	// cached pinned host blocks (upg_api.cu) and the staged upload of pageable host arrays built on them
 	cudaError_t pinned_block_acquire(size_t bytes, void **out, size_t *capacity);
