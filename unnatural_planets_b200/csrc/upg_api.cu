@@ -376,7 +376,7 @@ extern "C"
 			cudaFreeAsync(rowMinMax, stream);
 			rowMinMax = nullptr;
 		}
-		L.rowMinMax = rowMinMax;
+		L.rowMinMax = reinterpret_cast<float *>(rowMinMax);
 		int rc = launch_field(p, L, stream);
 		// with bit fields the extraction reads the signs from them and values only where the elevation was evaluated: no fill stores
 		if (rc == UPG_OK)

@@ -31,9 +31,9 @@ namespace upg
 		uint32_t *nearBits = nullptr;
 		uint32_t bitPitch = 0;
 		float nearTol = 0;
-		// row-wise water launches only: optional minimum / maximum of every grid row (x = min, y = max; NaN when the row holds one):
-		// the band sampler skips the rows whose whole neighbourhood lies on one side of the elevation band (upg_band.cu)
-		float2 *rowMinMax = nullptr;
+		// row-wise water launches only: optional minimum / maximum of every grid row (two floats per row: min, max; NaN when the row
+		// holds one): the band sampler skips the rows whose whole neighbourhood lies on one side of the elevation band (upg_band.cu)
+		float *rowMinMax = nullptr;
 	};
 
 	// runtime field selection (uniform across the grid) over the compile-time shape / elevation pair
@@ -341,7 +341,7 @@ namespace upg
 				const float lo = __uint_as_float((ka & 0x80000000u) ? (ka & 0x7fffffffu) : ~ka), hi = __uint_as_float((kb & 0x80000000u) ? (kb & 0x7fffffffu) : ~kb);
 				const float nan = __int_as_float(0x7fc00000);
 				const bool hasNan = (rowHasNan >> threadIdx.x) & 1u;
-				L.rowMinMax[row0 + threadIdx.x] = hasNan ? make_float2(nan, nan) : make_float2(lo, hi);
+				reinterpret_cast<float2 *>(L.rowMinMax)[row0 + threadIdx.x] = hasNan ? make_float2(nan, nan) : make_float2(lo, hi);
 			}
 		}
 		if (bad)
