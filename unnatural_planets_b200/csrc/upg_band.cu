@@ -92,16 +92,6 @@ namespace upg
 			}
 		}
 
-		// bit i of the low byte -> bit 4 i
-		__device__ __forceinline__ uint32_t band_spread4(uint32_t b)
-		{
-			b &= 0xffu;
-			b = (b | (b << 12)) & 0x000f000fu;
-			b = (b | (b << 6)) & 0x03030303u;
-			b = (b | (b << 3)) & 0x11111111u;
-			return b;
-		}
-
 		template<int ELEV>
 		__global__ void __launch_bounds__(BAND_BLOCK) band_sample_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ BandLaunch L)
 		{
