@@ -201,7 +201,8 @@ namespace upg
 #if UPG_COLUMN_TERRACES
 		PerlinFbmColumn<3> terraceColumn; // the three Perlin octaves behind the terrace mask
 #endif
-		bool bad = false;
+		// NaN bookkeeping of the stored samples: one NaN-propagating maximum per store (FMNMX.NAN) instead of compare + select + or
+		float nanAcc = 0.0f;
 		uint64_t idx = ((uint64_t)zBegin * res + y) * res + x;
 		const uint64_t slice = (uint64_t)res * res;
 		for (uint32_t zl = zBegin; zl < zEnd; zl++, idx += slice)
@@ -227,27 +228,27 @@ namespace upg
 				if (L.out)
 				{
 					L.out[idx] = land;
-					bad |= isnan_(land);
+					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(land));
 				}
 				if (L.outWater)
 				{
 					L.outWater[idx] = base;
-					bad |= isnan_(base);
+					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(base));
 				}
 				if (L.outNavigation)
 				{
 					L.outNavigation[idx] = nav;
-					bad |= isnan_(nav);
+					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(nav));
 				}
 			}
 			else
 			{
 				const float v = field == FD_ELEVATION_RAW ? elev : field == FD_NAVIGATION ? base - fmax_(elev / 10.0f, 0.0f) : base - elev / 10.0f;
-				bad |= isnan_(v);
+				asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(v));
 				L.out[idx] = v;
 			}
 		}
-		if (bad)
+		if (isnan_(nanAcc))
 			atomicOr(L.status, 1u);
 	}
 
