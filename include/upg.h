@@ -30,12 +30,12 @@
 extern "C" {
 #endif
 
-#define UPG_API_VERSION 2
+#define UPG_API_VERSION 3
 
 enum
 {
 	UPG_OK = 0,
-	UPG_ERR_ARGUMENT = 1, /* unknown mode name / id, null pointer, resolution <= 5 (marchingCubes.cpp:21-23) */
+	UPG_ERR_ARGUMENT = 1, /* unknown mode name / id, null pointer, resolution <= 5 (marchingCubes.cpp:21-23) or > UPG_MAX_GRID_RESOLUTION */
 	UPG_ERR_CUDA = 2, /* no device, launch or allocation failure */
 	UPG_ERR_INVALID_VALUE = 3, /* a NaN sample: "invalid land sdf value" (sources/modesConfiguration.cpp:255-256) */
 	UPG_ERR_EMPTY_MESH = 4 /* "generated empty base land mesh" (sources/meshGeneration.cpp:51-52) */
@@ -64,6 +64,26 @@ enum
 	UPG_SAMPLING_DENSE = 1
 };
 
+/*
+ * Arithmetic of the dense sampling kernel (K1, upg_field_samples* / upg_fields_samples_device).  The reference is built for baseline
+ * x86-64, which has no fused multiply-add (externals/cage/cmake/cage_build_configuration.cmake sets no -march).  EXACT evaluates
+ * every + - * / sqrt in the reference's order without contraction: those operations and all integer work are bit-identical to the
+ * CPU.  CONTRACT lets the compiler fuse a * b + c inside the noise interpolation, the gradient dot products and the shape
+ * expressions (fewer issue slots per sample); the integer lattice (hashes, cell indices: the products that feed a floor / round are
+ * rounded as before), the grid coordinates and the final shape - elevation / 10 stay exact.  Values then agree with EXACT within the
+ * tolerance BASELINE.json states (1e-4 relative on the SDF; measured in tests/test_gpu_field.py).  The mesh entry points, the bake
+ * and upg_field_points always run EXACT: they are the validator.
+ */
+enum
+{
+	UPG_ARITH_EXACT = 0,
+	UPG_ARITH_CONTRACT = 1
+};
+
+#define UPG_MAX_DEVICES 8
+/* largest grid resolution a planet accepts: the isosurface stage indexes cells with 32 bits, (res - 1)^3 < 2^32 */
+#define UPG_MAX_GRID_RESOLUTION 1626
+
 typedef struct upg_planet upg_planet;
 
 /*
@@ -83,8 +103,15 @@ typedef struct upg_planet_desc
 	uint64_t seed[2]; /* xoroshiro128** state (both non-zero, random.cpp:14-17) */
 	float box_size; /* meshing box side, reference constant 4000 (sources/meshGeneration.cpp:19) */
 	int32_t grid_resolution; /* samples per axis, reference constant 500 (110 in debug builds) (:20-28) */
-	int32_t device; /* CUDA device ordinal */
+	int32_t device; /* CUDA device ordinal (the planet's home device: single-device entry points run here) */
 	int32_t mesh_sampling; /* UPG_SAMPLING_*: how the mesh entry points (upg_field_meshes*) fill the grid; the meshes are identical */
+	int32_t arithmetic; /* UPG_ARITH_*: see above */
+	/* Multi-GPU inside ONE process (the generator is a single process with pool threads, sources/generator.cpp:432-439): with
+	 * device_count > 1 the entry points marked "multi-device" below split their work over devices[0 .. device_count) -- z-slabs for
+	 * sampling + extraction, texel-row tiles for baking -- from one host thread per device; results are bit-identical to one device.
+	 * devices[0] must equal `device`.  device_count 0 or 1 = `device` alone. */
+	int32_t device_count;
+	int32_t devices[UPG_MAX_DEVICES];
 } upg_planet_desc;
 
 /* fills the reference's defaults: shape "random" is NOT resolved here (pass an explicit id), elevation lakes,
@@ -107,6 +134,25 @@ int upg_shape_count(void);
  * kernel arguments) */
 int upg_planet_create(const upg_planet_desc *desc, upg_planet **out);
 void upg_planet_destroy(upg_planet *planet);
+
+/* The ASYNCHRONOUS device-pointer entry points (upg_field_samples_device, upg_fields_samples_device, upg_fields_samples_band_device)
+ * cannot report a NaN sample when they return; they raise a sticky flag on the planet instead.  This call synchronises `cuda_stream`,
+ * returns UPG_ERR_INVALID_VALUE if the flag was raised since the last query ("invalid land sdf value", sources/modesConfiguration.cpp:
+ * 255-256) and clears it.  Every synchronous entry point checks (and owns) its own flag: concurrent calls never see each other's. */
+int upg_planet_async_status(upg_planet *planet, void *cuda_stream);
+
+/*
+ * Scratch memory.  Per-call device arrays (sample fields, isosurface / clean-up work arrays, float images) come from ONE library-owned
+ * stream-ordered pool per device, mesh results and upload staging from a cache of pinned host blocks; both keep what a call
+ * releases so that the next planet of a batch finds it.  upg_reserve grows the pool of `device` to `device_bytes` and pre-creates
+ * `pinned_blocks` pinned host blocks of `pinned_block_bytes` each, so that the FIRST planet does not pay for the growth (the driver
+ * calls cost tens of milliseconds, more than a 500^3 planet); upg_trim gives everything cached back (device pool down to `keep_bytes`,
+ * all pinned blocks).  Neither touches the device's default memory pool.
+ */
+int upg_reserve(int device, uint64_t device_bytes, uint64_t pinned_block_bytes, int pinned_blocks);
+int upg_trim(int device, uint64_t keep_bytes);
+/* bytes the device pool holds from the driver / high-water mark of bytes in use / bytes of cached pinned host blocks */
+int upg_memory_stats(int device, uint64_t *device_reserved, uint64_t *device_used_high, uint64_t *pinned_cached);
 
 /* the 32-bit seeds in the order noiseSeed() handed them out; returns how many were drawn (for parity checks) */
 int upg_planet_seed_log(const upg_planet *planet, uint32_t *out, int capacity);

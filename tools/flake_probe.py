@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Runs the mesh entry points (band sampling, three concurrent extractions, K9 clean-up) on a few planets and prints a digest of every
+mesh: under compute-sanitizer --tool initcheck this shows reads of scratch memory nobody wrote; under two different UPG_POISON bytes the
+digests must agree.   python tools/flake_probe.py [--res 130] [--repeat 1]"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unnatural_planets_b200 import Planet  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--res", type=int, default=130)
+ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--planets", default="sphere:lakes,torus:craters,doubletorus:islands,mandelbulb:simple")
+a = ap.parse_args()
+digests = {}
+for it in range(a.repeat):
+    for spec in a.planets.split(","):
+        shape, elev = spec.split(":")
+        for sampling in ("band", "dense"):
+            p = Planet(shape=shape, elevation=elev, grid=a.res, mesh_sampling=sampling)
+            m = p.field_meshes_clean(("land", "water", "navigation"))
+            h = hashlib.sha1()
+            for f in ("land", "water", "navigation"):
+                for k in ("positions", "normals", "indices"):
+                    h.update(m[f][k].tobytes())
+            key = "%s:%s" % (spec, sampling)
+            d = h.hexdigest()[:16]
+            if key in digests and digests[key] != d:
+                print("MISMATCH", key, "iteration", it, digests[key], d)
+            digests[key] = d
+            p.close()
+print(json.dumps(digests, sort_keys=True))

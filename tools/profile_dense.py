@@ -12,8 +12,9 @@ from unnatural_planets_b200 import Planet  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--grid", type=int, default=1000)
 ap.add_argument("--repeat", type=int, default=2)
+ap.add_argument("--arithmetic", default="exact")
 a = ap.parse_args()
-p = Planet(shape="sphere", elevation="lakes", grid=a.grid)
+p = Planet(shape="sphere", elevation="lakes", grid=a.grid, arithmetic=a.arithmetic)
 bufs = [torch.empty(a.grid**3, dtype=torch.float32, device="cuda") for _ in range(3)]
 s = torch.cuda.current_stream()
 for _ in range(a.repeat):

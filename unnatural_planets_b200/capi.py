@@ -28,10 +28,14 @@ class PlanetDesc(C.Structure):
         ("grid_resolution", C.c_int32),
         ("device", C.c_int32),
         ("mesh_sampling", C.c_int32),
+        ("arithmetic", C.c_int32),
+        ("device_count", C.c_int32),
+        ("devices", C.c_int32 * 8),
     ]
 
 
 SAMPLING = {"band": 0, "dense": 1}
+ARITHMETIC = {"exact": 0, "contract": 1}
 
 
 class Mesh(C.Structure):
@@ -120,6 +124,10 @@ def load_library():
     L.upg_planet_destroy.argtypes = [vp]
     L.upg_planet_destroy.restype = None
     L.upg_planet_seed_log.argtypes = [vp, fp, i32]
+    L.upg_planet_async_status.argtypes = [vp, vp]
+    L.upg_reserve.argtypes = [i32, u64, u64, i32]
+    L.upg_trim.argtypes = [i32, u64]
+    L.upg_memory_stats.argtypes = [i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.upg_field_samples.argtypes = [vp, i32, i32, i32, fp]
     L.upg_field_samples_device.argtypes = [vp, i32, i32, i32, fp, vp]
     L.upg_fields_samples_device.argtypes = [vp, i32, i32, fp, fp, fp, vp]

@@ -60,7 +60,11 @@ namespace upg
 	bool field_launch_e##E##_p0(int, const PlanetParams &, const FieldLaunch &, void *); \
 	bool field_launch_e##E##_p1(int, const PlanetParams &, const FieldLaunch &, void *); \
 	bool field_launch_e##E##_p2(int, const PlanetParams &, const FieldLaunch &, void *); \
-	bool field_launch_e##E##_p3(int, const PlanetParams &, const FieldLaunch &, void *);
+	bool field_launch_e##E##_p3(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launchc_e##E##_p0(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launchc_e##E##_p1(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launchc_e##E##_p2(int, const PlanetParams &, const FieldLaunch &, void *); \
+	bool field_launchc_e##E##_p3(int, const PlanetParams &, const FieldLaunch &, void *);
 	UPG_DECL_LAUNCHERS(0)
 	UPG_DECL_LAUNCHERS(1)
 	UPG_DECL_LAUNCHERS(2)
@@ -71,6 +75,11 @@ namespace upg
 	static const FieldLauncher fieldLaunchers[EL_COUNT][4] = {
 		UPG_LIST_LAUNCHERS(0), UPG_LIST_LAUNCHERS(1), UPG_LIST_LAUNCHERS(2), UPG_LIST_LAUNCHERS(3), UPG_LIST_LAUNCHERS(4), UPG_LIST_LAUNCHERS(5),
 	};
+	// the same kernels compiled with FMA contraction (UPG_ARITH_CONTRACT): dense grid launches of the sampling entry points only
+#define UPG_LIST_LAUNCHERS_C(E) { field_launchc_e##E##_p0, field_launchc_e##E##_p1, field_launchc_e##E##_p2, field_launchc_e##E##_p3 }
+	static const FieldLauncher fieldLaunchersContract[EL_COUNT][4] = {
+		UPG_LIST_LAUNCHERS_C(0), UPG_LIST_LAUNCHERS_C(1), UPG_LIST_LAUNCHERS_C(2), UPG_LIST_LAUNCHERS_C(3), UPG_LIST_LAUNCHERS_C(4), UPG_LIST_LAUNCHERS_C(5),
+	};
 
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream)
 	{
@@ -78,10 +87,12 @@ namespace upg
 			return UPG_OK;
 		const PlanetParams &P = planet->params;
 		// the water field is the bare shape: its grid launches take the row-wise kernel that lives with the elevation-free instantiations
-		const int table = (L.field == FD_WATER && !L.positions) ? (int)EL_NONE : P.elevation;
+		const bool waterRows = L.field == FD_WATER && !L.positions;
+		const int table = waterRows ? (int)EL_NONE : P.elevation;
+		const bool contract = L.contract && planet->arithmetic == UPG_ARITH_CONTRACT && !waterRows && !L.positions;
 		bool done = false;
 		for (int part = 0; part < 4 && !done; part++)
-			done = fieldLaunchers[table][part](P.shape, P, L, (void *)stream);
+			done = (contract ? fieldLaunchersContract : fieldLaunchers)[table][part](P.shape, P, L, (void *)stream);
 		if (!done)
 			return fail(UPG_ERR_ARGUMENT, "no kernel for shape %d elevation %d", P.shape, P.elevation);
 		const cudaError_t e = cudaGetLastError();
@@ -90,17 +101,68 @@ namespace upg
 		return UPG_OK;
 	}
 
+	static thread_local uint32_t *t_statusWord = nullptr;
+
+	uint32_t *status_word(const Planet *planet)
+	{
+		return t_statusWord ? t_statusWord : planet->status;
+	}
+
+	int StatusSlot::open(Planet *p, cudaStream_t s)
+	{
+		planet = p;
+		// a free bit of the mask; more than STATUS_SLOTS concurrent calls on one planet wait for one to finish
+		while (index < 0)
+		{
+			uint64_t mask = p->statusSlots.load();
+			if (~mask == 0)
+			{
+				std::this_thread::yield();
+				continue;
+			}
+			const int bit = __builtin_ctzll(~mask);
+			if (p->statusSlots.compare_exchange_weak(mask, mask | (1ull << bit)))
+				index = bit;
+		}
+		const cudaError_t e = cudaMemsetAsync(p->status + 1 + index, 0, sizeof(uint32_t), s);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaMemsetAsync(status)");
+		adopt(p->status + 1 + index);
+		return UPG_OK;
+	}
+
+	void StatusSlot::adopt(uint32_t *word)
+	{
+		previous = t_statusWord;
+		t_statusWord = word;
+		installed = true;
+	}
+
+	uint32_t *StatusSlot::word() const
+	{
+		return index >= 0 ? planet->status + 1 + index : nullptr;
+	}
+
+	StatusSlot::~StatusSlot()
+	{
+		if (installed)
+			t_statusWord = previous;
+		if (index >= 0)
+			planet->statusSlots.fetch_and(~(1ull << index));
+	}
+
 	int check_status(Planet *planet, cudaStream_t stream, const char *what)
 	{
 		uint32_t st = 0;
-		cudaError_t e = cudaMemcpyAsync(&st, planet->status, sizeof(st), cudaMemcpyDeviceToHost, stream);
+		uint32_t *word = status_word(planet);
+		cudaError_t e = cudaMemcpyAsync(&st, word, sizeof(st), cudaMemcpyDeviceToHost, stream);
 		if (e == cudaSuccess)
 			e = stream_sync(stream);
 		if (e != cudaSuccess)
 			return cuda_fail(e, what);
 		if (st & 1u)
 		{
-			cudaMemsetAsync(planet->status, 0, sizeof(uint32_t), stream);
+			cudaMemsetAsync(word, 0, sizeof(uint32_t), stream);
 			stream_sync(stream);
 			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in %s", what);
 		}
@@ -182,14 +244,25 @@ extern "C"
 			return fail(UPG_ERR_ARGUMENT, "unknown elevation mode configuration (%d)", d->elevation);
 		if (d->coloring < 0 || d->coloring >= CL_COUNT)
 			return fail(UPG_ERR_ARGUMENT, "unknown coloring mode configuration (%d)", d->coloring);
-		if (d->grid_resolution <= 5 || d->grid_resolution > 2048)
-			return fail(UPG_ERR_ARGUMENT, "grid resolution %d outside (5, 2048]", d->grid_resolution);
+		// (5: marchingCubes.cpp:21-23; upper bound: the isosurface stage indexes cells with 32 bits, upg_dmc.cu)
+		if (d->grid_resolution <= 5 || d->grid_resolution > UPG_MAX_GRID_RESOLUTION)
+			return fail(UPG_ERR_ARGUMENT, "grid resolution %d outside (5, %d]", d->grid_resolution, UPG_MAX_GRID_RESOLUTION);
 		if (d->seed[0] == 0 || d->seed[1] == 0)
 			return fail(UPG_ERR_ARGUMENT, "seed words must be non-zero");
 		if (!(d->box_size > 0))
 			return fail(UPG_ERR_ARGUMENT, "box size must be positive");
 		if (d->mesh_sampling != UPG_SAMPLING_BAND && d->mesh_sampling != UPG_SAMPLING_DENSE)
 			return fail(UPG_ERR_ARGUMENT, "unknown mesh sampling %d", d->mesh_sampling);
+		if (d->arithmetic != UPG_ARITH_EXACT && d->arithmetic != UPG_ARITH_CONTRACT)
+			return fail(UPG_ERR_ARGUMENT, "unknown arithmetic mode %d", d->arithmetic);
+		if (d->device_count < 0 || d->device_count > UPG_MAX_DEVICES)
+			return fail(UPG_ERR_ARGUMENT, "device count %d outside [0, %d]", d->device_count, UPG_MAX_DEVICES);
+		if (d->device_count > 0 && d->devices[0] != d->device)
+			return fail(UPG_ERR_ARGUMENT, "devices[0] (%d) must be the planet's home device (%d)", d->devices[0], d->device);
+		for (int i = 0; i < d->device_count; i++)
+			for (int j = 0; j < i; j++)
+				if (d->devices[i] == d->devices[j])
+					return fail(UPG_ERR_ARGUMENT, "device %d listed twice", d->devices[i]);
 
 		Planet *p = new (std::nothrow) Planet();
 		if (!p)
@@ -204,6 +277,11 @@ extern "C"
 		p->boxSize = d->box_size;
 		p->device = d->device;
 		p->sampling = d->mesh_sampling;
+		p->arithmetic = d->arithmetic;
+		p->deviceCount = d->device_count > 1 ? d->device_count : 1;
+		p->devices[0] = d->device;
+		for (int i = 1; i < p->deviceCount; i++)
+			p->devices[i] = d->devices[i];
 		// UPG_MESH_SAMPLING=dense|band overrides the descriptor (A/B timing of the two ways to fill the grid)
 		if (const char *env = std::getenv("UPG_MESH_SAMPLING"))
 			p->sampling = std::strcmp(env, "dense") == 0 ? UPG_SAMPLING_DENSE : std::strcmp(env, "band") == 0 ? UPG_SAMPLING_BAND : p->sampling;
@@ -221,19 +299,15 @@ extern "C"
 		cudaError_t e = cudaSetDevice(p->device);
 		if (e == cudaSuccess)
 		{
-			// keep freed stream-ordered allocations cached in the pool: the per-call scratch (up to res^3 floats) is
-			// re-used by the next call instead of going back to the driver at every synchronisation
+			// the library's own stream-ordered pool of this device (upg_mem.h): created here so that a planet on an unusable device
+			// fails at creation, and never the device's default pool (other allocators of the process keep theirs as it is)
 			cudaMemPool_t pool = nullptr;
-			if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess)
-			{
-				uint64_t threshold = UINT64_MAX;
-				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
-			}
+			e = device_pool(p->device, &pool);
 		}
 		if (e == cudaSuccess)
-			e = cudaMalloc(&p->status, sizeof(uint32_t) * 4);
+			e = cudaMalloc(&p->status, sizeof(uint32_t) * (STATUS_SLOTS + 1));
 		if (e == cudaSuccess)
-			e = cudaMemset(p->status, 0, sizeof(uint32_t) * 4);
+			e = cudaMemset(p->status, 0, sizeof(uint32_t) * (STATUS_SLOTS + 1));
 		if (e == cudaSuccess)
 			e = cudaMalloc(&p->cellularTable, sizeof(float) * 1024);
 		if (e == cudaSuccess)
@@ -281,6 +355,30 @@ extern "C"
 		return UPG_OK;
 	}
 
+	int upg_planet_async_status(upg_planet *planet, void *cuda_stream)
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		uint32_t st = 0;
+		cudaStream_t s = (cudaStream_t)cuda_stream;
+		e = cudaMemcpyAsync(&st, p->status, sizeof(st), cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = stream_sync(s);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "upg_planet_async_status");
+		if (st & 1u)
+		{
+			cudaMemsetAsync(p->status, 0, sizeof(uint32_t), s);
+			stream_sync(s);
+			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in an asynchronous sampling call");
+		}
+		return UPG_OK;
+	}
+
 	int upg_planet_seed_log(const upg_planet *planet, uint32_t *out, int capacity)
 	{
 		const Planet *p = reinterpret_cast<const Planet *>(planet);
@@ -308,7 +406,8 @@ extern "C"
 		L.count = (uint64_t)(z1 - z0) * res * res;
 		L.z0 = (uint32_t)z0;
 		L.field = field;
-		L.status = p->status;
+		L.status = status_word(p);
+		L.contract = true;
 		return launch_field(p, L, (cudaStream_t)cuda_stream);
 	}
 
@@ -331,20 +430,21 @@ extern "C"
 		L.count = (uint64_t)(z1 - z0) * res * res;
 		L.z0 = (uint32_t)z0;
 		L.field = FD_ALL;
-		L.status = p->status;
+		L.status = status_word(p);
+		L.contract = true;
 		return launch_field(p, L, (cudaStream_t)cuda_stream);
 	}
 
 	// the samples an extraction needs of slices [za, zb): dense (one fused evaluation per node) or, with `band`, the water field
 	// densely followed by K1b (upg_band.cu), which needs `water` even when the caller does not ask for that field
-	static int sample_for_extraction(Planet *p, bool band, int za, int zb, float *land, float *water, float *navigation, unsigned long long *evaluatedDevice, cudaStream_t stream, const SignBits *bits3 = nullptr)
+	static int sample_for_extraction(Planet *p, bool band, int za, int zb, float *land, float *water, float *navigation, unsigned long long *evaluatedDevice, cudaStream_t stream, const SignBits *bits3 = nullptr, cudaEvent_t waterDone = nullptr)
 	{
 		const int res = p->params.grid.res;
 		FieldLaunch L;
 		L.positions = nullptr;
 		L.count = (uint64_t)(zb - za) * res * res;
 		L.z0 = (uint32_t)za;
-		L.status = p->status;
+		L.status = status_word(p);
 		if (!band || (!land && !navigation))
 		{
 			L.out = land;
@@ -364,7 +464,7 @@ extern "C"
 		}
 		// the water launch also leaves the minimum / maximum of every row: the band sampler skips the rows whose neighbourhood is settled
 		float2 *rowMinMax = nullptr;
-		if (bits3 && cudaMallocAsync(&rowMinMax, sizeof(float2) * (uint64_t)(zb - za) * res, stream) != cudaSuccess)
+		if (bits3 && device_alloc(&rowMinMax, sizeof(float2) * (uint64_t)(zb - za) * res, stream) != cudaSuccess)
 		{
 			cudaGetLastError();
 			rowMinMax = nullptr; // optional
@@ -378,6 +478,9 @@ extern "C"
 		}
 		L.rowMinMax = reinterpret_cast<float *>(rowMinMax);
 		int rc = launch_field(p, L, stream);
+		// the water field (and its bit fields) is complete here: an extraction of it may start beside the band kernel, which only reads it
+		if (rc == UPG_OK && waterDone && cudaEventRecord(waterDone, stream) != cudaSuccess)
+			rc = cuda_fail(cudaGetLastError(), "cudaEventRecord(water)");
 		// with bit fields the extraction reads the signs from them and values only where the elevation was evaluated: no fill stores
 		if (rc == UPG_OK)
 			rc = band_sample(p, za, zb, water, land, navigation, evaluatedDevice, stream, bits3 ? &bits3[FD_LAND] : nullptr, bits3 ? &bits3[FD_NAVIGATION] : nullptr, bits3 == nullptr, rowMinMax);
@@ -397,11 +500,11 @@ extern "C"
 			fields += (mask >> f) & 1u;
 		if (!fields || !words)
 			return UPG_OK;
-		cudaError_t e = cudaMallocAsync(block, sizeof(uint32_t) * words * 2 * fields, stream);
+		cudaError_t e = device_alloc(block, sizeof(uint32_t) * words * 2 * fields, stream);
 		if (e == cudaSuccess)
 			e = cudaMemsetAsync(*block, 0, sizeof(uint32_t) * words * 2 * fields, stream);
 		if (e != cudaSuccess)
-			return cuda_fail(e, "cudaMallocAsync(sign bits)");
+			return cuda_fail(e, "device_alloc(sign bits)");
 		uint32_t *at = *block;
 		for (int f = 0; f < 3; f++)
 			if (mask & (1u << f))
@@ -427,9 +530,9 @@ extern "C"
 			if (rc != UPG_OK)
 				return rc;
 			float *shape = nullptr;
-			const cudaError_t e = cudaMallocAsync(&shape, sizeof(float) * count, stream);
+			const cudaError_t e = device_alloc(&shape, sizeof(float) * count, stream);
 			if (e != cudaSuccess)
-				return cuda_fail(e, "cudaMallocAsync(shape field)");
+				return cuda_fail(e, "device_alloc(shape field)");
 			rc = sample_for_extraction(p, true, za, zb, field == FD_LAND ? dens : nullptr, shape, field == FD_NAVIGATION ? dens : nullptr, nullptr, stream, bits3);
 			cudaFreeAsync(shape, stream);
 			*bits = bits3[field];
@@ -441,7 +544,7 @@ extern "C"
 		L.count = count;
 		L.z0 = (uint32_t)za;
 		L.field = field;
-		L.status = p->status;
+		L.status = status_word(p);
 		return launch_field(p, L, stream);
 	}
 
@@ -463,21 +566,21 @@ extern "C"
 		unsigned long long *counter = nullptr;
 		if (band && !device_water && count)
 		{
-			e = cudaMallocAsync(&scratch, sizeof(float) * count, stream);
+			e = device_alloc(&scratch, sizeof(float) * count, stream);
 			if (e != cudaSuccess)
-				return cuda_fail(e, "cudaMallocAsync(shape field)");
+				return cuda_fail(e, "device_alloc(shape field)");
 		}
 		if (evaluated_nodes)
 		{
 			*evaluated_nodes = band ? 0 : count;
-			e = cudaMallocAsync(&counter, sizeof(unsigned long long), stream);
+			e = device_alloc(&counter, sizeof(unsigned long long), stream);
 			if (e == cudaSuccess)
 				e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream);
 			if (e != cudaSuccess)
 			{
 				if (scratch)
 					cudaFreeAsync(scratch, stream);
-				return cuda_fail(e, "cudaMallocAsync(counter)");
+				return cuda_fail(e, "device_alloc(counter)");
 			}
 		}
 		int rc = count ? sample_for_extraction(p, band, z0, z1, device_land, device_water ? device_water : scratch, device_navigation, counter, stream) : UPG_OK;
@@ -517,11 +620,18 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		float *buf[2] = { nullptr, nullptr };
 		cudaEvent_t sampled[2] = { nullptr, nullptr }, drained[2] = { nullptr, nullptr };
 		for (int i = 0; i < 2 && e == cudaSuccess; i++)
 		{
-			e = cudaMallocAsync(&buf[i], sizeof(float) * sliceElems * slabSlices, cs.compute);
+			e = device_alloc(&buf[i], sizeof(float) * sliceElems * slabSlices, cs.compute);
 			if (e == cudaSuccess)
 				e = cudaEventCreateWithFlags(&sampled[i], cudaEventDisableTiming);
 			if (e == cudaSuccess)
@@ -542,7 +652,8 @@ extern "C"
 			L.count = (uint64_t)(ze - z) * sliceElems;
 			L.z0 = (uint32_t)z;
 			L.field = field;
-			L.status = p->status;
+			L.status = status_word(p);
+			L.contract = true;
 			rc = launch_field(p, L, cs.compute);
 			if (rc)
 				break;
@@ -591,10 +702,17 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		float *dpos = nullptr, *dout = nullptr;
-		e = cudaMallocAsync(&dpos, sizeof(float) * 3 * n, cs.compute);
+		e = device_alloc(&dpos, sizeof(float) * 3 * n, cs.compute);
 		if (e == cudaSuccess)
-			e = cudaMallocAsync(&dout, sizeof(float) * n, cs.compute);
+			e = device_alloc(&dout, sizeof(float) * n, cs.compute);
 		if (e == cudaSuccess)
 			e = cudaMemcpyAsync(dpos, host_positions, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, cs.compute);
 		if (e == cudaSuccess)
@@ -605,7 +723,7 @@ extern "C"
 			L.count = n;
 			L.z0 = 0;
 			L.field = field;
-			L.status = p->status;
+			L.status = status_word(p);
 			rc = launch_field(p, L, cs.compute);
 		}
 		if (e == cudaSuccess && rc == UPG_OK)
@@ -665,7 +783,7 @@ namespace upg
 				std::lock_guard<std::mutex> lock(g_pinnedMutex);
 				int best = -1;
 				for (int i = 0; i < g_pinnedCount; i++)
-					if (g_pinnedFree[i].bytes >= bytes && g_pinnedFree[i].bytes <= bucket * 2 && (best < 0 || g_pinnedFree[i].bytes < g_pinnedFree[best].bytes))
+					if (g_pinnedFree[i].bytes >= bytes && g_pinnedFree[i].bytes <= bucket * 8 && (best < 0 || g_pinnedFree[i].bytes < g_pinnedFree[best].bytes))
 						best = i;
 				if (best >= 0)
 				{
@@ -697,6 +815,32 @@ namespace upg
 	}
 
 	cudaError_t pinned_block_acquire(size_t bytes, void **out, size_t *capacity) { return pinned_acquire(bytes, out, capacity); }
+	static cudaError_t pinned_reserve(size_t bytes, int count)
+	{
+		const size_t bucket = pinned_bucket(bytes);
+		for (int i = 0; i < count; i++)
+		{
+			void *ptr = nullptr;
+			const cudaError_t e = cudaMallocHost(&ptr, bucket);
+			if (e != cudaSuccess)
+				return e;
+			pinned_release(ptr, bucket);
+		}
+		return cudaSuccess;
+	}
+	static void pinned_trim()
+	{
+		std::lock_guard<std::mutex> lock(g_pinnedMutex);
+		for (int i = 0; i < g_pinnedCount; i++)
+			cudaFreeHost(g_pinnedFree[i].ptr);
+		g_pinnedCount = 0;
+		g_pinnedBytes = 0;
+	}
+	static size_t pinned_cached()
+	{
+		std::lock_guard<std::mutex> lock(g_pinnedMutex);
+		return g_pinnedBytes;
+	}
 	void pinned_block_release(void *ptr, size_t capacity) { pinned_release(ptr, capacity); }
 
 	// Pageable host memory -> device.  cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread (~11 GB/s
@@ -945,13 +1089,20 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		const bool trace = trace_enabled();
 		const double t0 = trace ? now_ms() : 0;
 		double t1 = 0, t2 = 0;
 		float *dens = nullptr;
-		e = cudaMallocAsync(&dens, sizeof(float) * (uint64_t)res * res * res, cs.compute);
+		e = device_alloc(&dens, sizeof(float) * (uint64_t)res * res * res, cs.compute);
 		if (e != cudaSuccess)
-			rc = cuda_fail(e, "cudaMallocAsync(field)");
+			rc = cuda_fail(e, "device_alloc(field)");
 		SignBits bits;
 		uint32_t *bitBlock = nullptr;
 		if (rc == UPG_OK)
@@ -1043,24 +1194,31 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		const bool trace = trace_enabled();
 		const double t0 = trace ? now_ms() : 0;
 		float *dens[3] = { nullptr, nullptr, nullptr };
 		for (int f = 0; f < 3 && rc == UPG_OK; f++)
 			if (field_mask & (1u << f))
 			{
-				e = cudaMallocAsync(&dens[f], sizeof(float) * count, cs.compute);
+				e = device_alloc(&dens[f], sizeof(float) * count, cs.compute);
 				if (e != cudaSuccess)
-					rc = cuda_fail(e, "cudaMallocAsync(field)");
+					rc = cuda_fail(e, "device_alloc(field)");
 			}
 		// band sampling reads the shape from the water field: a scratch copy when the caller does not want that mesh
 		const bool band = band_sampling_applies(p) && (dens[FD_LAND] || dens[FD_NAVIGATION]);
 		float *shapeScratch = nullptr;
 		if (rc == UPG_OK && band && !dens[FD_WATER])
 		{
-			e = cudaMallocAsync(&shapeScratch, sizeof(float) * count, cs.compute);
+			e = device_alloc(&shapeScratch, sizeof(float) * count, cs.compute);
 			if (e != cudaSuccess)
-				rc = cuda_fail(e, "cudaMallocAsync(shape field)");
+				rc = cuda_fail(e, "device_alloc(shape field)");
 		}
 		// shape and elevation are evaluated ONCE per sample for all requested fields (and the elevation only where the isosurface
 		// can see it, UPG_SAMPLING_BAND)
@@ -1068,8 +1226,18 @@ extern "C"
 		uint32_t *bitBlock = nullptr;
 		if (rc == UPG_OK && band)
 			rc = alloc_sign_bits(res, zb - za, field_mask, cs.compute, bits3, &bitBlock);
+		// UPG_EARLY_WATER=1 (experimental): the water extraction starts as soon as the water launch is done,
+		// beside the band kernel, and the workers are released without the host synchronisation of check_status below
+		static const bool earlyWater = std::getenv("UPG_EARLY_WATER") && std::getenv("UPG_EARLY_WATER")[0] == '1';
+		cudaEvent_t waterDone = nullptr;
+		if (rc == UPG_OK && earlyWater && band && dens[FD_WATER])
+		{
+			e = cudaEventCreateWithFlags(&waterDone, cudaEventDisableTiming);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "cudaEventCreate");
+		}
 		if (rc == UPG_OK)
-			rc = sample_for_extraction(p, band, za, zb, dens[FD_LAND], dens[FD_WATER] ? dens[FD_WATER] : shapeScratch, dens[FD_NAVIGATION], nullptr, cs.compute, band ? bits3 : nullptr);
+			rc = sample_for_extraction(p, band, za, zb, dens[FD_LAND], dens[FD_WATER] ? dens[FD_WATER] : shapeScratch, dens[FD_NAVIGATION], nullptr, cs.compute, band ? bits3 : nullptr, waterDone);
 		if (shapeScratch)
 			cudaFreeAsync(shapeScratch, cs.compute);
 		cudaEvent_t sampled = nullptr;
@@ -1081,7 +1249,7 @@ extern "C"
 			if (e != cudaSuccess)
 				rc = cuda_fail(e, "cudaEventRecord");
 		}
-		if (rc == UPG_OK)
+		if (rc == UPG_OK && !earlyWater)
 			rc = check_status(p, cs.compute, "upg_field_meshes");
 		const double t1 = trace ? now_ms() : 0;
 		// the three extractions are independent: one host thread and one stream pair each, like the generator's three tasks
@@ -1099,6 +1267,8 @@ extern "C"
 					[&, f]()
 					{
 						int r = UPG_OK;
+						StatusSlot workerSlot;
+						workerSlot.adopt(slot.word()); // the workers belong to this call
 						cudaError_t ee = cudaSetDevice(p->device);
 						CallStreams ws;
 						if (ee != cudaSuccess)
@@ -1107,7 +1277,7 @@ extern "C"
 							r = ws.open();
 						if (r == UPG_OK)
 						{
-							ee = cudaStreamWaitEvent(ws.compute, sampled, 0);
+							ee = cudaStreamWaitEvent(ws.compute, (f == FD_WATER && waterDone) ? waterDone : sampled, 0);
 							if (ee != cudaSuccess)
 								r = cuda_fail(ee, "cudaStreamWaitEvent");
 						}
@@ -1167,7 +1337,11 @@ extern "C"
 			for (int f = 0; f < 3 && rc == UPG_OK; f++)
 				if (rcs[f] != UPG_OK)
 					rc = fail(rcs[f], "%s", errs[f].c_str());
+			if (rc == UPG_OK && earlyWater)
+				rc = check_status(p, cs.compute, "upg_field_meshes");
 		}
+		if (waterDone)
+			cudaEventDestroy(waterDone);
 		if (trace)
 			std::fprintf(stderr, "[upg] field_meshes(mask %#x) res %d: %s sampling %.2f ms, extraction + download %.2f ms\n", field_mask, res, band ? "band" : "dense fused", t1 - t0, now_ms() - t1);
 		if (sampled)
@@ -1261,11 +1435,11 @@ extern "C"
 		cudaStream_t s = cs.compute;
 		float *dp = nullptr, *dn = nullptr;
 		uint32_t *di = nullptr;
-		e = cudaMallocAsync((void **)&dp, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
+		e = device_alloc(&dp, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
 		if (e == cudaSuccess)
-			e = cudaMallocAsync((void **)&dn, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
+			e = device_alloc(&dn, sizeof(float) * 3 * (vertex_count ? vertex_count : 1), s);
 		if (e == cudaSuccess)
-			e = cudaMallocAsync((void **)&di, sizeof(uint32_t) * (index_count ? index_count : 1), s);
+			e = device_alloc(&di, sizeof(uint32_t) * (index_count ? index_count : 1), s);
 		if (e == cudaSuccess && vertex_count)
 			e = cudaMemcpyAsync(dp, positions, sizeof(float) * 3 * vertex_count, cudaMemcpyHostToDevice, s);
 		if (e == cudaSuccess && vertex_count)
@@ -1329,11 +1503,18 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		float *dens = nullptr;
 		const uint64_t count = (uint64_t)(b - a) * res * res;
-		e = cudaMallocAsync(&dens, sizeof(float) * count, cs.compute);
+		e = device_alloc(&dens, sizeof(float) * count, cs.compute);
 		if (e != cudaSuccess)
-			rc = cuda_fail(e, "cudaMallocAsync(slab)");
+			rc = cuda_fail(e, "device_alloc(slab)");
 		SignBits bits;
 		uint32_t *bitBlock = nullptr;
 		if (rc == UPG_OK)
@@ -1371,7 +1552,7 @@ extern "C"
 			return rc;
 		const uint64_t n = (uint64_t)rx * ry * rz;
 		float *dens = nullptr;
-		e = cudaMallocAsync(&dens, sizeof(float) * n, cs.compute);
+		e = device_alloc(&dens, sizeof(float) * n, cs.compute);
 		if (e == cudaSuccess)
 			e = cudaMemcpyAsync(dens, host_samples, sizeof(float) * n, cudaMemcpyHostToDevice, cs.compute);
 		if (e != cudaSuccess)
@@ -1408,6 +1589,48 @@ extern "C"
 		if (rc == UPG_OK && e != cudaSuccess)
 			rc = cuda_fail(e, "upg_upload");
 		return rc;
+	}
+
+	int upg_reserve(int device, uint64_t device_bytes, uint64_t pinned_block_bytes, int pinned_blocks)
+	{
+		if (pinned_blocks < 0 || pinned_blocks > 32)
+			return fail(UPG_ERR_ARGUMENT, "pinned block count %d outside [0, 32]", pinned_blocks);
+		cudaError_t e = cudaSetDevice(device);
+		if (e == cudaSuccess && device_bytes)
+			e = device_pool_reserve(device, device_bytes);
+		if (e == cudaSuccess && pinned_blocks && pinned_block_bytes)
+			e = pinned_reserve((size_t)pinned_block_bytes, pinned_blocks);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "upg_reserve");
+		return UPG_OK;
+	}
+
+	int upg_trim(int device, uint64_t keep_bytes)
+	{
+		cudaError_t e = cudaSetDevice(device);
+		if (e == cudaSuccess)
+			e = cudaDeviceSynchronize(); // stream-ordered frees of finished calls become visible to the trim
+		if (e == cudaSuccess)
+			e = device_pool_trim(device, keep_bytes);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "upg_trim");
+		pinned_trim();
+		return UPG_OK;
+	}
+
+	int upg_memory_stats(int device, uint64_t *device_reserved, uint64_t *device_used_high, uint64_t *pinned_cached_bytes)
+	{
+		uint64_t r = 0, u = 0;
+		const cudaError_t e = device_pool_stats(device, &r, &u);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "upg_memory_stats");
+		if (device_reserved)
+			*device_reserved = r;
+		if (device_used_high)
+			*device_used_high = u;
+		if (pinned_cached_bytes)
+			*pinned_cached_bytes = pinned_cached();
+		return UPG_OK;
 	}
 
 	void upg_mesh_free(upg_mesh *mesh)

@@ -749,7 +749,7 @@ namespace upg
 						err = cudaErrorMemoryAllocation;
 					return nullptr;
 				}
-				err = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), s);
+				err = device_alloc(&p, (n ? n : 1) * sizeof(T), s);
 				if (err == cudaSuccess)
 					ptrs[count++] = p;
 				return (T *)p;
@@ -773,7 +773,7 @@ namespace upg
 			L.count = (uint64_t)9 * n;
 			L.z0 = 0;
 			L.field = FD_ELEVATION;
-			L.status = p->status;
+			L.status = status_word(p);
 			int rc = launch_field(p, L, s);
 			if (rc)
 				return rc;
@@ -793,7 +793,7 @@ namespace upg
 			A.cellular = p->cellularTable;
 			A.n = n;
 			A.purpose = purpose;
-			A.status = p->status;
+			A.status = status_word(p);
 			const unsigned blocks = blocks_for(n, COLOR_BLOCK);
 			switch (p->params.coloring)
 			{
@@ -859,6 +859,13 @@ extern "C"
 		int rc = cs.open();
 		if (rc)
 			return rc;
+		StatusSlot slot; // this call's own NaN flag
+		rc = slot.open(p, cs.compute);
+		if (rc)
+		{
+			cs.close();
+			return rc;
+		}
 		{
 			Scratch mem(cs.compute);
 			const uint32_t cnt = (uint32_t)n;
@@ -1043,7 +1050,10 @@ extern "C"
 		t_lastCovered = 0;
 		if (row0 == row1)
 			return UPG_OK;
-		int rc = UPG_OK;
+		StatusSlot slot; // this call's own NaN flag
+		int rc = slot.open(p, s);
+		if (rc)
+			return rc;
 		const bool trace = trace_enabled();
 		double tr[6] = { trace ? now_ms() : 0, 0, 0, 0, 0, 0 };
 		{
@@ -1323,7 +1333,7 @@ extern "C"
 			void *staging = nullptr;
 			size_t stagingCapacity = 0;
 			if (e != cudaSuccess)
-				rc = cuda_fail(e, "cudaMallocAsync(mesh)");
+				rc = cuda_fail(e, "device_alloc(mesh)");
 			else
 			{
 				// the rasteriser needs uvs + indices first; positions / normals follow while it runs

@@ -405,7 +405,7 @@ namespace upg
 		// fifteen times the near-zero threshold 1e-3
 		L.margin = 0.03125f;
 		L.vector = res % 4 == 0 && ((uintptr_t)water & 15) == 0 && ((uintptr_t)land & 15) == 0 && ((uintptr_t)navigation & 15) == 0;
-		L.status = planet->status;
+		L.status = status_word(planet);
 		L.evaluated = evaluated;
 		L.fill = fill ? 1u : 0u;
 		L.landSigns = land && landBits ? landBits->signs : nullptr;

@@ -23,8 +23,29 @@
 #define UPG_D inline
 #endif
 
+// UPG_CONTRACT: the translation unit is compiled with -fmad=true (the tolerance build of the dense K1 kernels, UPG_ARITH_CONTRACT of
+// include/upg.h).  The kernels carry the build in their type so that the two builds of one template never share a symbol.
+#if defined(UPG_CONTRACT)
+#define UPG_ARITH_BUILD 1
+#else
+#define UPG_ARITH_BUILD 0
+#endif
+
 namespace upg
 {
+	// Single IEEE operations that are NEVER fused with a neighbour, whatever the build: the grid coordinates and everything that feeds
+	// a lattice index (frequency / lacunarity scaling, the simplex rotation) go through these, so that the integer lattice of the
+	// contracted build is the exact build's bit for bit.  In the exact build (and on the host) they are the plain operators.
+#if defined(__CUDA_ARCH__)
+	UPG_HD float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+	UPG_HD float add_rn(float a, float b) { return __fadd_rn(a, b); }
+	UPG_HD float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+#else
+	UPG_HD float mul_rn(float a, float b) { return a * b; }
+	UPG_HD float add_rn(float a, float b) { return a + b; }
+	UPG_HD float sub_rn(float a, float b) { return a - b; }
+#endif
+
 	// ---- cage scalar semantics (externals/cage/sources/include/cage-core/math.h:1021-1059, 798-809, 1173-1177) ----
 	// min/max are the ternaries the reference uses (NaN-order sensitive), NOT fminf/fmaxf.
 	UPG_HD float fmin_(float a, float b) { return a < b ? a : b; }

@@ -765,7 +765,7 @@ namespace upg
 		cudaError_t dalloc(T **p, uint64_t count, cudaStream_t s)
 		{
 			*p = nullptr;
-			return cudaMallocAsync((void **)p, sizeof(T) * (count ? count : 1), s);
+			return device_alloc(p, sizeof(T) * (count ? count : 1), s);
 		}
 
 		cudaError_t exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t s)
@@ -775,7 +775,7 @@ namespace upg
 			if (e != cudaSuccess)
 				return e;
 			void *tmp = nullptr;
-			e = cudaMallocAsync(&tmp, bytes ? bytes : 1, s);
+			e = device_alloc(&tmp, bytes ? bytes : 1, s);
 			if (e != cudaSuccess)
 				return e;
 			e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, s);

@@ -25,6 +25,7 @@ namespace upg
 		uint32_t z0; // first z-slice (grid mode)
 		int32_t field; // Field
 		uint32_t *status; // device status word
+		bool contract = false; // dense sampling entry points only: the planet's UPG_ARITH_CONTRACT build may serve this launch
 		// row-wise water launches only (shape_rows_kernel): optional sign / near-zero bit fields of the samples, one bit per node,
 		// bit (x & 31) of word (row * bitPitch + (x >> 5)); see SignBits in upg_internal.h
 		uint32_t *signBits = nullptr;
@@ -61,7 +62,9 @@ namespace upg
 #if defined(__CUDACC__)
 	// status word: bit 0 = a NaN sample was produced (the reference throws "invalid ... sdf value",
 	// sources/modesConfiguration.cpp:255-256; the host layer turns the flag into UPG_ERR_INVALID_VALUE)
-	template<int SHAPE, int ELEV>
+	// ARITH = the arithmetic build of the translation unit (UPG_ARITH_BUILD): part of the kernel's TYPE, so that the exact and the contracted
+	// build of one (shape, elevation) pair are two symbols (two weak template instantiations with one name would be merged by the linker)
+	template<int SHAPE, int ELEV, int ARITH = UPG_ARITH_BUILD>
 	__global__ void __launch_bounds__(FIELD_BLOCK) sdf_sample_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
 	{
 		grad_table_init<FIELD_BLOCK>(); // shared-memory gradient table of the Perlin / OpenSimplex generators (upg_noise.cuh)
@@ -163,7 +166,7 @@ namespace upg
 #ifndef UPG_COLUMN_MIN_BLOCKS
 #define UPG_COLUMN_MIN_BLOCKS 5 // resident blocks per SM the register allocation aims at (A/B in profiles/)
 #endif
-	template<int SHAPE, int ELEV>
+	template<int SHAPE, int ELEV, int ARITH = UPG_ARITH_BUILD>
 	__global__ void __launch_bounds__(FIELD_BLOCK, UPG_COLUMN_MIN_BLOCKS) sdf_column_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
 	{
 		__shared__ float coordZ[COLUMN_Z];

@@ -1,5 +1,6 @@
 // upg_field_inst.cu -- instantiates K1 for ONE elevation mode and a range of shapes.
-// Compiled once per (UPG_ELEV, UPG_PART) by the Makefile so that the 34 x 6 specialisations build in parallel.
+// Compiled once per (UPG_ELEV, UPG_PART) by the Makefile so that the 34 x 6 specialisations build in parallel, and a second time with
+// -fmad=true -DUPG_CONTRACT for the elevation modes that have noise: the tolerance build (UPG_ARITH_CONTRACT, include/upg.h).
 #include <cuda_runtime.h>
 
 #include "upg_field.cuh"
@@ -22,14 +23,14 @@ namespace upg
 		// ELEV and PART are part of the type on purpose: nvcc names this anonymous namespace after the SOURCE FILE, which the 24 translation
 		// units share, and emits the members as weak symbols -- without the two arguments the linker would merge the 24 different run()
 		// bodies into whichever came first (it did, as soon as run() grew too big to be inlined: every planet sampled with elevation "none").
-		template<int S, int ELEV = UPG_ELEV, int PART = UPG_PART>
+		template<int S, int ELEV = UPG_ELEV, int PART = UPG_PART, int ARITH = UPG_ARITH_BUILD>
 		struct Dispatch
 		{
 			static bool run(int shape, const PlanetParams &P, const FieldLaunch &L, cudaStream_t stream)
 			{
 				if (shape == S)
 				{
-#if UPG_ELEV == 0
+#if UPG_ELEV == 0 && !UPG_ARITH_BUILD
 					// whole grid rows of the water field: the row-wise kernel (launch_field routes every planet's water launches here)
 					if (L.field == FD_WATER && !L.positions && L.count % (uint64_t)P.grid.res == 0)
 					{
@@ -55,17 +56,22 @@ namespace upg
 					sdf_sample_kernel<S, UPG_ELEV><<<(unsigned)blocks, FIELD_BLOCK, 0, stream>>>(P, L);
 					return true;
 				}
-				return Dispatch<S + 1, ELEV, PART>::run(shape, P, L, stream);
+				return Dispatch<S + 1, ELEV, PART, ARITH>::run(shape, P, L, stream);
 			}
 		};
 		template<>
-		struct Dispatch<HI, UPG_ELEV, UPG_PART>
+		struct Dispatch<HI, UPG_ELEV, UPG_PART, UPG_ARITH_BUILD>
 		{
 			static bool run(int, const PlanetParams &, const FieldLaunch &, cudaStream_t) { return false; }
 		};
 	}
 
-	bool UPG_CAT(field_launch_e, UPG_ELEV, _p, UPG_PART)(int shape, const PlanetParams &P, const FieldLaunch &L, void *stream)
+#if UPG_ARITH_BUILD
+#define UPG_LAUNCHER_PREFIX field_launchc_e
+#else
+#define UPG_LAUNCHER_PREFIX field_launch_e
+#endif
+	bool UPG_CAT(UPG_LAUNCHER_PREFIX, UPG_ELEV, _p, UPG_PART)(int shape, const PlanetParams &P, const FieldLaunch &L, void *stream)
 	{
 		if (shape < LO || shape >= HI)
 			return false;

@@ -3,9 +3,11 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 
 #include "upg_field.cuh"
+#include "upg_mem.h"
 #include "upg_planet_host.h"
 
 namespace upg
@@ -23,7 +25,32 @@ namespace upg
 		float boxSize = 4000;
 		int device = 0;
 		int sampling = 0; // UPG_SAMPLING_* of include/upg.h
-		uint32_t *status = nullptr; // device: bit 0 = NaN sample seen
+		int arithmetic = 0; // UPG_ARITH_* of include/upg.h: which build of the dense K1 kernels the sampling entry points launch
+		int deviceCount = 1; // devices that share the planet's work in the multi-device entry points
+		int devices[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // devices[0] == device
+		// device: STATUS_SLOTS + 1 words, bit 0 of each = "a NaN sample was produced".  Word 0 is the sticky flag of the ASYNCHRONOUS
+		// device-pointer entry points (read and cleared by upg_planet_async_status); words 1.. are handed out one per synchronous
+		// call (StatusSlot), so that concurrent calls on one planet -- the generator's three field tasks and its chunk bakes,
+		// sources/generator.cpp:432-439, :159 -- never report or clear each other's flag.
+		uint32_t *status = nullptr;
+		std::atomic<uint64_t> statusSlots{ 0 }; // bit i: word i + 1 is in use
+	};
+	constexpr int STATUS_SLOTS = 64;
+
+	// the status word kernels of the current call flag NaNs in: the calling thread's slot, or the planet's sticky word
+	uint32_t *status_word(const Planet *planet);
+	// one per synchronous entry point: takes a free word of the planet, zeroes it on `s` and makes it the calling thread's word until
+	// the object dies.  Worker threads of the same call adopt() the parent's word.
+	struct StatusSlot
+	{
+		Planet *planet = nullptr;
+		int index = -1;
+		uint32_t *previous = nullptr;
+		bool installed = false;
+		int open(Planet *p, cudaStream_t s);
+		void adopt(uint32_t *word);
+		uint32_t *word() const;
+		~StatusSlot();
 	};
 
 	// a private pair of streams per API call: calls arrive concurrently from the reference's pool threads

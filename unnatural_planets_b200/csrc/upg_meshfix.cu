@@ -48,7 +48,7 @@ namespace upg
 				void *p = nullptr;
 				if (err != cudaSuccess)
 					return nullptr;
-				err = cudaMallocAsync(&p, sizeof(T) * (n ? n : 1), s);
+				err = device_alloc(&p, sizeof(T) * (n ? n : 1), s);
 				if (err == cudaSuccess)
 					ptrs.push_back(p);
 				return (T *)p;
@@ -702,9 +702,9 @@ namespace upg
 				return e; // "if all triangles were removed ... poly->clear()"
 			float *po = nullptr, *no = nullptr;
 			uint32_t *io = nullptr;
-			MF_TRY(cudaMallocAsync((void **)&po, sizeof(float) * 3 * nv, s));
-			MF_TRY(cudaMallocAsync((void **)&no, sizeof(float) * 3 * nv, s));
-			MF_TRY(cudaMallocAsync((void **)&io, sizeof(uint32_t) * 3 * nt, s));
+			MF_TRY(device_alloc(&po, sizeof(float) * 3 * nv, s));
+			MF_TRY(device_alloc(&no, sizeof(float) * 3 * nv, s));
+			MF_TRY(device_alloc(&io, sizeof(uint32_t) * 3 * nt, s));
 			if (e == cudaSuccess)
 			{
 				compact_vertices_kernel<<<blocks_of(w.verts), MF_BLOCK, 0, s>>>(w.positions, w.normals, used, newId, w.verts, flip ? -1.0f : 1.0f, po, no);
@@ -901,7 +901,7 @@ namespace upg
 				L.count = nv;
 				L.z0 = 0;
 				L.field = FD_ELEVATION_RAW;
-				L.status = planet->status;
+				L.status = status_word(planet);
 				rc = launch_field(planet, L, s);
 			}
 			if (e == cudaSuccess && rc == UPG_OK)

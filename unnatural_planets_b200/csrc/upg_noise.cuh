@@ -710,16 +710,17 @@ namespace upg
 	template<int TYPE, int FRACTAL, int OCTAVES, bool OUTLINED = false>
 	UPG_HD float noise3(const NoiseInst &n, float x, float y, float z)
 	{
-		x *= n.frequency;
-		y *= n.frequency;
-		z *= n.frequency;
+		// coordinates that reach a floor / round are single rounded operations in every build (mul_rn & co, upg_common.cuh)
+		x = mul_rn(x, n.frequency);
+		y = mul_rn(y, n.frequency);
+		z = mul_rn(z, n.frequency);
 		if (TYPE == NT_SIMPLEX || TYPE == NT_SIMPLEX_REDUCED)
 		{
 			const float R3 = (float)(2.0 / 3.0);
-			const float r = (x + y + z) * R3;
-			x = r - x;
-			y = r - y;
-			z = r - z;
+			const float r = mul_rn(add_rn(add_rn(x, y), z), R3);
+			x = sub_rn(r, x);
+			y = sub_rn(r, y);
+			z = sub_rn(r, z);
 		}
 		if (FRACTAL == FT_NONE)
 			return OUTLINED ? noise_single_outlined<TYPE>(n.seed, x, y, z) : noise_single<TYPE>(n.seed, x, y, z);
@@ -732,9 +733,9 @@ namespace upg
 			const float v = OUTLINED ? noise_single_outlined<TYPE>(seed, x, y, z) : noise_single<TYPE>(seed, x, y, z);
 			seed = iadd(seed, 1);
 			sum += fractal_term<FRACTAL>(v) * amp;
-			x *= n.lacunarity;
-			y *= n.lacunarity;
-			z *= n.lacunarity;
+			x = mul_rn(x, n.lacunarity);
+			y = mul_rn(y, n.lacunarity);
+			z = mul_rn(z, n.lacunarity);
 			amp *= n.gain;
 		}
 		return sum;
@@ -780,9 +781,9 @@ namespace upg
 	template<int OCTAVES>
 	UPG_HD float value_fbm_column(const NoiseInst &n, float x, float y, float z, ValueFbmColumn<OCTAVES> &c)
 	{
-		x *= n.frequency;
-		y *= n.frequency;
-		z *= n.frequency;
+		x = mul_rn(x, n.frequency);
+		y = mul_rn(y, n.frequency);
+		z = mul_rn(z, n.frequency);
 		int32_t seed = n.seed;
 		float sum = 0;
 		float amp = n.bounding;
@@ -802,9 +803,9 @@ namespace upg
 			const float v = nlerp(c.yf0[o], c.yf1[o], zs) * VALUE_SCALE;
 			seed = iadd(seed, 1);
 			sum += fractal_term<FT_FBM>(v) * amp;
-			x *= n.lacunarity;
-			y *= n.lacunarity;
-			z *= n.lacunarity;
+			x = mul_rn(x, n.lacunarity);
+			y = mul_rn(y, n.lacunarity);
+			z = mul_rn(z, n.lacunarity);
 			amp *= n.gain;
 		}
 		c.fresh = false;
@@ -888,9 +889,9 @@ namespace upg
 	template<int OCTAVES>
 	UPG_HD float perlin_fbm_column(const NoiseInst &n, float x, float y, float z, PerlinFbmColumn<OCTAVES> &c)
 	{
-		x *= n.frequency;
-		y *= n.frequency;
-		z *= n.frequency;
+		x = mul_rn(x, n.frequency);
+		y = mul_rn(y, n.frequency);
+		z = mul_rn(z, n.frequency);
 		int32_t seed = n.seed;
 		float sum = 0;
 		float amp = n.bounding;
@@ -900,9 +901,9 @@ namespace upg
 			const float v = perlin_column(seed, x, y, z, c.octave[o]);
 			seed = iadd(seed, 1);
 			sum += fractal_term<FT_FBM>(v) * amp;
-			x *= n.lacunarity;
-			y *= n.lacunarity;
-			z *= n.lacunarity;
+			x = mul_rn(x, n.lacunarity);
+			y = mul_rn(y, n.lacunarity);
+			z = mul_rn(z, n.lacunarity);
 			amp *= n.gain;
 		}
 		return sum;
@@ -912,9 +913,9 @@ namespace upg
 	template<int DIST, int OP, int FRACTAL, int OCTAVES>
 	UPG_HD float noise3_cellular(const float *rv, const NoiseInst &n, float x, float y, float z)
 	{
-		x *= n.frequency;
-		y *= n.frequency;
-		z *= n.frequency;
+		x = mul_rn(x, n.frequency);
+		y = mul_rn(y, n.frequency);
+		z = mul_rn(z, n.frequency);
 		if (FRACTAL == FT_NONE)
 			return single_cellular_outlined<DIST, OP>(rv, n.seed, x, y, z);
 		int32_t seed = n.seed;
@@ -926,9 +927,9 @@ namespace upg
 			const float v = single_cellular_outlined<DIST, OP>(rv, seed, x, y, z);
 			seed = iadd(seed, 1);
 			sum += fractal_term<FRACTAL>(v) * amp;
-			x *= n.lacunarity;
-			y *= n.lacunarity;
-			z *= n.lacunarity;
+			x = mul_rn(x, n.lacunarity);
+			y = mul_rn(y, n.lacunarity);
+			z = mul_rn(z, n.lacunarity);
 			amp *= n.gain;
 		}
 		return sum;
@@ -941,9 +942,9 @@ namespace upg
 	template<int DIST, int OP_A, int OP_B, int FRACTAL, int OCTAVES>
 	UPG_HD void noise3_cellular_pair(const float *rv, const NoiseInst &n, float x, float y, float z, float &a, float &b)
 	{
-		x *= n.frequency;
-		y *= n.frequency;
-		z *= n.frequency;
+		x = mul_rn(x, n.frequency);
+		y = mul_rn(y, n.frequency);
+		z = mul_rn(z, n.frequency);
 		if (FRACTAL == FT_NONE)
 		{
 			const CellularScan c = cellular_scan_outlined<DIST>(rv, n.seed, x, y, z);
@@ -961,9 +962,9 @@ namespace upg
 			seed = iadd(seed, 1);
 			sumA += fractal_term<FRACTAL>(cellular_result<DIST, OP_A>(c)) * amp;
 			sumB += fractal_term<FRACTAL>(cellular_result<DIST, OP_B>(c)) * amp;
-			x *= n.lacunarity;
-			y *= n.lacunarity;
-			z *= n.lacunarity;
+			x = mul_rn(x, n.lacunarity);
+			y = mul_rn(y, n.lacunarity);
+			z = mul_rn(z, n.lacunarity);
 			amp *= n.gain;
 		}
 		a = sumA;
@@ -973,6 +974,6 @@ namespace upg
 	// GetNoise(x, 0) for the Value kind, no fractal (sources/coloringModes.cpp:36-48)
 	UPG_HD float noise1_value(const NoiseInst &n, float x)
 	{
-		return single_value2(n.seed, x * n.frequency, 0.0f * n.frequency);
+		return single_value2(n.seed, mul_rn(x, n.frequency), mul_rn(0.0f, n.frequency));
 	}
 }

@@ -608,7 +608,7 @@ namespace upg
 			return land;
 
 		// noise3<NT_PERLIN, FT_NONE>: frequency scale, then the single generator
-		const float mask = maskColumn ? perlin_column(E.n[1].seed, pos.x * E.n[1].frequency, pos.y * E.n[1].frequency, pos.z * E.n[1].frequency, *maskColumn) : noise3<NT_PERLIN, FT_NONE, 3>(E.n[1], pos);
+		const float mask = maskColumn ? perlin_column(E.n[1].seed, mul_rn(pos.x, E.n[1].frequency), mul_rn(pos.y, E.n[1].frequency), mul_rn(pos.z, E.n[1].frequency), *maskColumn) : noise3<NT_PERLIN, FT_NONE, 3>(E.n[1], pos);
 		const float rm = smoothstep_(saturate_(mask * +7 - 0.3f));
 		const float tm = smoothstep_(saturate_(mask * -7 - 1.5f));
 
@@ -729,6 +729,6 @@ namespace upg
 	UPG_HD float grid_coord(const GridConsts &g, uint32_t i)
 	{
 		const float f = ((float)i - 2.0f) / g.resMinus5;
-		return g.boxSpan * f + g.boxA;
+		return add_rn(mul_rn(g.boxSpan, f), g.boxA); // never fused: the sample positions are the reference's in every build
 	}
 }

@@ -130,8 +130,23 @@ def texture_tail(special=None, height=None, strength=1.0, device=0):
     return pbr, nm
 
 
+def reserve(device=0, device_bytes=0, pinned_block_bytes=0, pinned_blocks=0):
+    """grows the library's device pool / pinned-block cache ahead of the first planet (upg_reserve)"""
+    capi.check(capi.load_library().upg_reserve(device, device_bytes, pinned_block_bytes, pinned_blocks))
+
+
+def trim(device=0, keep_bytes=0):
+    capi.check(capi.load_library().upg_trim(device, keep_bytes))
+
+
+def memory_stats(device=0):
+    r, u, h = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    capi.check(capi.load_library().upg_memory_stats(device, C.byref(r), C.byref(u), C.byref(h)))
+    return {"device_reserved": int(r.value), "device_used_high": int(u.value), "pinned_cached": int(h.value)}
+
+
 class Planet:
-    def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0, mesh_sampling="band"):
+    def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0, mesh_sampling="band", arithmetic="exact", devices=None):
         L = capi.load_library()
         d = capi.PlanetDesc()
         L.upg_planet_desc_default(C.byref(d))
@@ -149,6 +164,13 @@ class Planet:
         d.grid_resolution = grid
         d.device = device
         d.mesh_sampling = capi.SAMPLING[mesh_sampling]
+        d.arithmetic = capi.ARITHMETIC[arithmetic]
+        if devices:  # multi-GPU inside one process: devices[0] is the home device
+            d.device = devices[0]
+            d.device_count = len(devices)
+            for i, dev in enumerate(devices):
+                d.devices[i] = dev
+            device = devices[0]
         self.res = grid
         self.box = box
         self.device = device
@@ -166,6 +188,10 @@ class Planet:
             self.close()
         except Exception:
             pass
+
+    def async_status(self, stream=0):
+        """raises UpgError(3) if an asynchronous sampling call produced a NaN since the last query (upg_planet_async_status)"""
+        capi.check(self._lib.upg_planet_async_status(self._h, C.c_void_p(stream)))
 
     def seed_log(self):
         out = np.zeros(128, dtype=np.uint32)
