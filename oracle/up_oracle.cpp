@@ -213,7 +213,7 @@ namespace
 		double rangeDouble(double lo, double hi) // interpolate(double, double, Real): the chance is narrowed to float
 		{
 			const real c = (real)chanceD();
-			return lo + (hi - lo) * c;
+			return lo + (hi - lo) * (double)c;
 		}
 	};
 

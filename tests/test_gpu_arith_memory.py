@@ -18,7 +18,7 @@ from unnatural_planets_b200.planet import memory_stats, reserve, trim
 
 pytestmark = pytest.mark.gpu
 
-STEP = 50.0 / 6.0 / 10.0
+STEP = 12.5 / 10.0  # smoothMax(0, 0, 50) / meshElevationRatio: the reference's own cover-threshold step (tests/test_gpu_fullsize.py)
 
 
 @pytest.mark.parametrize("shape,elev", [("sphere", "lakes"), ("torus", "craters"), ("fibers", "simple"), ("bunny", "legacy"), ("asteroid", "islands"), ("knot", "none")])

@@ -12,8 +12,8 @@ to the reference's makeMesh + meshRemoveDisconnected + meshFlipNormals run over 
 
 The one cause of out-of-tolerance samples is a DISCONTINUITY OF THE REFERENCE ITSELF: commonElevationMountains returns `land` when
 cover < 1e-7 and `land + smoothMax(0, max(ridge, terraces), 50)` otherwise (sources/elevationModes.cpp:102-104, 122); with both masks
-at zero the second form is land + 50 / 6 (sources/math.cpp:28-38).  `land` comes out of powf (libm: a few ulp apart on CPU and GPU),
-so a sample whose land lies within those ulps of -10 takes the other branch: a step of 8.33 m = 0.833 field units.  No other mode
+at zero the second form is land + 12.5 (smoothMin's k * h * (1 - h) at h = 1/2, sources/math.cpp:28-38).  `land` comes out of powf (libm: a few ulp apart on CPU and GPU),
+so a sample whose land lies within those ulps of -10 takes the other branch: a step of 12.5 m = 1.25 field units.  No other mode
 of the BASELINE configurations has a discontinuity."""
 import os
 
@@ -26,7 +26,7 @@ from unnatural_planets_b200 import Planet, capi, isosurface
 pytestmark = pytest.mark.gpu
 
 THREADS = os.cpu_count() or 1
-STEP = 50.0 / 6.0 / 10.0  # smoothMax(0, 0, 50) / meshElevationRatio
+STEP = 12.5 / 10.0  # smoothMax(0, 0, 50) / meshElevationRatio
 
 
 def ref_or_skip(**kw):
@@ -61,7 +61,7 @@ def check_field(p, ref, field, res, blocks, elev_mode):
             c = ref.grid_positions(res)
             pts = np.stack([c[xx], c[yy], c[zz + z0]], axis=1)
             raw = ref.eval("elevraw", pts)
-            assert np.all((np.abs(raw + 10.0) < 2e-2) | (np.abs(raw - (-10.0 + 50.0 / 6.0)) < 2e-2)), raw[:8]
+            assert np.all((np.abs(raw + 10.0) < 2e-2) | (np.abs(raw - 2.5) < 2e-2)), raw[:8]
             bad_total += int(bad.sum())
         far = np.abs(want) > SDF_ATOL
         flips = ((got >= 0) != (want >= 0)) & far & ok

@@ -157,3 +157,38 @@ def test_default_size_planet_generator_meshes():
     edges = np.concatenate([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]])
     und = np.unique(np.sort(edges, axis=1), axis=0)
     assert len(und) * 2 == len(tri) * 3
+
+
+def test_connected_components_flatten_is_race_free():
+    """Regression test of the round-1 flake ("one run lost a land vertex after the clean-up", profiles/r02_flake.md): the pass that turns
+    the union-find forest into representatives used path halving, whose stores could overwrite a vertex's final root with an inner node;
+    the faces whose FIRST vertex that was were then dropped as "disconnected".  A long strip whose vertex ids are scrambled builds deep
+    trees with many walkers per path: every one of its faces must survive meshRemoveDisconnected, in every repetition, also when
+    three clean-ups run concurrently like the generator's three field tasks."""
+    import threading
+
+    n = 400000
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(n).astype(np.uint32)  # vertex k of the strip gets id perm[k]
+    k = np.arange(n - 2, dtype=np.uint32)
+    tris = np.stack([perm[k], perm[k + 1 + (k & 1)], perm[k + 2 - (k & 1)]], axis=1)  # consistent winding along the strip
+    tris = tris[rng.permutation(len(tris))]
+    pos = np.zeros((n, 3), np.float32)
+    inv = np.empty(n, np.int64)
+    inv[perm] = np.arange(n)
+    pos[:, 0] = (inv // 2) * 0.004 - 800.0  # inside the +-2000 box, far apart compared with the 1e-5 merge threshold
+    pos[:, 1] = (inv % 2) * 0.5
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (n, 1))
+    idx = np.ascontiguousarray(tris.reshape(-1))
+    failures = []
+
+    def work(rep):
+        m = mesh_clean(pos, nrm, idx, stages=capi.MESH_REMOVE_DISCONNECTED)
+        if len(m["indices"]) != len(idx) or len(m["positions"]) != n:
+            failures.append((rep, len(m["indices"]) // 3, len(m["positions"])))
+
+    for rep in range(6):
+        ts = [threading.Thread(target=work, args=(rep,)) for _ in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not failures, failures[:3]

@@ -1229,6 +1229,9 @@ extern "C"
 		// UPG_EARLY_WATER=1 (experimental): the water extraction starts as soon as the water launch is done,
 		// beside the band kernel, and the workers are released without the host synchronisation of check_status below
 		static const bool earlyWater = std::getenv("UPG_EARLY_WATER") && std::getenv("UPG_EARLY_WATER")[0] == '1';
+		// UPG_DEBUG_WORKERS=<bits>: 1 = one worker at a time, 2 = every worker waits (host side) for the sampling before its first call
+		static const unsigned long debugWorkers = std::getenv("UPG_DEBUG_WORKERS") ? std::strtoul(std::getenv("UPG_DEBUG_WORKERS"), nullptr, 0) : 0;
+		static std::mutex debugWorkerMutex;
 		cudaEvent_t waterDone = nullptr;
 		if (rc == UPG_OK && earlyWater && band && dens[FD_WATER])
 		{
@@ -1267,6 +1270,9 @@ extern "C"
 					[&, f]()
 					{
 						int r = UPG_OK;
+						std::unique_lock<std::mutex> oneAtATime(debugWorkerMutex, std::defer_lock);
+						if (debugWorkers & 1)
+							oneAtATime.lock();
 						StatusSlot workerSlot;
 						workerSlot.adopt(slot.word()); // the workers belong to this call
 						cudaError_t ee = cudaSetDevice(p->device);
@@ -1278,6 +1284,8 @@ extern "C"
 						if (r == UPG_OK)
 						{
 							ee = cudaStreamWaitEvent(ws.compute, (f == FD_WATER && waterDone) ? waterDone : sampled, 0);
+							if (ee == cudaSuccess && (debugWorkers & 2))
+								ee = stream_sync(ws.compute);
 							if (ee != cudaSuccess)
 								r = cuda_fail(ee, "cudaStreamWaitEvent");
 						}

@@ -108,6 +108,8 @@ namespace upg
 	UPG_HD float length_squared(V3 a) { return dot(a, a); }
 	UPG_HD float length_squared(V2 a) { return dot(a, a); }
 	UPG_HD float length(V3 a) { return sqrtf(dot(a, a)); }
+	// length() out of never-fused operations: for a length that feeds a lattice index (the asteroid shape samples a noise at pos / |pos|)
+	UPG_HD float length_rn(V3 a) { return sqrtf(add_rn(add_rn(add_rn(0.0f, mul_rn(a.x, a.x)), mul_rn(a.y, a.y)), mul_rn(a.z, a.z))); }
 	UPG_HD float length(V2 a) { return sqrtf(dot(a, a)); }
 	UPG_HD float distance_squared(V3 a, V3 b) { return length_squared(a - b); }
 	UPG_HD float distance(V3 a, V3 b) { return sqrtf(distance_squared(a, b)); }

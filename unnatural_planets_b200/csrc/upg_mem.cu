@@ -52,6 +52,19 @@ namespace upg
 				cudaMemPoolDestroy(created);
 				return e;
 			}
+			// UPG_POOL_REUSE_OFF=<bits>: switch off the pool's cross-stream reuse policies (1 follow event dependencies, 2 opportunistic,
+			// 4 internal dependencies) -- debugging aid for ordering problems between the streams of concurrent calls
+			if (const char *env = std::getenv("UPG_POOL_REUSE_OFF"))
+			{
+				const unsigned long off = std::strtoul(env, nullptr, 0);
+				int zero = 0;
+				if (off & 1)
+					cudaMemPoolSetAttribute(created, cudaMemPoolReuseFollowEventDependencies, &zero);
+				if (off & 2)
+					cudaMemPoolSetAttribute(created, cudaMemPoolReuseAllowOpportunistic, &zero);
+				if (off & 4)
+					cudaMemPoolSetAttribute(created, cudaMemPoolReuseAllowInternalDependencies, &zero);
+			}
 			g_pools[device] = created;
 		}
 		*pool = g_pools[device];

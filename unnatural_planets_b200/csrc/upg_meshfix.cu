@@ -446,11 +446,26 @@ namespace upg
 			if (i < n)
 				a[i] = i;
 		}
-		__global__ void __launch_bounds__(MF_BLOCK) flatten_kernel(uint32_t *__restrict__ parent, uint32_t n)
+		// parent[i] = root of i, for every i.  The walk is READ-ONLY on purpose: uf_find()'s path halving stores an ancestor it read a
+		// moment ago into p[x], and when that store (by a thread walking THROUGH i) lands after thread i has written its final root, i
+		// is left pointing at an inner node.  The next kernels take parent[] for the representative, so the faces whose first vertex is i
+		// were counted into the wrong component and dropped by meshRemoveDisconnected -- one vertex and its six triangles lost in about
+		// one mesh of a hundred when three clean-ups ran concurrently (profiles/r02_flake.md).  Here location i is written by thread i
+		// alone, and every value a walker can read (an old ancestor or the final root) leads to the same root.
+		__global__ void __launch_bounds__(MF_BLOCK) flatten_kernel(uint32_t *parent, uint32_t n)
 		{
 			const uint32_t i = blockIdx.x * MF_BLOCK + threadIdx.x;
-			if (i < n)
-				parent[i] = uf_find(parent, i);
+			if (i >= n)
+				return;
+#if defined(UPG_FLATTEN_HALVING) // the round-1 form, kept for the A/B run that demonstrates the race (profiles/r02_flake.md)
+			parent[i] = uf_find(parent, i);
+			return;
+#endif
+			const volatile uint32_t *p = parent;
+			uint32_t x = i;
+			for (uint32_t px = p[x]; px != x; px = p[x])
+				x = px;
+			parent[i] = x;
 		}
 
 		// ---- meshMergeCloseVertices({}) (meshAlgorithms.cpp:447-499): threshold 1e-5 (meshAlgorithms.h:23) ----------------------------

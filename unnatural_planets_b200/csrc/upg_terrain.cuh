@@ -467,7 +467,7 @@ namespace upg
 				return -(sd_box(pos, v3(1300, 1300, 1300)) - 200);
 			case SH_ASTEROID:
 			{
-				const float l = length(pos);
+				const float l = length_rn(pos); // exact in every build: d reaches the lattice of the noise (OpenSimplex2 has small steps at axis ties)
 				if (l < 1)
 					return -100;
 				const V3 d = pos / l;
