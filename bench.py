@@ -40,36 +40,49 @@ METRIC = "sdf_samples_per_s"
 UNIT = "samples/s"
 FIELDS = ("land", "water", "navigation")
 SHAPE, ELEVATION, COLORING = "sphere", "lakes", "default"
-# algorithmic FP32 work (FMA = 2) per unit, counted from the un-contracted arithmetic; DESIGN.md "Work per unit"
-FLOPS_PER_SAMPLE_LAND = 640.0
-FLOPS_PER_TEXEL_LAND = 7200.0
-# dram__bytes_read.sum + dram__bytes_write.sum of the fused K1 launch per grid node, from the committed `ncu --set full` capture
-# (profiles/); None until a capture of this kernel exists
-def _k1_traffic():
+# Algorithmic FP32 work per unit (FMA = 2): EXACT COUNTS from the instrumented build of the CPU restatement (oracle/up_count.cpp,
+# tests/hostlib/upg_host_count.cpp; tools/count_ops.py wrote profiles/r02_work_counts_config3.json, tests/test_oracle_counts.py pins
+# it).  Per SDF sample as the reference evaluates it (each field on its own: sources/generator.cpp:432-439), per baked land texel.
+def _work_counts():
+    c = json.load(open(os.path.join(ROOT, "profiles", "r02_work_counts_config3.json")))
+    f = c["fields"]
+    return {
+        "per_grid_node": c["flops_per_grid_node"],  # land + water + navigation, three evaluations like the reference's three tasks
+        "per_sample": c["flops_per_grid_node"] / 3.0,
+        "one_evaluation": f["land"]["flops"] + 3.0,  # ONE shape + ONE elevation evaluation feeding the three combinations (what the fused launch needs)
+        "special_per_grid_node": c["special_per_grid_node"],
+        "land_texel": c["texels"]["land"]["flops"], "land_texel_fp64": c["texels"]["land"]["flops_fp64"],
+        "water_texel": c["texels"]["water"]["flops"],
+    }
+
+
+WORK = _work_counts()
+
+
+def _ncu(name):
+    """per-unit figures of a committed ncu capture (profiles/<name>.json, tools/ncu_ops_json.py); None when absent"""
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "k1_column_ncu.json")))["dram_bytes_per_grid_node"])
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
     except Exception:
         return None
 
 
-K1_TRAFFIC_BYTES_PER_NODE = _k1_traffic()
-
-
-def _k1_issue():
-    """issue-slot view of the same committed capture: the arithmetic is un-contracted (no FMA), so every flop of the reference's
-    expression costs one issue slot where the FMA peak counts two, and the hash lattice costs INT32 slots on top"""
-    try:
-        c = json.load(open(os.path.join(ROOT, "profiles", "k1_column_ncu.json")))
-        per_node = c["smsp__inst_executed.sum"] * 32.0 / c["grid_nodes"]  # issue slots x 32 lanes, whether or not every lane is active
-        return {"issue_active_frac": c["smsp__issue_active.avg.pct_of_peak_sustained_active"] / 100.0, "thread_instructions_per_grid_node": per_node,
-                "frac_ceiling_at_full_issue": FLOPS_PER_SAMPLE_LAND / (2.0 * per_node),
-                "source": "profiles/k1_column_ncu.json (ncu --set full of this kernel); frac_ceiling = flops_per_grid_node / (2 x instructions per node): what roofline.frac would be with every issue slot busy"}
-    except Exception:
-        return None
+K1_NCU = _ncu("r02_k1_ops_exact.json")
+K6_NCU = _ncu("r02_k6_ops.json")
 
 
 def workload(args):
     return "BASELINE configs[2]: --shape sphere (elevation lakes, colouring default, default seed), 3 fields (land, water, navigation) x %d^3 grid, %d x %d land + water bake" % (args.grid, args.texture, args.texture)
+
+
+def bench_config(args):
+    """the SAME object in both arms (ours / --impl reference): what is generated and what one unit of the metric is"""
+    n = args.grid**3
+    return {
+        "workload": workload(args), "grid": args.grid, "fields": list(FIELDS), "texture": args.texture, "planets_per_step": args.gpus,
+        "sample": "one terrainSdf* value; every grid node yields three (land, water, navigation) and BOTH arms evaluate all three fields of the nodes they time",
+        "l2": "a sampling step writes %.1f GB per GPU and a bake step touches > 1 GB of float images (>> 126 MB L2); inputs are a ~2 KB parameter block and a mesh" % (12e-9 * n),
+    }
 
 
 def seed_for(index):
@@ -131,19 +144,27 @@ class ClockSampler:
 
 # ---- CPU reference legs (oracle/_ref; oracle/ is only ever the checker or the timed baseline, never the product) ----
 def cpu_sampling_rate(res, slices, threads):
-    """the reference's sampling loop (MarchingCubes::updateByPosition x terrainSdfLand) on `slices` z-slices around the equator"""
+    """the reference's sampling loops (MarchingCubes::updateByPosition x terrainSdfLand / Water / Navigation: the three tasks of
+    sources/generator.cpp:432-439) on `slices` z-slices around the equator, every loop split over `threads` threads;
+    returns (samples/s counting all three fields, seconds, kind)"""
     from oracle import ref as oref
 
+    z0 = res // 2 - slices // 2
     if not oref.available():
         from oracle import port as oport  # the standalone restatement
 
-        return oport.sample_rate(SHAPE, ELEVATION, res, slices, threads) + ("port",)
+        p = oport.OraclePlanet(SHAPE, ELEVATION)
+        t = time.perf_counter()
+        for f in FIELDS:
+            p.grid(f, res, z0=z0, z1=z0 + slices, threads=threads)
+        dt = time.perf_counter() - t
+        return len(FIELDS) * slices * res * res / dt, dt, "port"
     planet = oref.RefPlanet(shape=SHAPE, elevation=ELEVATION)
-    z0 = res // 2 - slices // 2
     t = time.perf_counter()
-    planet.grid("land", res, z0=z0, z1=z0 + slices, threads=threads)
+    for f in FIELDS:
+        planet.grid(f, res, z0=z0, z1=z0 + slices, threads=threads)
     dt = time.perf_counter() - t
-    return slices * res * res / dt, dt, "reference"
+    return len(FIELDS) * slices * res * res / dt, dt, "reference"
 
 
 def cpu_bake_rate(mesh, texture, window, threads):
@@ -183,7 +204,7 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     res = args.grid
-    slices = max(1, (12 * threads * 250000) // (res * res))  # ~3e6 samples per thread and step: seconds of CPU work
+    slices = max(1, (6 * threads * 250000) // (res * res))  # ~1.5e6 nodes x 3 fields per thread and step: seconds of CPU work
     rates = []
     for i in range(args.warmup + args.steps):
         r, dt, kind = cpu_sampling_rate(res, slices, threads)
@@ -191,11 +212,11 @@ def run_reference(args, rank, world):
             rates.append((r, dt))
     value = statistics.mean(r for r, _ in rates)
     ms = statistics.mean(dt for _, dt in rates) * 1e3
-    sample = "%d z-slices x %d^2 of the land field per step (%.3g of one planet's %.3g samples), %d threads" % (slices, res, slices / (3.0 * res), 3.0 * res**3, threads)
+    sample = "land + water + navigation of %d z-slices x %d^2 per step (%.3g of one planet's %.3g samples), %d threads" % (slices, res, slices / float(res), 3.0 * res**3, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload(args), "note": "host CPU, no GPU involved"},
+        "config": bench_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,6 +291,21 @@ def run_ours(args, rank, world, local_rank):
             k1.synchronize()
             kernel_ms.append(k0.elapsed_time(k1))
         single_ms[f] = statistics.mean(kernel_ms)
+
+    # the same fused launch in the contracted build (UPG_ARITH_CONTRACT: FMA contraction, within the 1e-4 tolerance of the exact build)
+    cplanet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank), arithmetic="contract")
+    cplanet.fields_samples_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
+    k0.record(stream)
+    csteps = max(3, min(args.steps, 10))
+    for _ in range(csteps):
+        cplanet.fields_samples_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
+    k1.record(stream)
+    k1.synchronize()
+    contract_ms = k0.elapsed_time(k1) / csteps
+    cplanet.async_status(stream.cuda_stream)
+    cplanet.close()
+    planet.async_status(stream.cuda_stream)
+    multi_line = None
 
     # end to end through the host-buffer C-ABI call: device->host copies inside the timed region
     host = torch.empty(n, dtype=torch.float32, pin_memory=True)
@@ -546,12 +582,12 @@ def run_ours(args, rank, world, local_rank):
             }
 
     texels = covered["land"] + covered["water"]
-    times = torch.tensor([ms_total, e2e_s * 1e3, bake_ms, bake_e2e_s * 1e3, mesh_s * 1e3, mesh_raw_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3, bake_ms, bake_e2e_s * 1e3, mesh_s * 1e3, mesh_raw_s * 1e3, contract_ms], dtype=torch.float64, device=dev)
     counts = torch.tensor([float(texels)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, bake_ms_max, bake_e2e_ms, mesh_ms, mesh_raw_ms = (float(x) for x in times)
+    ms_total, e2e_ms, bake_ms_max, bake_e2e_ms, mesh_ms, mesh_raw_ms, contract_ms_max = (float(x) for x in times)
     texels_all = float(counts[0])
     if rank != 0:
         return
@@ -562,61 +598,103 @@ def run_ours(args, rank, world, local_rank):
 
     peak = fp32_peak(capi, local_rank)
     fused_ms = ms_total / args.steps  # one launch per step
-    achieved = FLOPS_PER_SAMPLE_LAND * n / (fused_ms * 1e-3) / 1e12
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
     peak_source = "FP32 FMA ceiling measured in this run by upg_measure_fp32_peak (MEASURED_PEAKS.json has no FP32 SIMT figure)"
+
+    def tflops(flops_per_node, ms):
+        return flops_per_node * n / (ms * 1e-3) / 1e12
+
+    # `achieved`: the contract's ALGORITHMIC figure -- the reference's arithmetic for the samples one launch produces (instrumented
+    # count per sample x 3e9 samples; the reference evaluates each field on its own) over the launch time.  Next to it, as scalars the
+    # driver keeps: the same with ONE evaluation per grid node credited (what the fused launch has to do), and the flops the kernel
+    # EXECUTES (ncu instruction counts of the committed capture; exact work elimination makes it less than either).
+    achieved = tflops(WORK["per_grid_node"], fused_ms)
+    one_eval = tflops(WORK["one_evaluation"], fused_ms)
+    executed = tflops(K1_NCU["executed_flops_per_unit"], fused_ms) if K1_NCU else None
+    issue_peak = None
+    if K1_NCU and clocks.summary()["sm_mhz"]:
+        issue_peak = 148 * 4 * 32 * clocks.summary()["sm_mhz"] * 1e6  # thread-instruction issue slots per second
     roofline = {
-        "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": K1_TRAFFIC_BYTES_PER_NODE * n if K1_TRAFFIC_BYTES_PER_NODE else None, "peak_source": peak_source,
-        "kernel_ms": fused_ms, "flops_per_grid_node": FLOPS_PER_SAMPLE_LAND, "samples_per_grid_node": len(FIELDS),
-        "single_field_kernel_ms": single_ms, "issue_slots": _k1_issue(),
-        "hbm": {"achieved_gbs": 4.0 * len(FIELDS) * n / (fused_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "note": "12 B written per grid node (3 fields); the kernel is FP32/INT32 issue bound"},
+        "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk), exact arithmetic build", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": (K1_NCU["dram_bytes_read"] + K1_NCU["dram_bytes_write"]) if K1_NCU else None, "peak_source": peak_source,
+        "kernel_ms": fused_ms, "flops_per_grid_node": WORK["per_grid_node"], "flops_per_sample": WORK["per_sample"], "samples_per_grid_node": len(FIELDS),
+        "flops_source": "instrumented build of the CPU restatement, every 2nd node per axis of the 1000^3 grid (profiles/r02_work_counts_config3.json)",
+        "frac_one_evaluation_per_node": one_eval / peak if peak else None, "flops_one_evaluation_per_node": WORK["one_evaluation"],
+        "frac_executed": executed / peak if (peak and executed) else None, "executed_flops_per_grid_node": K1_NCU["executed_flops_per_unit"] if K1_NCU else None,
+        "issue_slot_frac": (K1_NCU["issue_slots_x32_per_unit"] * n / (fused_ms * 1e-3) / issue_peak) if issue_peak else None,
+        "thread_instructions_per_grid_node": K1_NCU["thread_instructions_per_unit"] if K1_NCU else None,
+        "fp32_instruction_share": (K1_NCU["fp32_instructions_per_unit"] / K1_NCU["thread_instructions_per_unit"]) if K1_NCU else None,
+        "hbm_achieved_gbs": 4.0 * len(FIELDS) * n / (fused_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+        "contract_kernel_ms": contract_ms_max, "contract_samples_per_s": samples_per_step / (contract_ms_max * 1e-3), "contract_frac": tflops(WORK["per_grid_node"], contract_ms_max) / peak if peak else None,
+        "single_field_kernel_ms_land": single_ms["land"], "single_field_kernel_ms_water": single_ms["water"], "single_field_kernel_ms_navigation": single_ms["navigation"],
     }
-    bake_achieved = FLOPS_PER_TEXEL_LAND * covered["land"] / (bake_land_ms * 1e-3) / 1e12
+    bake_achieved = WORK["land_texel"] * covered["land"] / (bake_land_ms * 1e-3) / 1e12
     texel_bake = {
         "metric": "baked_texels_per_s", "value": texels_all / (bake_ms_max * 1e-3), "unit": "texels/s", "steps": bake_steps, "ms_per_step": bake_ms_max,
         "texels_per_step": int(texels_all), "covered": {k: int(v) for k, v in covered.items()}, "texture": [tex, tex],
         "note": "texels = covered texels (one terrainTile each; the reference evaluates every (triangle, texel) visit) of the land (3+2+1 ch) and water (4+2+1 ch) surfaces; UVs: synthetic octahedral chart",
         "e2e": {"value": texels_all / (bake_e2e_ms * 1e-3), "unit": "texels/s", "h2d_bytes_per_step": int(h2d_bake), "d2h_bytes_per_step": int(d2h_bake), "path": "upg_bake_export: host mesh -> device, pinned host albedo / pbr / normal-map images <- device, wall clock"},
-        "roofline": {"bound": "fp32", "kernel": "tile_color_kernel<default> + its K1 probes (land bake, whole upg_bake_device call)", "achieved": bake_achieved, "peak": peak, "unit": "TFLOP/s", "frac": bake_achieved / peak if peak else None, "traffic": None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": FLOPS_PER_TEXEL_LAND},
+        "roofline": {"bound": "fp32", "kernel": "tile_color_kernel<default> + its K1 probes (land bake, whole upg_bake_device call)", "achieved": bake_achieved, "peak": peak, "unit": "TFLOP/s", "frac": bake_achieved / peak if peak else None,
+                     "traffic": (K6_NCU["dram_bytes_read"] + K6_NCU["dram_bytes_write"]) if K6_NCU else None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": WORK["land_texel"], "fp64_flops_per_texel": WORK["land_texel_fp64"]},
     }
+    # the second half of the metric and the planet times as SCALARS inside `roofline` (the driver's record keeps scalars there)
+    roofline.update({
+        "texel_bake_texels_per_s": texel_bake["value"], "texel_bake_e2e_texels_per_s": texel_bake["e2e"]["value"], "texel_bake_ms_per_step": bake_ms_max, "texel_bake_land_call_ms": bake_land_ms,
+        "texel_bake_frac": texel_bake["roofline"]["frac"], "texel_bake_flops_per_texel": WORK["land_texel"], "texel_bake_traffic": texel_bake["roofline"]["traffic"], "texel_bake_covered_texels": int(texels_all),
+    })
     planet_ms = mesh_ms + bake_e2e_ms
     planet_line = {
         "ms": planet_ms, "base_meshes_ms": mesh_ms, "base_meshes_without_cleanup_ms": mesh_raw_ms, "bake_ms": bake_e2e_ms, "bake_one_after_the_other_ms": bake_seq_s * 1e3, "field_mesh_land_ms": field_mesh_land_s * 1e3,
         "what": "upg_field_meshes_clean (band sampling of the 3 fields + 3 concurrent Dual Marching Cubes extractions + K9 clean-up = the bodies of meshGenerateBaseLand/Water/Navigation + mesh downloads) + 2 x upg_bake_export (bake + pbr / normal-map tail; land and water from two host threads like the generator's chunk tasks), host buffers, wall clock",
         "mesh": mesh_stats, "base_meshes": final_stats, "mesh_sampling": sampling_stats,
     }
+    roofline.update({"planet_ms": planet_ms, "planet_base_meshes_ms": mesh_ms, "planet_bake_ms": bake_e2e_ms, "planet_band_sampling_ms": sampling_stats["band_sampling_ms"], "planet_land_triangles": final_stats["land"]["triangles"]})
 
     threads = os.cpu_count() or 1
     cpu = {"value": None, "unit": UNIT, "cores": threads, "kind": "unavailable", "sample": ""}
     try:
-        slices = max(1, min(res, (30 * threads * 250000) // (res * res)))  # ~10 s of CPU work in total, spread over every host thread
+        slices = max(1, min(res, (10 * threads * 250000) // (res * res)))  # ~10 s of CPU work in total, spread over every host thread
         cpu_rate, cpu_dt, kind = cpu_sampling_rate(res, slices, threads)
-        cpu = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": "%d z-slices x %d^2 of the land field (%.1f s on %d threads)" % (slices, res, cpu_dt, threads)}
+        cpu = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": "land + water + navigation of %d z-slices x %d^2 (%.1f s on %d threads)" % (slices, res, cpu_dt, threads)}
         planet_line["cpu_sampling_ms_extrapolated"] = 3.0 * n / cpu_rate * 1e3
+        cpu["planet_sampling_ms_extrapolated"] = planet_line["cpu_sampling_ms_extrapolated"]
         window = 256
         r = cpu_bake_rate(meshes["land"], tex, window, threads)
         if r:
-            cpu["texel_bake"] = {"value": r[0], "unit": "texels/s", "sample": "%d windows of %d^2 texels of the %d^2 land bake, one per thread (%.1f s, %d covered texels)" % (threads, window, tex, r[1], r[2])}
+            cpu["texel_bake_value"] = r[0]
+            cpu["texel_bake_sample"] = "%d windows of %d^2 texels of the %d^2 land bake, one per thread (%.1f s, %d covered texels)" % (threads, window, tex, r[1], r[2])
             planet_line["cpu_bake_ms_extrapolated"] = texels_all / world / r[0] * 1e3
+            cpu["planet_bake_ms_extrapolated"] = planet_line["cpu_bake_ms_extrapolated"]
     except Exception as ex:  # the baseline is reported, never required for the GPU number
         cpu["sample"] = "failed: %r" % (ex,)
 
-    launches_sampling = args.steps  # one fused sdf_sample_kernel launch per step
+    if sharded_line:
+        roofline.update({"sharded_planet_grid": sharded_line["grid"], "sharded_planet_texture": sharded_line["texture"], "sharded_planet_isosurface_ms": sharded_line["isosurface_ms"], "sharded_planet_bake_ms": sharded_line["bake_ms"]})
+    if multi_line:
+        roofline.update({k: v for k, v in multi_line.items() if isinstance(v, (int, float))})
+    if batch_line:
+        roofline.update({"batch_planets": batch_line["planets"], "batch_planets_per_s": batch_line["planets_per_s"], "batch_ms_per_planet": batch_line["generation_ms_per_planet"], "batch_failed": batch_line["failed"]})
+        # the per-planet list is long: stderr, not the JSON line
+        print("[bench] batch planets of rank 0: " + json.dumps(batch_line.pop("rank0_planets")), file=sys.stderr, flush=True)
+
+    launches_sampling = args.steps  # one fused sdf_column_kernel launch per step
+    param_bytes = int(capi.load_library().upg_kernel_param_bytes())
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload(args), "grid": res, "fields": list(FIELDS), "texture": tex, "planets_per_step": world, "l2": "each sampling step writes %.1f GB per GPU and each bake step touches > 1 GB of float images (>> 126 MB L2); inputs are a ~2 KB parameter block and a mesh" % (12e-9 * n)},
+        "config": bench_config(args),
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * n * len(FIELDS), "path": "upg_field_samples -> pinned host buffer, wall clock incl. D2H"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 3 * param_bytes * max(1, (n * 4 + (64 << 20) - 1) // (64 << 20)), "d2h_bytes_per_step": 4 * n * len(FIELDS),
+                "path": "3 x upg_field_samples -> pinned host buffer, wall clock incl. D2H; the only host -> device input of a generator step is the planet's parameter block (%d B), sent with every slab launch as kernel arguments" % param_bytes},
         "gpu_launches": launches_sampling,
-        "roofline": roofline,
         "texel_bake": texel_bake,
         "planet": planet_line,
         "sharded_planet": sharded_line,
+        "multi_device_planet": multi_line,
         "batch": batch_line,
         "cpu_baseline": cpu,
+        "roofline": roofline,
     }
     print(json.dumps(line), file=_STDOUT, flush=True)
 

@@ -392,6 +392,11 @@ int upg_dilate(int device, float *image, uint32_t width, uint32_t height, uint32
  * MEASURED_PEAKS.json only carries HBM and tensor-core peaks */
 int upg_measure_fp32_peak(int device, float *tflops_out);
 
+/* bytes of per-planet input a sampling launch carries from the host to the device: the planet's parameter block (mode ids, seeds,
+ * prepared shape constants) and the launch descriptor travel as __grid_constant__ kernel arguments -- a generator has no other per-step
+ * input (bench.py declares them as the host -> device bytes of a sampling step) */
+uint32_t upg_kernel_param_bytes(void);
+
 /* thread-local description of the last failure on this thread ("" if none) */
 const char *upg_last_error(void);
 

@@ -60,9 +60,6 @@ namespace upc
 	{
 		T v;
 		counted() = default;
-		counted(const counted &) = default;
-		counted &operator=(const counted &) = default;
-		counted(const volatile counted &o) : v(o.v) {} // `volatile real x; real y = x;` in the restatement
 		// from any arithmetic type: integer sources are a conversion instruction, floating literals are free
 		template<class U, class = typename std::enable_if<std::is_arithmetic<U>::value>::type>
 		constexpr __attribute__((always_inline)) counted(U u) : v((T)u)
@@ -170,6 +167,8 @@ namespace upc
 	typedef counted<float, OP_FADD, OP_FMUL, OP_FDIV, OP_FSQRT, OP_FCMP, OP_SPECIAL> cfloat;
 	typedef counted<double, OP_DADD, OP_DMUL, OP_DDIV, OP_DSQRT, OP_DCMP, OP_DSPECIAL> cdouble;
 	static_assert(sizeof(cfloat) == sizeof(float) && sizeof(cdouble) == sizeof(double), "layout compatible with the native types");
+	// trivially copyable: passed and returned in registers like the native type, so the counted libraries keep the C ABI of the plain ones
+	static_assert(std::is_trivially_copyable<cfloat>::value && std::is_trivially_copyable<cdouble>::value, "same calling convention as the native types");
 
 	template<class C>
 	struct traits;

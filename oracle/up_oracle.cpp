@@ -589,8 +589,8 @@ namespace
 		if (len2(pos_) < (real)1e-3)
 			return 0;
 		const vec3 pos = pos_ * (real)0.0004;
-		volatile real power = 3.0f; // keep pow() a run-time call, as in the reference (cage::pow lives in another TU)
-		const real Power = power;
+		volatile int power = 3; // keep pow() a run-time call, as in the reference (cage::pow lives in another TU)
+		const real Power = (real)power;
 		vec3 z = pos;
 		real dr = 1.0f, r = 0.0f;
 		for (uint32_t i = 0; i < 20; i++)

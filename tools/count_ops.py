@@ -57,6 +57,55 @@ def count_field(L, shape, elevation, field, res, stride, threads, box=4000.0, ch
     return per
 
 
+def count_texels(shape, elevation, coloring, mesh_res, purposes=("land", "water")):
+    """operation counts of terrainTile per surface point: the points are the vertices (positions + normals) of the oracle's own
+    isosurface of the land / water field at `mesh_res`^3 -- spread over the whole planet like the covered texels of a bake"""
+    d = os.path.join(ROOT, "tests", "hostlib")
+    subprocess.check_call(["make", "-s", "-C", d, "libupg_hostcount.so", "libupg_hosttest.so"])
+    out = {}
+    libs = {}
+    for name in ("libupg_hostcount.so", "libupg_hosttest.so"):
+        H = C.CDLL(os.path.join(d, name))
+        H.upgh_create.restype = C.c_void_p
+        H.upgh_create.argtypes = [C.c_int] * 5 + [C.c_uint64] * 2 + [C.c_float, C.c_int]
+        H.upgh_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        libs[name] = H
+    HC, HP = libs["libupg_hostcount.so"], libs["libupg_hosttest.so"]
+    HC.upghc_get.argtypes = [C.c_void_p]
+    nops = HC.upghc_op_count()
+    L = counted_lib()
+    names = [L.upc_op_name(i).decode() for i in range(nops)]
+    colorings = ("default", "barren", "debug")
+    args = (oport.SHAPES.index(shape), oport.ELEVATIONS.index(elevation), colorings.index(coloring), 0, 0, oport.DEFAULT_SEED[0], oport.DEFAULT_SEED[1], 4000.0, mesh_res)
+    hc, hp = HC.upgh_create(*args), HP.upgh_create(*args)
+    planet = oport.OraclePlanet(shape, elevation)
+    for purpose in purposes:
+        grid = planet.grid("land" if purpose == "land" else "water", mesh_res, threads=os.cpu_count() or 1)
+        m = oport.isosurface(grid)
+        pos = np.ascontiguousarray(m["positions"], dtype=np.float32)
+        nrm = np.ascontiguousarray(-m["normals"], dtype=np.float32)  # meshFlipNormals: the generator bakes the flipped mesh
+        keep = np.isfinite(nrm).all(axis=1) & (np.abs((nrm * nrm).sum(axis=1) - 1) < 1e-3)
+        pos, nrm = pos[keep], nrm[keep]
+        code = {"land": 1, "water": 2}[purpose]
+        got = np.zeros((len(pos), 13), dtype=np.float32)
+        want = np.zeros((len(pos), 13), dtype=np.float32)
+        HC.upghc_reset()
+        HC.upgh_tiles(C.c_void_p(hc), code, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), len(pos), got.ctypes.data_as(C.c_void_p))
+        counts = np.zeros(nops, dtype=np.uint64)
+        HC.upghc_get(counts.ctypes.data_as(C.c_void_p))
+        HP.upgh_tiles(C.c_void_p(hp), code, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), len(pos), want.ctypes.data_as(C.c_void_p))
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), "counted colouring build differs from the plain host build"
+        per = {n: float(c) / len(pos) for n, c in zip(names, counts)}
+        per["flops"] = per["fadd"] + per["fmul"] + per["fdiv"] + per["fsqrt"]
+        per["flops_fp64"] = per["dadd"] + per["dmul"] + per["ddiv"] + per["dsqrt"]
+        per["points"] = int(len(pos))
+        out[purpose] = per
+        print("%-6s texel %8.1f FP32 flops (fadd %.1f fmul %.1f fdiv %.2f fsqrt %.2f) + %.1f FP64 flops + fcmp %.1f i2f %.1f f2i %.1f special %.2f dspecial %.2f   [%d surface points]" % (
+            purpose, per["flops"], per["fadd"], per["fmul"], per["fdiv"], per["fsqrt"], per["flops_fp64"], per["fcmp"], per["i2f"], per["f2i"], per["special"], per["dspecial"], len(pos)), flush=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=1000)
@@ -65,6 +114,9 @@ def main():
     ap.add_argument("--elevation", default="lakes")
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--texels", action="store_true", help="also count terrainTile per surface point (colouring default)")
+    ap.add_argument("--coloring", default="default")
+    ap.add_argument("--mesh-res", type=int, default=200)
     a = ap.parse_args()
     L = counted_lib()
     out = {"shape": a.shape, "elevation": a.elevation, "grid": a.grid, "stride": a.stride, "fields": {}}
@@ -77,6 +129,8 @@ def main():
     out["flops_per_grid_node"] = sum(out["fields"][f]["flops"] for f in out["fields"])
     out["special_per_grid_node"] = sum(out["fields"][f]["special"] for f in out["fields"])
     print("per grid node (land + water + navigation, each evaluated on its own like the reference's three tasks): %.1f flops, %.2f libm calls" % (out["flops_per_grid_node"], out["special_per_grid_node"]))
+    if a.texels:
+        out["texels"] = count_texels(a.shape, a.elevation, a.coloring, a.mesh_res)
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)
 

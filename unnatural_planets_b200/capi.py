@@ -125,6 +125,7 @@ def load_library():
     L.upg_planet_destroy.restype = None
     L.upg_planet_seed_log.argtypes = [vp, fp, i32]
     L.upg_planet_async_status.argtypes = [vp, vp]
+    L.upg_kernel_param_bytes.restype = C.c_uint32
     L.upg_reserve.argtypes = [i32, u64, u64, i32]
     L.upg_trim.argtypes = [i32, u64]
     L.upg_memory_stats.argtypes = [i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]

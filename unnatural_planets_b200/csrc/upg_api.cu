@@ -202,6 +202,11 @@ extern "C"
 		d->device = 0;
 	}
 
+	uint32_t upg_kernel_param_bytes(void)
+	{
+		return (uint32_t)(sizeof(PlanetParams) + sizeof(FieldLaunch));
+	}
+
 	int upg_shape_id(const char *name)
 	{
 		return lookup(shapeNames, SH_COUNT, name);
@@ -325,6 +330,16 @@ extern "C"
 			delete p;
 			return cuda_fail(e, "upg_planet_create");
 		}
+		p->children[0] = p;
+		if (p->deviceCount > 1)
+		{
+			const int rc = multi_setup(p, d);
+			if (rc != UPG_OK)
+			{
+				upg_planet_destroy(reinterpret_cast<upg_planet *>(p));
+				return rc;
+			}
+		}
 		*out = reinterpret_cast<upg_planet *>(p);
 		return UPG_OK;
 	}
@@ -334,6 +349,7 @@ extern "C"
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p)
 			return;
+		multi_teardown(p);
 		cudaSetDevice(p->device);
 		if (p->status)
 			cudaFree(p->status);
@@ -347,9 +363,14 @@ extern "C"
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !table1024)
 			return fail(UPG_ERR_ARGUMENT, "null argument");
-		cudaError_t e = cudaSetDevice(p->device);
-		if (e == cudaSuccess)
-			e = cudaMemcpy(p->cellularTable, table1024, sizeof(float) * 1024, cudaMemcpyHostToDevice);
+		cudaError_t e = cudaSuccess;
+		for (int i = 0; i < p->deviceCount && e == cudaSuccess; i++)
+		{
+			Planet *c = p->children[i];
+			e = cudaSetDevice(c->device);
+			if (e == cudaSuccess)
+				e = cudaMemcpy(c->cellularTable, table1024, sizeof(float) * 1024, cudaMemcpyHostToDevice);
+		}
 		if (e != cudaSuccess)
 			return cuda_fail(e, "upg_planet_set_cellular_table");
 		return UPG_OK;
@@ -1017,7 +1038,7 @@ namespace upg
 	}
 
 	// copies a device-side DmcResult into one pinned host block and fills the ABI struct
-	static int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
+	int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
 	{
 		// a slab result only hands out the blocks it owns (DmcResult::first* / owned*); a whole volume owns everything
 		const uint64_t nv = r.ownedVertices, nq = r.quads ? r.ownedQuads : 0, ni = (uint64_t)r.ownedTriangles * 3;
@@ -1226,9 +1247,12 @@ extern "C"
 		uint32_t *bitBlock = nullptr;
 		if (rc == UPG_OK && band)
 			rc = alloc_sign_bits(res, zb - za, field_mask, cs.compute, bits3, &bitBlock);
-		// UPG_EARLY_WATER=1 (experimental): the water extraction starts as soon as the water launch is done,
-		// beside the band kernel, and the workers are released without the host synchronisation of check_status below
-		static const bool earlyWater = std::getenv("UPG_EARLY_WATER") && std::getenv("UPG_EARLY_WATER")[0] == '1';
+		// The water extraction starts as soon as the water launch is done, beside the band kernel of land / navigation (which only READS
+		// the water field), and the workers are released without a host synchronisation: their streams wait for the sampling on the
+		// device, the NaN status of the sampling is checked after they are done.  Round 1 reverted this ordering because one run lost a
+		// vertex; the cause was the union-find flatten of K9, in every ordering (profiles/r02_flake.md: 0 deviations in 1200 planets
+		// since).  UPG_EARLY_WATER=0 restores the conservative ordering.
+		static const bool earlyWater = !(std::getenv("UPG_EARLY_WATER") && std::getenv("UPG_EARLY_WATER")[0] == '0');
 		// UPG_DEBUG_WORKERS=<bits>: 1 = one worker at a time, 2 = every worker waits (host side) for the sampling before its first call
 		static const unsigned long debugWorkers = std::getenv("UPG_DEBUG_WORKERS") ? std::strtoul(std::getenv("UPG_DEBUG_WORKERS"), nullptr, 0) : 0;
 		static std::mutex debugWorkerMutex;
@@ -1374,6 +1398,9 @@ extern "C"
 
 	int upg_field_meshes(upg_planet *planet, unsigned field_mask, upg_mesh *out3)
 	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (p && p->deviceCount > 1)
+			return multi_field_meshes(p, field_mask, 0, out3);
 		return field_meshes_impl(planet, field_mask, 0, 0, 0, out3);
 	}
 
@@ -1414,6 +1441,9 @@ extern "C"
 	{
 		if (stages == 0)
 			return fail(UPG_ERR_ARGUMENT, "no clean-up stage requested");
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (p && p->deviceCount > 1)
+			return multi_field_meshes(p, field_mask, stages, out3);
 		return field_meshes_impl(planet, field_mask, stages, 0, 0, out3);
 	}
 
@@ -1648,5 +1678,13 @@ extern "C"
 		if (mesh->owner)
 			pinned_release(mesh->owner, (size_t)mesh->owner_bytes);
 		std::memset(mesh, 0, sizeof(*mesh));
+	}
+}
+
+namespace upg
+{
+	int field_meshes_slab_device(Planet *planet, unsigned field_mask, int slab, int slabCount, upg_device_mesh *out3)
+	{
+		return field_meshes_impl(reinterpret_cast<upg_planet *>(planet), field_mask, 0, slab, slabCount, nullptr, out3);
 	}
 }

@@ -1029,7 +1029,11 @@ extern "C"
 
 	// the bake proper; outputs may be device or host memory (cudaMemcpyDefault).  dSpecial / dHeight are the images
 	// generateTextures* returns, dPbr / dNormal what the generator exports after K8; any of the four may be null.
-	static int bake_core(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, uint8_t *dPbr, uint8_t *dNormal, float normalStrength, void *cuda_stream)
+	}
+
+namespace upg
+{
+	int bake_core(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, uint8_t *dPbr, uint8_t *dNormal, float normalStrength, void *cuda_stream)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !dpos || !dnrm || !duv || !didx || !dAlbedo)
@@ -1239,6 +1243,10 @@ extern "C"
 		return rc;
 	}
 
+}
+
+extern "C"
+{
 	int upg_bake_device(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, void *cuda_stream)
 	{
 		if (!dSpecial || !dHeight)
@@ -1314,6 +1322,9 @@ extern "C"
 		int rc = check_mesh(uvs, nverts, idx, nidx, w, h, false);
 		if (rc)
 			return rc;
+		// a multi-device planet splits the rows over its devices (upg_multi.cu); bands of a few rows are not worth the fan-out
+		if (p->deviceCount > 1 && row1 - row0 >= 64u * (uint32_t)p->deviceCount)
+			return multi_bake(p, water, positions, normals, uvs, nverts, idx, nidx, w, h, row0, row1, albedo, special, heightMap, pbr, normalMap);
 		cudaError_t e = cudaSetDevice(p->device);
 		if (e != cudaSuccess)
 			return cuda_fail(e, "cudaSetDevice");
@@ -1385,4 +1396,15 @@ extern "C"
 	{
 		return upg_bake_rows(planet, water, positions, normals, uvs, nverts, idx, nidx, w, h, 0, h, albedo, special, heightMap);
 	}
+}
+
+namespace upg
+{
+	int check_bake_mesh(const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h)
+	{
+		return check_mesh(uvs, nverts, idx, nidx, w, h, false);
+	}
+	// the calling thread's upg_bake_last_covered_texels() value (the multi-device bake sums its workers' into the caller's)
+	uint64_t bake_thread_covered() { return t_lastCovered; }
+	void bake_set_thread_covered(uint64_t n) { t_lastCovered = n; }
 }

@@ -997,6 +997,15 @@ namespace upg
 		return rc;
 	}
 
+	int rebase_ids(uint32_t *ids, uint64_t n, uint32_t add, cudaStream_t s)
+	{
+		if (n == 0 || add == 0)
+			return UPG_OK;
+		dmc_rebase<<<(unsigned)((n + DMC_BLOCK - 1) / DMC_BLOCK), DMC_BLOCK, 0, s>>>(ids, n, 0u - add); // the kernel subtracts
+		const cudaError_t e = cudaGetLastError();
+		return e == cudaSuccess ? UPG_OK : cuda_fail(e, "rebase_ids");
+	}
+
 	void dmc_release(DmcResult &r, cudaStream_t s)
 	{
 		void *p[] = { r.rawVertices, r.positions, r.normals, r.indices, r.quads };

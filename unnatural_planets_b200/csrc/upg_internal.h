@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstddef>
 
+#include "../../include/upg.h"
 #include "upg_field.cuh"
 #include "upg_mem.h"
 #include "upg_planet_host.h"
@@ -28,6 +29,9 @@ namespace upg
 		int arithmetic = 0; // UPG_ARITH_* of include/upg.h: which build of the dense K1 kernels the sampling entry points launch
 		int deviceCount = 1; // devices that share the planet's work in the multi-device entry points
 		int devices[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // devices[0] == device
+		// multi-device planets: one single-device planet per further device (same modes, seeds and table; own status words and
+		// cellular table in that device's memory); children[0] is the planet itself
+		Planet *children[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 		// device: STATUS_SLOTS + 1 words, bit 0 of each = "a NaN sample was produced".  Word 0 is the sticky flag of the ASYNCHRONOUS
 		// device-pointer entry points (read and cleared by upg_planet_async_status); words 1.. are handed out one per synchronous
 		// call (StatusSlot), so that concurrent calls on one planet -- the generator's three field tasks and its chunk bakes,
@@ -146,5 +150,25 @@ namespace upg
 	double now_ms();
 
 	int launch_field(const Planet *planet, const FieldLaunch &L, cudaStream_t stream);
+
+	// ---- pieces of the single-device entry points the multi-device layer (upg_multi.cu) composes -------------------------------
+	// upg_field_meshes_slab_device for an internal planet pointer (slabCount 0 = the whole grid)
+	int field_meshes_slab_device(Planet *planet, unsigned field_mask, int slab, int slabCount, upg_device_mesh *out3);
+	// device-side result -> one pinned host block + the ABI struct (synchronises `s`)
+	int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out);
+	// ids[i] += add (mod 2^32) over n ids on `s`: slab-relative vertex ids -> ids of the stitched mesh
+	int rebase_ids(uint32_t *ids, uint64_t n, uint32_t add, cudaStream_t s);
+	// rows [row0, row1) of a bake with the mesh in device memory of the CURRENT device; outputs are host or device memory and hold
+	// (row1 - row0) rows (upg_bake.cu); synchronises `cuda_stream`
+	int bake_core(upg_planet *planet, int water, const float *dpos, const float *dnrm, const float *duv, uint32_t nverts, const uint32_t *didx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *dAlbedo, uint8_t *dSpecial, uint8_t *dHeight, uint8_t *dPbr, uint8_t *dNormal, float normalStrength, void *cuda_stream);
+	uint64_t bake_thread_covered();
+	void bake_set_thread_covered(uint64_t n);
+	int check_bake_mesh(const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h);
+
+	// multi-device layer (upg_multi.cu): planets created with upg_planet_desc::device_count > 1
+	int multi_setup(Planet *planet, const upg_planet_desc *desc);
+	void multi_teardown(Planet *planet);
+	int multi_field_meshes(Planet *planet, unsigned field_mask, unsigned stages, upg_mesh *out3);
+	int multi_bake(Planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t nverts, const uint32_t *idx, uint32_t nidx, uint32_t w, uint32_t h, uint32_t row0, uint32_t row1, uint8_t *albedo, uint8_t *special, uint8_t *heightMap, uint8_t *pbr, uint8_t *normalMap);
 	int check_status(Planet *planet, cudaStream_t stream, const char *what);
 }
