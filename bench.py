@@ -513,6 +513,62 @@ def run_ours(args, rank, world, local_rank):
             }
         del smeshes, src
 
+    # ---- leg 4b: the same planet over all GPUs from ONE process through the C ABI (upg_planet_desc::device_count, csrc/upg_multi.cu):
+    # rank 0 drives every GPU of the job, the other ranks wait at the barrier with their GPUs idle --------------------------------------
+    if args.sharded_grid > 0:
+        try:
+            del dmesh, outs
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            from unnatural_planets_b200 import synth as _synth
+
+            mres, mtex = args.sharded_grid, args.sharded_texture
+            mp = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=mres, devices=list(range(world)))
+            for _ in range(2):
+                mm = mp.field_meshes_clean(FIELDS)
+            mt = []
+            for _ in range(3):
+                mm = mp.field_meshes_clean(FIELDS)
+                mt.append(mp.last_call_s)
+            msrc = {}
+            for name in ("land", "water"):
+                uv = _synth.octahedral_uv(mm[name]["positions"])
+                msrc[name] = (mm[name]["positions"], mm[name]["normals"], uv, _synth.drop_folded_triangles(uv, mm[name]["indices"]))
+            mimg = {"land": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (3, 3, 3)], "water": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (4, 3, 3)]}
+            mtexels = [0]
+
+            def mbake(name, water):
+                pos, nrm, uv, idx = msrc[name]
+                o = mimg[name]
+                capi.check(L.upg_bake_export(mp._h, water, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), mtex, mtex, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr())))
+                mtexels[0] += int(L.upg_bake_last_covered_texels())
+
+            def mbake_both():
+                mtexels[0] = 0
+                ts = [threading.Thread(target=mbake, args=x) for x in (("land", 0), ("water", 1))]
+                [t.start() for t in ts]
+                [t.join() for t in ts]
+
+            mbake_both()
+            bt = []
+            for _ in range(3):
+                t = time.perf_counter()
+                mbake_both()
+                bt.append(time.perf_counter() - t)
+            m_ms, b_ms = statistics.median(mt) * 1e3, statistics.median(bt) * 1e3
+            multi_line = {
+                "what": "ONE planet over %d GPU(s) from ONE process through the C ABI (upg_planet_desc::device_count): upg_field_meshes_clean (z-slab per device, chunks gathered over NVLink per field, K9 + download on three devices) + 2 x upg_bake_export from two host threads (mesh parts uploaded per device and exchanged over NVLink, texel rows per device written straight into the pinned host images); host buffers, wall clock, median of three calls" % world,
+                "multi_device_planet_devices": world, "multi_device_planet_grid": mres, "multi_device_planet_texture": mtex,
+                "multi_device_planet_base_meshes_ms": m_ms, "multi_device_planet_bake_ms": b_ms, "multi_device_planet_ms": m_ms + b_ms,
+                "multi_device_planet_texels_per_s": mtexels[0] / (b_ms * 1e-3), "multi_device_planet_samples_per_s": 3.0 * mres**3 / (m_ms * 1e-3),
+            }
+            mp.close()
+            del mm, msrc, mimg
+        barrier()
+
     # ---- leg 5: a batch of planets back to back (BASELINE configs[3]: random base shape per seed, every elevation mode) ----
     batch_line = None
     if args.batch > 0:

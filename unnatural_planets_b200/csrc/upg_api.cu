@@ -102,6 +102,10 @@ namespace upg
 	}
 
 	static thread_local uint32_t *t_statusWord = nullptr;
+	static thread_local bool t_forceDense = false; // set while an entry point repeats a call whose band premise failed
+
+	bool force_dense_sampling() { return t_forceDense; }
+	void set_force_dense_sampling(bool on) { t_forceDense = on; }
 
 	uint32_t *status_word(const Planet *planet)
 	{
@@ -160,11 +164,13 @@ namespace upg
 			e = stream_sync(stream);
 		if (e != cudaSuccess)
 			return cuda_fail(e, what);
-		if (st & 1u)
+		if (st & 3u)
 		{
 			cudaMemsetAsync(word, 0, sizeof(uint32_t), stream);
 			stream_sync(stream);
-			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in %s", what);
+			if (st & 1u)
+				return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in %s", what);
+			return fail(UPG_ERR_BAND_INTERVAL, "an elevation left the interval band sampling assumes (%s)", what);
 		}
 		return UPG_OK;
 	}
@@ -954,9 +960,9 @@ namespace upg
 		// to back on the GPU after that and both sets of images come back at the end.  One after the other, the first call's colouring
 		// starts after half the time, the second upload hides behind it, and the first download hides behind the second colouring.
 		// UPG_UPLOAD_TURNS=0 switches it off (A/B in profiles/).
-		static std::mutex uploadTurn;
+		static std::mutex uploadTurn[64]; // one per device: uploads to different GPUs use different links and run side by side
 		static const bool turns = !(std::getenv("UPG_UPLOAD_TURNS") && std::getenv("UPG_UPLOAD_TURNS")[0] == '0');
-		std::unique_lock<std::mutex> turn(uploadTurn, std::defer_lock);
+		std::unique_lock<std::mutex> turn(uploadTurn[device & 63], std::defer_lock);
 		if (turns)
 			turn.lock();
 		std::vector<std::thread> pool;

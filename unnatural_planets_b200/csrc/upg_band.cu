@@ -323,6 +323,11 @@ namespace upg
 						const float base = L.water[idx];
 						// the dense kernel's expressions (upg_field.cuh, FD_ALL)
 						const float e10 = elevation_raw<ELEV>(P, pos) / 10.0f;
+						// run-time guard of the premise: every evaluated elevation must lie inside the interval the classification assumed
+						// (elevation_interval10: numeric suprema of the generators + 2 %).  One outside it means a settled node somewhere
+						// may carry the wrong sign: status bit 1 makes the entry point redo the call with dense sampling.
+						if (!(e10 >= lo && e10 <= hi) && !isnan_(e10))
+							atomicOr(L.status, 2u);
 						const float land = base - e10;
 						const float nav = base - fmax_(e10, 0.0f);
 						bool bad = false;
@@ -378,7 +383,7 @@ namespace upg
 	bool band_sampling_applies(const Planet *planet)
 	{
 		// a constant elevation needs no noise at all: the dense kernel is already a plain store
-		return planet->sampling == UPG_SAMPLING_BAND && planet->params.elevation != EL_NONE;
+		return planet->sampling == UPG_SAMPLING_BAND && planet->params.elevation != EL_NONE && !force_dense_sampling();
 	}
 
 	// land / navigation over z-slices [za, zb) given the water field of the same slices; asynchronous on `stream`

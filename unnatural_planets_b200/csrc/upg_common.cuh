@@ -46,6 +46,18 @@ namespace upg
 	UPG_HD float sub_rn(float a, float b) { return a - b; }
 #endif
 
+	// pow of a base that is known to be >= 0.  Exact build (and host): libm-grade powf, a few ulp from the CPU's (~45 instructions and a
+	// call; 10 % of the dense kernel's issue slots).  Contracted build: ex2(y * lg2(x)) on the special-function unit, relative error
+	// ~5e-7 for the arguments of the elevation curves -- the tolerance build states <= 1e-4 relative on the field (include/upg.h).
+	UPG_HD float pow_pos(float x, float y)
+	{
+#if defined(__CUDA_ARCH__) && UPG_ARITH_BUILD
+		return __powf(x, y);
+#else
+		return powf(x, y);
+#endif
+	}
+
 	// ---- cage scalar semantics (externals/cage/sources/include/cage-core/math.h:1021-1059, 798-809, 1173-1177) ----
 	// min/max are the ternaries the reference uses (NaN-order sensitive), NOT fminf/fmaxf.
 	UPG_HD float fmin_(float a, float b) { return a < b ? a : b; }

@@ -125,6 +125,11 @@ namespace upg
 	// K1b (upg_band.cu): land / navigation of slices [za, zb) from the water (= shape) field of the same slices, exact wherever the
 	// isosurface can see the value; asynchronous on `stream`.  `evaluated`: optional device counter of evaluated nodes.
 	bool band_sampling_applies(const Planet *planet);
+	// internal status code of check_status: an evaluated elevation was outside elevation_interval10 (band_sample_kernel's guard).  The
+	// mesh entry points catch it and repeat the call with dense sampling; it never reaches the caller.
+	constexpr int UPG_ERR_BAND_INTERVAL = 1000;
+	bool force_dense_sampling();
+	void set_force_dense_sampling(bool on);
 	// With `landBits` / `navigationBits` (zero-filled by the caller) the kernel also writes the sign / near-zero bits of both fields and,
 	// unless `fill`, stores sample VALUES only where it evaluated them (all that dmc_build reads).
 	int band_sample(const Planet *planet, int za, int zb, const float *water, float *land, float *navigation, unsigned long long *evaluated, cudaStream_t stream, const SignBits *landBits = nullptr, const SignBits *navigationBits = nullptr, bool fill = true, const float2 *rowMinMax = nullptr);

@@ -184,7 +184,16 @@ namespace upg
 		return f >= 0 ? (int32_t)f : (int32_t)f - 1;
 #endif
 	}
-	UPG_HD int32_t fast_round(float f) { return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f); }
+	// FastRound: f >= 0 ? (int)(f + 0.5f) : (int)(f - 0.5f).  On the device the select becomes the sign bit of f moved onto the 0.5 (one
+	// LOP3): same values for every input -- -0.0f takes the second branch here and the first in the library, both give 0; NaN converts to 0.
+	UPG_HD int32_t fast_round(float f)
+	{
+#if defined(__CUDA_ARCH__)
+		return (int32_t)(f + __uint_as_float((__float_as_uint(f) & 0x80000000u) | 0x3f000000u));
+#else
+		return f >= 0 ? (int32_t)(f + 0.5f) : (int32_t)(f - 0.5f);
+#endif
+	}
 	UPG_HD float nlerp(float a, float b, float t) { return a + t * (b - a); }
 	UPG_HD float interp_hermite(float t) { return t * t * (3 - 2 * t); }
 	UPG_HD float interp_quintic(float t) { return t * t * t * (t * (t * 6 - 15) + 10); }

@@ -622,7 +622,7 @@ namespace upg
 		{
 			ridge = noise3<NT_SIMPLEX, FT_RIDGED, 4>(E.n[2], pos);
 			ridge = fmax_(ridge - 0.1f, 0.0f);
-			ridge = powf(ridge, 1.6f);
+			ridge = pow_pos(ridge, 1.6f); // ridge >= 0 after the max above
 			ridge *= rm * cover;
 			ridge *= 1000;
 		}
@@ -679,7 +679,7 @@ namespace upg
 			{
 				float land = first * 0.5f + 0.5f;
 				land = saturate_(land);
-				land = 1 - powf(land, ELEV == EL_LAKES ? 1.24f : 0.83f);
+				land = 1 - pow_pos(land, ELEV == EL_LAKES ? 1.24f : 0.83f); // land is saturated to [0, 1]
 				land = land * 2 - 1;
 				land = land / (abs_(land) + 0.17f) + 0.15f;
 				land *= 150;
