@@ -397,11 +397,13 @@ extern "C"
 			e = stream_sync(s);
 		if (e != cudaSuccess)
 			return cuda_fail(e, "upg_planet_async_status");
-		if (st & 1u)
+		if (st & 3u)
 		{
 			cudaMemsetAsync(p->status, 0, sizeof(uint32_t), s);
 			stream_sync(s);
-			return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in an asynchronous sampling call");
+			if (st & 1u)
+				return fail(UPG_ERR_INVALID_VALUE, "invalid sdf value (NaN) in an asynchronous sampling call");
+			return fail(UPG_ERR_INVALID_VALUE, "upg_fields_samples_band_device: an elevation left the interval band sampling assumes; use the dense entry point for this planet");
 		}
 		return UPG_OK;
 	}
@@ -1043,6 +1045,23 @@ namespace upg
 		return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 	}
 
+	// Repeats `call` with dense sampling when band sampling's run-time guard fired (UPG_ERR_BAND_INTERVAL, upg_band.cu): the premise of
+	// the shortcut failed for this planet, the reference's way of filling the grid does not depend on it.
+	template<class F>
+	static int with_dense_retry(F call)
+	{
+		int rc = call();
+		if (rc == UPG_ERR_BAND_INTERVAL)
+		{
+			if (trace_enabled())
+				std::fprintf(stderr, "[upg] band sampling: an elevation left its interval, repeating the call with dense sampling\n");
+			set_force_dense_sampling(true);
+			rc = call();
+			set_force_dense_sampling(false);
+		}
+		return rc;
+	}
+
 	// copies a device-side DmcResult into one pinned host block and fills the ABI struct
 	int mesh_to_host(DmcResult &r, cudaStream_t s, upg_mesh *out)
 	{
@@ -1100,7 +1119,7 @@ namespace upg
 
 extern "C"
 {
-	int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out)
+	static int field_mesh_once(upg_planet *planet, int field, upg_mesh *out)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !out)
@@ -1185,7 +1204,18 @@ extern "C"
 	}
 
 	// slabCount == 0: the whole grid.  Exactly one of hostOut3 / deviceOut3 is given.
+	int upg_field_mesh(upg_planet *planet, int field, upg_mesh *out)
+	{
+		return with_dense_retry([&]() { return field_mesh_once(planet, field, out); });
+	}
+
+	static int field_meshes_once(upg_planet *planet, unsigned field_mask, unsigned stages, int slab, int slabCount, upg_mesh *out3, upg_device_mesh *deviceOut3);
 	static int field_meshes_impl(upg_planet *planet, unsigned field_mask, unsigned stages, int slab, int slabCount, upg_mesh *out3, upg_device_mesh *deviceOut3 = nullptr)
+	{
+		return with_dense_retry([&]() { return field_meshes_once(planet, field_mask, stages, slab, slabCount, out3, deviceOut3); });
+	}
+
+	static int field_meshes_once(upg_planet *planet, unsigned field_mask, unsigned stages, int slab, int slabCount, upg_mesh *out3, upg_device_mesh *deviceOut3)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || (!out3 && !deviceOut3))
@@ -1521,7 +1551,13 @@ extern "C"
 			*z1 = a + base + (slab < rem ? 1 : 0);
 	}
 
+	static int field_mesh_slab_once(upg_planet *planet, int field, int slab, int slab_count, upg_mesh *out);
 	int upg_field_mesh_slab(upg_planet *planet, int field, int slab, int slab_count, upg_mesh *out)
+	{
+		return with_dense_retry([&]() { return field_mesh_slab_once(planet, field, slab, slab_count, out); });
+	}
+
+	static int field_mesh_slab_once(upg_planet *planet, int field, int slab, int slab_count, upg_mesh *out)
 	{
 		Planet *p = reinterpret_cast<Planet *>(planet);
 		if (!p || !out)

@@ -20,6 +20,8 @@
 // warps that scan the rows.  Each block scans 32 grid rows, 1024 nodes (four per thread) at a time, and PUSHES the nodes to evaluate into a
 // shared-memory ring (ballot + warp prefix); whenever 256 are queued the whole block evaluates one node per thread, so the
 // expensive code always runs with full warps and exists once in the instruction stream.
+#include <cstdlib>
+
 #include "../../include/upg.h"
 #include "upg_internal.h"
 
@@ -403,8 +405,10 @@ namespace upg
 		L.zcount = (uint32_t)(zb - za);
 		L.rows = L.zcount * res;
 		L.z0 = (uint32_t)za;
-		L.lo = (float)lo;
-		L.hi = (float)hi;
+		// UPG_BAND_INTERVAL_SCALE (test hook): shrinks the assumed interval so that the run-time guard of the kernel fires
+		static const double scale = std::getenv("UPG_BAND_INTERVAL_SCALE") ? std::atof(std::getenv("UPG_BAND_INTERVAL_SCALE")) : 1.0;
+		L.lo = (float)(lo * scale);
+		L.hi = (float)(hi * scale);
 		// the float subtraction of the field and the one of the classification round independently (relative 2^-24 of values up to
 		// the box diagonal ~3500 + |hi|): 1/32 is two orders of magnitude above that and keeps every stored value at least 1/64 from zero,
 		// fifteen times the near-zero threshold 1e-3

@@ -58,6 +58,25 @@ namespace upg
 #endif
 	}
 
+	// a / b and sqrt(x) where the tolerance build may use the fast forms (no IEEE slow-path call inside the sample loop: a call makes the
+	// compiler rebuild the shared-memory window base of the gradient table after it).  Exact build and host: the IEEE operations.
+	UPG_HD float div_tol(float a, float b)
+	{
+#if defined(__CUDA_ARCH__) && UPG_ARITH_BUILD
+		return __fdividef(a, b);
+#else
+		return a / b;
+#endif
+	}
+	UPG_HD float sqrt_tol(float x)
+	{
+#if defined(__CUDA_ARCH__) && UPG_ARITH_BUILD
+		return x > 0.0f ? x * rsqrtf(x) : sqrtf(x); // rsqrt(0) is +inf: zero, negative and NaN inputs take the IEEE form
+#else
+		return sqrtf(x);
+#endif
+	}
+
 	// ---- cage scalar semantics (externals/cage/sources/include/cage-core/math.h:1021-1059, 798-809, 1173-1177) ----
 	// min/max are the ternaries the reference uses (NaN-order sensitive), NOT fminf/fmaxf.
 	UPG_HD float fmin_(float a, float b) { return a < b ? a : b; }

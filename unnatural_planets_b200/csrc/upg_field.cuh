@@ -225,7 +225,7 @@ namespace upg
 			// the expressions of sdf_sample_kernel
 			if (field == FD_ALL)
 			{
-				const float e10 = elev / 10.0f;
+				const float e10 = div_tol(elev, 10.0f);
 				const float land = base - e10;
 				const float nav = base - fmax_(e10, 0.0f);
 				if (L.out)
@@ -246,7 +246,7 @@ namespace upg
 			}
 			else
 			{
-				const float v = field == FD_ELEVATION_RAW ? elev : field == FD_NAVIGATION ? base - fmax_(elev / 10.0f, 0.0f) : base - elev / 10.0f;
+				const float v = field == FD_ELEVATION_RAW ? elev : field == FD_NAVIGATION ? base - fmax_(div_tol(elev, 10.0f), 0.0f) : base - div_tol(elev, 10.0f);
 				asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(v));
 				L.out[idx] = v;
 			}

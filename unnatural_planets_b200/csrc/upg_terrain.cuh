@@ -18,7 +18,7 @@ namespace upg
 	// ---- sources/math.cpp -----------------------------------------------------------------------
 	UPG_HD float smooth_min(float a, float b, float k)
 	{
-		const float h = saturate_((b - a) / k * 0.5f + 0.5f);
+		const float h = saturate_(div_tol(b - a, k) * 0.5f + 0.5f);
 		return lerp_(b, a, h) - k * h * (1 - h);
 	}
 	UPG_HD float smooth_max(float a, float b, float k) { return -smooth_min(-a, -b, k); }
@@ -37,7 +37,7 @@ namespace upg
 		const V3 c = normal * d;
 		return dot(normal, pos - c);
 	}
-	UPG_HD float sd_sphere(V3 pos, float radius) { return length(pos) - radius; }
+	UPG_HD float sd_sphere(V3 pos, float radius) { return sqrt_tol(dot(pos, pos)) - radius; }
 	UPG_HD float sd_capsule(V3 pos, float prolong, float radius)
 	{
 		V3 p = pos;
@@ -681,7 +681,7 @@ namespace upg
 				land = saturate_(land);
 				land = 1 - pow_pos(land, ELEV == EL_LAKES ? 1.24f : 0.83f); // land is saturated to [0, 1]
 				land = land * 2 - 1;
-				land = land / (abs_(land) + 0.17f) + 0.15f;
+				land = div_tol(land, abs_(land) + 0.17f) + 0.15f;
 				land *= 150;
 				return elevation_mountains(E, pos, land, maskColumn, terraceColumn);
 			}
