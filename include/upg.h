@@ -375,6 +375,18 @@ int upg_bake_export_device(upg_planet *planet, int water, const float *device_po
  * imageConvertHeigthToNormal's `strength` (> 0; the generator passes 1).  Either pair may be NULL. */
 int upg_texture_tail(int device, const uint8_t *special, const uint8_t *height_map, uint32_t width, uint32_t height, float strength, uint8_t *pbr, uint8_t *normal_map);
 
+/*
+ * K10: PNG encoding of an 8-bit image on the device -- what Image::exportFile(".png") does for the three textures of a chunk right
+ * after the texture tail (sources/generator.cpp:135-139, 187-191; externals/cage/sources/libcore/image/png.cpp -> libpng + zlib).
+ * `pixels`: width x height x channels bytes, tightly packed rows, host OR device memory of `device` (channels 1 grey, 2 grey + alpha,
+ * 3 RGB, 4 RGBA).  `out` (host memory, `capacity` >= upg_png_bound()) receives a complete PNG file of *size bytes: signature, IHDR,
+ * one IDAT chunk per 8 KiB deflate block, IEND.  Scanlines are filtered with libpng's minimum-sum heuristic; the zlib stream uses fixed
+ * Huffman codes over an 8 KiB window (faster and a little larger than zlib's default level).  Any PNG decoder returns the pixels bit
+ * for bit; the file bytes are not those of libpng.
+ */
+uint64_t upg_png_bound(uint32_t width, uint32_t height, uint32_t channels);
+int upg_png_encode(int device, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels, uint8_t *out, uint64_t capacity, uint64_t *size);
+
 /* coverage statistics of the last upg_bake on this thread: texels written by the rasteriser (= terrainTile evaluations;
  * the reference evaluates every (triangle, texel) visit, this library only the winning one) */
 uint64_t upg_bake_last_covered_texels(void);

@@ -86,11 +86,19 @@ for which in (0, 1):   # 0: the patch (GPU), 1: the reference's own generateText
     rc = L.upgshim_textures(which, 0, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), tex, tex, a.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p))
     assert rc == 0, L.upgshim_last_error()
     res[which] = (a, s, h)
+# the reference's own body a second time: sand texels draw their colour deviation from the thread RNG (SURVEY.md F7), so only the
+# texels it reproduces itself can be compared
+a2 = np.zeros((tex, tex, 3), np.uint8); s2 = np.zeros((tex, tex, 2), np.uint8); h2 = np.zeros((tex, tex, 1), np.uint8)
+assert L.upgshim_textures(1, 0, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), tex, tex, a2.ctypes.data_as(C.c_void_p), s2.ctypes.data_as(C.c_void_p), h2.ctypes.data_as(C.c_void_p)) == 0
+stable = (a2 == res[1][0]).all(axis=2)
 direct = p.bake(0, pos, nrm, uv, idx, tex, tex)
 out["textures"] = {"equal_to_direct_call": bool(all(np.array_equal(x, y) for x, y in zip(res[0], direct)))}
 for k, name in enumerate(("albedo", "special", "height")):
     d = np.abs(res[0][k].astype(np.int32) - res[1][k].astype(np.int32))
     out["textures"][name] = {"within_1": float((d <= 1).mean()), "max": int(d.max()), "covered": float((res[1][k] != 0).any(axis=2).mean())}
+    if name == "albedo":
+        out["textures"][name]["stable_fraction"] = float(stable.mean())
+        out["textures"][name]["within_1_on_stable"] = float((d.max(axis=2) <= 1)[stable].mean())
 print(json.dumps(out))
 """
 
@@ -106,10 +114,12 @@ def test_patched_entry_points_through_cage_types(shape, elev):
     for name, m in out["meshes"].items():
         # Holder<Mesh> of the patched meshGenerateBase* == the library's own result, bit for bit (which tests/test_gpu_fullsize.py and
         # tests/test_gpu_meshfix.py compare with the reference's makeMesh + meshRemoveDisconnected + meshFlipNormals)
-        assert m["equal"] and m["triangles"] > 1000, (name, m)
+        assert m["equal"], (name, m)
+        assert m["triangles"] > 1000 or name == "water", (name, m)  # the water culling may leave nothing (torus + craters: every vertex is above 0.1)
     t = out["textures"]
     assert t["equal_to_direct_call"]
     # against the reference's own generateTexturesLand in the same process: <= 1/255 per channel except the sand texels (the reference
     # draws their colour deviation from the thread RNG) and the libm threshold flips tests/test_gpu_bake.py enumerates
-    assert t["height"]["within_1"] > 0.995 and t["special"]["within_1"] > 0.99 and t["albedo"]["within_1"] > 0.90, t
+    assert t["height"]["within_1"] > 0.995 and t["special"]["within_1"] > 0.99, t
+    assert t["albedo"]["stable_fraction"] > 0.3 and t["albedo"]["within_1_on_stable"] > 0.99, t
     assert t["albedo"]["covered"] > 0.5

@@ -163,6 +163,9 @@ def load_library():
     L.upg_texture_tail.argtypes = [i32, fp, fp, u32, u32, C.c_float, fp, fp]
     L.upg_raster.argtypes = [i32, fp, u32, fp, u32, u32, u32, fp, fp, C.POINTER(u64)]
     L.upg_dilate.argtypes = [i32, fp, u32, u32, u32, u32, i32, fp]
+    L.upg_png_bound.argtypes = [u32, u32, u32]
+    L.upg_png_bound.restype = u64
+    L.upg_png_encode.argtypes = [i32, fp, u32, u32, u32, fp, u64, C.POINTER(u64)]
     _lib = L
     return L
 

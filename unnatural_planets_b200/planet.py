@@ -145,6 +145,26 @@ def memory_stats(device=0):
     return {"device_reserved": int(r.value), "device_used_high": int(u.value), "pinned_cached": int(h.value)}
 
 
+def png_encode(image, device=0):
+    """K10 (upg_png_encode): an (h, w[, ch]) uint8 image (host array) or a CUDA uint8 tensor of that shape -> bytes of a PNG file"""
+    L = capi.load_library()
+    if hasattr(image, "data_ptr"):  # torch tensor on the device
+        h, w = int(image.shape[0]), int(image.shape[1])
+        ch = int(image.shape[2]) if image.dim() == 3 else 1
+        ptr = C.c_void_p(image.data_ptr())
+        keep = image
+    else:
+        keep = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = keep.shape[:2]
+        ch = keep.shape[2] if keep.ndim == 3 else 1
+        ptr = _ptr(keep)
+    cap = int(L.upg_png_bound(w, h, ch))
+    out = np.empty(cap, dtype=np.uint8)
+    size = C.c_uint64(0)
+    capi.check(L.upg_png_encode(device, ptr, w, h, ch, _ptr(out), cap, C.byref(size)))
+    return out[: size.value].tobytes()
+
+
 class Planet:
     def __init__(self, shape="sphere", elevation="lakes", coloring="default", poles=False, flowers=False, seed=DEFAULT_SEED, grid=500, box=4000.0, device=0, mesh_sampling="band", arithmetic="exact", devices=None):
         L = capi.load_library()
