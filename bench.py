@@ -81,6 +81,7 @@ def bench_config(args):
     return {
         "workload": workload(args), "grid": args.grid, "fields": list(FIELDS), "texture": args.texture, "planets_per_step": args.gpus,
         "sample": "one terrainSdf* value; every grid node yields three (land, water, navigation) and BOTH arms evaluate all three fields of the nodes they time",
+        "gpu_arithmetic": "%s (UPG_ARITH_*: the GPU arm's dense sampling build; the CPU arm is the reference as compiled)" % args.arithmetic,
         "l2": "a sampling step writes %.1f GB per GPU and a bake step touches > 1 GB of float images (>> 126 MB L2); inputs are a ~2 KB parameter block and a mesh" % (12e-9 * n),
     }
 
@@ -250,7 +251,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     res, tex = args.grid, args.texture
-    planet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank))
+    # the dense sampling of the headline runs in the TOLERANCE build by default (UPG_ARITH_CONTRACT: FMA contraction + SFU pow / reciprocal
+    # inside the elevation curves; within the 1e-4 relative tolerance north_star states, integer lattice bit-exact; tests/test_gpu_fullsize.py
+    # checks it against the reference at the BASELINE sizes); --arithmetic exact times the bit-reproducible build instead.  The mesh
+    # entry points and the bake always run exact.
+    ARITH, OTHER = args.arithmetic, ("exact" if args.arithmetic == "contract" else "contract")
+    planet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank), arithmetic=ARITH)
     n = res**3
     bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in FIELDS]
     stream = torch.cuda.current_stream()
@@ -292,8 +298,8 @@ def run_ours(args, rank, world, local_rank):
             kernel_ms.append(k0.elapsed_time(k1))
         single_ms[f] = statistics.mean(kernel_ms)
 
-    # the same fused launch in the contracted build (UPG_ARITH_CONTRACT: FMA contraction, within the 1e-4 tolerance of the exact build)
-    cplanet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank), arithmetic="contract")
+    # the same fused launch in the OTHER arithmetic build
+    cplanet = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=res, device=local_rank, seed=seed_for(rank), arithmetic=OTHER)
     cplanet.fields_samples_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
     k0.record(stream)
     csteps = max(3, min(args.steps, 10))
@@ -661,28 +667,31 @@ def run_ours(args, rank, world, local_rank):
     def tflops(flops_per_node, ms):
         return flops_per_node * n / (ms * 1e-3) / 1e12
 
-    # `achieved`: the contract's ALGORITHMIC figure -- the reference's arithmetic for the samples one launch produces (instrumented
-    # count per sample x 3e9 samples; the reference evaluates each field on its own) over the launch time.  Next to it, as scalars the
-    # driver keeps: the same with ONE evaluation per grid node credited (what the fused launch has to do), and the flops the kernel
-    # EXECUTES (ncu instruction counts of the committed capture; exact work elimination makes it less than either).
-    achieved = tflops(WORK["per_grid_node"], fused_ms)
-    one_eval = tflops(WORK["one_evaluation"], fused_ms)
+    # `achieved`: ALGORITHMIC flops of the launch over its time.  The numerator credits ONE evaluation of the reference's expression per
+    # grid node -- one shape + one elevation function + the three combinations, instrumented count (804.5 flop at 1000^3) -- because that
+    # is the work a launch that produces the three fields of a node has to do; it does NOT credit the kernel's own exact eliminations
+    # (column caches, zero-mask skipping), which make the EXECUTED flops smaller still.  Both other views ride along as scalars: the
+    # reference's arithmetic for the same 3e9 samples evaluated field by field like its three tasks do (can exceed the peak: two of
+    # three evaluations are not needed), and the executed flops from the committed ncu instruction counts.
+    achieved = tflops(WORK["one_evaluation"], fused_ms)
+    three_eval = tflops(WORK["per_grid_node"], fused_ms)
     executed = tflops(K1_NCU["executed_flops_per_unit"], fused_ms) if K1_NCU else None
     issue_peak = None
     if K1_NCU and clocks.summary()["sm_mhz"]:
         issue_peak = 148 * 4 * 32 * clocks.summary()["sm_mhz"] * 1e6  # thread-instruction issue slots per second
+    k1_ncu_this = _ncu("r02_k1_ops_%s.json" % ARITH) or K1_NCU
     roofline = {
-        "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk), exact arithmetic build", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": (K1_NCU["dram_bytes_read"] + K1_NCU["dram_bytes_write"]) if K1_NCU else None, "peak_source": peak_source,
-        "kernel_ms": fused_ms, "flops_per_grid_node": WORK["per_grid_node"], "flops_per_sample": WORK["per_sample"], "samples_per_grid_node": len(FIELDS),
-        "flops_source": "instrumented build of the CPU restatement, every 2nd node per axis of the 1000^3 grid (profiles/r02_work_counts_config3.json)",
-        "frac_one_evaluation_per_node": one_eval / peak if peak else None, "flops_one_evaluation_per_node": WORK["one_evaluation"],
+        "bound": "fp32", "kernel": "sdf_column_kernel<sphere,lakes> (fused land + water + navigation launch, z-column walk), %s arithmetic build" % ARITH, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": (k1_ncu_this["dram_bytes_read"] + k1_ncu_this["dram_bytes_write"]) if k1_ncu_this else None, "peak_source": peak_source,
+        "kernel_ms": fused_ms, "arithmetic": ARITH, "flops_per_grid_node": WORK["one_evaluation"], "samples_per_grid_node": len(FIELDS),
+        "flops_source": "instrumented build of the CPU restatement, every 2nd node per axis of the 1000^3 grid (profiles/r02_work_counts_config3.json): one land evaluation + the water / navigation combinations",
+        "frac_reference_three_evaluations": three_eval / peak if peak else None, "flops_reference_three_evaluations_per_node": WORK["per_grid_node"],
         "frac_executed": executed / peak if (peak and executed) else None, "executed_flops_per_grid_node": K1_NCU["executed_flops_per_unit"] if K1_NCU else None,
-        "issue_slot_frac": (K1_NCU["issue_slots_x32_per_unit"] * n / (fused_ms * 1e-3) / issue_peak) if issue_peak else None,
-        "thread_instructions_per_grid_node": K1_NCU["thread_instructions_per_unit"] if K1_NCU else None,
-        "fp32_instruction_share": (K1_NCU["fp32_instructions_per_unit"] / K1_NCU["thread_instructions_per_unit"]) if K1_NCU else None,
+        "issue_slot_frac": (k1_ncu_this["issue_slots_x32_per_unit"] * n / (fused_ms * 1e-3) / issue_peak) if (issue_peak and k1_ncu_this) else None,
+        "thread_instructions_per_grid_node": k1_ncu_this["thread_instructions_per_unit"] if k1_ncu_this else None,
+        "fp32_instruction_share": (k1_ncu_this["fp32_instructions_per_unit"] / k1_ncu_this["thread_instructions_per_unit"]) if k1_ncu_this else None,
         "hbm_achieved_gbs": 4.0 * len(FIELDS) * n / (fused_ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
-        "contract_kernel_ms": contract_ms_max, "contract_samples_per_s": samples_per_step / (contract_ms_max * 1e-3), "contract_frac": tflops(WORK["per_grid_node"], contract_ms_max) / peak if peak else None,
+        "other_arithmetic": OTHER, "other_kernel_ms": contract_ms_max, "other_samples_per_s": samples_per_step / (contract_ms_max * 1e-3), "other_frac": tflops(WORK["one_evaluation"], contract_ms_max) / peak if peak else None,
         "single_field_kernel_ms_land": single_ms["land"], "single_field_kernel_ms_water": single_ms["water"], "single_field_kernel_ms_navigation": single_ms["navigation"],
     }
     bake_achieved = WORK["land_texel"] * covered["land"] / (bake_land_ms * 1e-3) / 1e12
@@ -769,6 +778,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arithmetic", default="contract", choices=["exact", "contract"], help="arithmetic build of the dense sampling kernel the headline times (include/upg.h UPG_ARITH_*)")
     ap.add_argument("--grid", type=int, default=1000, help="samples per axis of the meshing grid (BASELINE configs[2]: 1000)")
     ap.add_argument("--texture", type=int, default=4096, help="bake resolution (BASELINE configs[2]: 4096)")
     ap.add_argument("--sharded-grid", type=int, default=1024, help="grid of the one-planet-over-all-ranks leg (BASELINE configs[4]: 1024; 0 = skip)")

@@ -72,16 +72,20 @@ def check_field(p, ref, field, res, blocks, elev_mode):
     return bad_total, n_total
 
 
+@pytest.mark.parametrize("arithmetic", ["exact", "contract"])
 @pytest.mark.parametrize("shape,elev,res,slices", [("sphere", "lakes", 500, 32), ("torus", "craters", 500, 32), ("sphere", "lakes", 1000, 16)])
-def test_baseline_config_fields_against_reference(shape, elev, res, slices):
+def test_baseline_config_fields_against_reference(shape, elev, res, slices, arithmetic):
+    """both arithmetic builds of the dense kernel against the reference itself: `contract` (FMA contraction, SFU pow / reciprocal in the
+    elevation curves -- the build bench.py's headline times) has to meet the same tolerance as `exact`"""
     ref = ref_or_skip(shape=shape, elevation=elev)
-    p = Planet(shape=shape, elevation=elev, grid=res)
+    p = Planet(shape=shape, elevation=elev, grid=res, arithmetic=arithmetic)
     blocks = slice_blocks(res, slices)
     for field in ("land", "water", "navigation"):
         check_field(p, ref, field, res, blocks, elev)
-    # the shape of both planets has no transcendental: the water field is bit-exact
-    z0, z1 = blocks[-1]
-    assert same_bits(p.field_samples("water", z0, z1), ref.grid("water", res, z0=z0, z1=z1, threads=THREADS)).all()
+    if arithmetic == "exact":
+        # the shape of both planets has no transcendental: the water field is bit-exact
+        z0, z1 = blocks[-1]
+        assert same_bits(p.field_samples("water", z0, z1), ref.grid("water", res, z0=z0, z1=z1, threads=THREADS)).all()
 
 
 def assert_same(m, positions, normals, indices, what=""):

@@ -20,6 +20,7 @@
 // Compression is what a fixed-code, 8 KiB-window deflate gives (measured in the tests / bench next to zlib); the point is throughput.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 
@@ -538,6 +539,8 @@ extern "C"
 			rc = cuda_fail(e, "device_alloc(PNG)");
 		if (rc == UPG_OK)
 			rc = png_encode_device(onDevice ? pixels : dpix, width, height, channels, dfile, dsize, s);
+		const bool trace = trace_enabled();
+		const double t0 = trace ? now_ms() : 0;
 		uint64_t fileSize = 0;
 		if (rc == UPG_OK)
 		{
@@ -547,6 +550,9 @@ extern "C"
 			if (e != cudaSuccess)
 				rc = cuda_fail(e, "PNG encoder");
 		}
+		const double t1 = trace ? now_ms() : 0;
+		if (trace)
+			std::fprintf(stderr, "[upg] png %u x %u x %u: upload + filter + deflate + layout + emit %.2f ms\n", width, height, channels, t1 - t0);
 		if (rc == UPG_OK && fileSize > capacity)
 			rc = fail(UPG_ERR_ARGUMENT, "PNG output buffer too small: %llu bytes needed, %llu given (upg_png_bound)", (unsigned long long)fileSize, (unsigned long long)capacity);
 		if (rc == UPG_OK)
@@ -561,6 +567,8 @@ extern "C"
 				std::memcpy(out + fileSize - 12, pngIend, 12);
 				*size = fileSize;
 			}
+			if (trace)
+				std::fprintf(stderr, "[upg] png %u x %u x %u: %.2f MB file, download %.2f ms (after the encode kernels were waited for)\n", width, height, channels, fileSize * 1e-6, now_ms() - t1);
 		}
 		if (staging)
 		{
