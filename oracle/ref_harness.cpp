@@ -20,7 +20,17 @@
 #include <thread>
 #include <vector>
 
+// With -DUPREF_UPSTREAM_FASTNOISE (oracle/Makefile: `make ref FASTNOISE=/path/FastNoiseLite.h`) the include below resolves to the REAL
+// Auburn/FastNoiseLite header instead of shims/FastNoiseLite.h: the pin hook for the day the un-vendored submodule is available
+// (tools/fastnoise_pin.py diff-reports the restatement against it and extracts the Cellular table).  Its constant tables are private.
+#if defined(UPREF_UPSTREAM_FASTNOISE)
+#define private public
+#include <FastNoiseLite.h>
+#undef private
+#include "up_noise.h" // upo_noise_cfg of the harness' C interface
+#else
 #include <FastNoiseLite.h> // the shim (registry of constructed noise objects)
+#endif
 
 #include <cage-core/color.h>
 #include <cage-core/config.h>
@@ -60,11 +70,13 @@ namespace unnatural
 using namespace cage;
 using namespace unnatural;
 
+#if !defined(UPREF_UPSTREAM_FASTNOISE)
 std::vector<const FastNoiseLite *> &upo_shim_registry()
 {
 	static std::vector<const FastNoiseLite *> r;
 	return r;
 }
+#endif
 
 namespace
 {
@@ -192,6 +204,7 @@ extern "C"
 		}
 	}
 
+#if !defined(UPREF_UPSTREAM_FASTNOISE)
 	int upref_noise_count()
 	{
 		return (int)upo_shim_registry().size();
@@ -206,6 +219,50 @@ extern "C"
 		const FastNoiseLite *f = upo_shim_registry()[i];
 		for (int k = 0; k < n; k++)
 			out[k] = f->GetNoise(pos[k * 3 + 0], pos[k * 3 + 1], pos[k * 3 + 2]);
+	}
+#else
+	// the real library keeps no registry of its objects
+	int upref_noise_count() { return 0; }
+	void upref_noise_get(int, upo_noise_cfg *) {}
+	void upref_noise_eval(int, const float *, int, float *) {}
+#endif
+	// 1 when this library was built against the real Auburn/FastNoiseLite header, 0 for the restatement (shims/FastNoiseLite.h)
+	int upref_fastnoise_is_upstream()
+	{
+#if defined(UPREF_UPSTREAM_FASTNOISE)
+		return 1;
+#else
+		return 0;
+#endif
+	}
+	// one FastNoiseLite object configured the way cage configures it (libcore/noiseFunction.cpp:97-107), evaluated at n points: the
+	// common ground on which the restatement and the real header are compared generator by generator (tools/fastnoise_pin.py)
+	void upref_fastnoise_eval(const upo_noise_cfg *c, const float *pos, int n, int dims, float *out)
+	{
+		FastNoiseLite f(c->seed);
+		static const FastNoiseLite::NoiseType types[] = { FastNoiseLite::NoiseType_OpenSimplex2, FastNoiseLite::NoiseType_OpenSimplex2S, FastNoiseLite::NoiseType_Cellular, FastNoiseLite::NoiseType_Perlin, FastNoiseLite::NoiseType_ValueCubic, FastNoiseLite::NoiseType_Value };
+		f.SetFrequency(c->frequency);
+		f.SetNoiseType(types[c->type]);
+		f.SetFractalType((FastNoiseLite::FractalType)c->fractal);
+		f.SetFractalOctaves(c->octaves);
+		f.SetFractalLacunarity(c->lacunarity);
+		f.SetFractalGain(c->gain);
+		f.SetCellularDistanceFunction((FastNoiseLite::CellularDistanceFunction)c->distance);
+		f.SetCellularReturnType((FastNoiseLite::CellularReturnType)c->operation);
+		for (int k = 0; k < n; k++)
+			out[k] = dims == 2 ? f.GetNoise(pos[k * 3 + 0], pos[k * 3 + 1]) : f.GetNoise(pos[k * 3 + 0], pos[k * 3 + 1], pos[k * 3 + 2]);
+	}
+	// the 256 x 4 jitter table of the Cellular generator this library evaluates with: upstream's constant, or the declared substitute
+	void upref_cellular_table(float *out1024)
+	{
+#if defined(UPREF_UPSTREAM_FASTNOISE)
+		for (int i = 0; i < 1024; i++)
+			out1024[i] = FastNoiseLite::Lookup<float>::RandVecs3D[i];
+#else
+		const float *t = upo_randvecs3d();
+		for (int i = 0; i < 1024; i++)
+			out1024[i] = t[i];
+#endif
 	}
 
 	int upref_eval(int what, const float *pos, int n, float *out)

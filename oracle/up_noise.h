@@ -12,7 +12,8 @@
  * PARITY STATUS: "parity unpinned" for noise VALUES -- the reference's own noise test
  * (externals/cage/sources/test-core/noiseFunction.cpp:18-157) asserts nothing, and the
  * pinned source cannot be fetched.  Structural checks (range, continuity across lattice
- * cells, hash known-answers derived by hand) live in tests/test_oracle_noise.py.
+ * cells, hash known-answers derived by hand) live in tests/test_oracle_port.py; tools/fastnoise_pin.py
+ * diff-reports this file against the real header generator by generator the day it is available (make -C oracle ref FASTNOISE=...).
  * The Cellular generator needs upstream's 256-entry RandVecs3D constant table, which cannot
  * be reconstructed; `upo_randvecs3d()` below is a DECLARED SUBSTITUTE (deterministic unit
  * vectors from a splitmix64 stream).  Every Cellular-dependent result is therefore

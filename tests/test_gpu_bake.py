@@ -350,3 +350,39 @@ def test_bake_export_is_bake_plus_tail_and_shards_by_rows(water):
     parts = [p.bake_export(water, pos, nrm, uv, idx, 192, 192, r0, r1) for r0, r1 in zip(cuts[:-1], cuts[1:])]
     for k, whole in enumerate((a2, pbr, nmap)):
         assert (np.concatenate([q[k] for q in parts], axis=0) == whole).all(), k
+
+
+def test_tile_outliers_are_discontinuities_of_the_reference():
+    """the tolerance tests above accept a small fraction of tiles outside 2e-4 / 1/255.  Here every such tile of a
+    40 000-tile live comparison is ENUMERATED and must carry a witness of its cause: the reference's own terrainTile jumps by at least as
+    much within a few centimetres of the tile position (a threshold -- biome class, `bf < 1e-7` early-out, cover / beach masks -- sits
+    within the libm ulps that separate CPU and GPU).  A tile whose GPU value is off although the reference is smooth around it would be
+    a real error: none is allowed.  The deviation of an explained tile is capped by the size of the reference's own jump."""
+    cfg = ("sphere", "lakes", "default", True, True)
+    ref = ref_planet(cfg)
+    pos, nrm = bc.tile_probes("sphere", n=40000, seed=123)
+    p = make_planet(cfg)
+    cols = [0, 1, 2, 3, 4, 5, 10]  # what the textures store: albedo, roughness, metallic, height, opacity
+    report = {}
+    for purpose in ("land", "water"):
+        got = p.tiles(purpose, pos, nrm)
+        want = ref.tiles_seeded(purpose, pos, nrm)
+        d = np.abs(got[:, cols].astype(np.float64) - want[:, cols]).max(axis=1)
+        out = np.flatnonzero(d > 1 / 255)
+        assert len(out) <= len(pos) * 0.003
+        unexplained = []
+        if len(out):
+            # the reference on a cloud of displaced copies of every outlier (the normal stays): 14 directions x 3 radii
+            dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [1, 1, 1], [-1, -1, -1], [1, -1, 1], [-1, 1, -1], [1, 1, -1], [-1, -1, 1], [-1, 1, 1], [1, -1, -1]], np.float32)
+            dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+            jump = np.zeros(len(out))
+            for eps in (2e-3, 2e-2, 1e-1):
+                for dv in dirs:
+                    moved = ref.tiles_seeded(purpose, pos[out] + dv * np.float32(eps), nrm[out])
+                    jump = np.maximum(jump, np.abs(moved[:, cols].astype(np.float64) - want[out][:, cols]).max(axis=1))
+            for k, i in enumerate(out):
+                if jump[k] < 0.5 * d[i]:
+                    unexplained.append((int(i), float(d[i]), float(jump[k])))
+        report[purpose] = (len(out), len(unexplained))
+        assert not unexplained, (purpose, len(out), unexplained[:5])
+    print("tile outliers (count, unexplained):", report)
