@@ -36,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 _STDOUT = sys.stdout
+_CPU_GROUP = None
 METRIC = "sdf_samples_per_s"
 UNIT = "samples/s"
 FIELDS = ("land", "water", "navigation")
@@ -528,6 +529,13 @@ def run_ours(args, rank, world, local_rank):
             pass
         torch.cuda.empty_cache()
         barrier()
+
+        def cpu_barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier(group=_CPU_GROUP)
+
+        cpu_barrier()
         if rank == 0:
             from unnatural_planets_b200 import synth as _synth
 
@@ -573,6 +581,7 @@ def run_ours(args, rank, world, local_rank):
             }
             mp.close()
             del mm, msrc, mimg
+        cpu_barrier()
         barrier()
 
     # ---- leg 5: a batch of planets back to back (BASELINE configs[3]: random base shape per seed, every elevation mode) ----
@@ -701,7 +710,7 @@ def run_ours(args, rank, world, local_rank):
         "note": "texels = covered texels (one terrainTile each; the reference evaluates every (triangle, texel) visit) of the land (3+2+1 ch) and water (4+2+1 ch) surfaces; UVs: synthetic octahedral chart",
         "e2e": {"value": texels_all / (bake_e2e_ms * 1e-3), "unit": "texels/s", "h2d_bytes_per_step": int(h2d_bake), "d2h_bytes_per_step": int(d2h_bake), "path": "upg_bake_export: host mesh -> device, pinned host albedo / pbr / normal-map images <- device, wall clock"},
         "roofline": {"bound": "fp32", "kernel": "tile_color_kernel<default> + its K1 probes (land bake, whole upg_bake_device call)", "achieved": bake_achieved, "peak": peak, "unit": "TFLOP/s", "frac": bake_achieved / peak if peak else None,
-                     "traffic": (K6_NCU["dram_bytes_read"] + K6_NCU["dram_bytes_write"]) if K6_NCU else None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": WORK["land_texel"], "fp64_flops_per_texel": WORK["land_texel_fp64"]},
+                     "traffic": (K6_NCU["dram_bytes_per_unit"] * covered["land"]) if K6_NCU else None, "peak_source": peak_source, "call_ms": bake_land_ms, "flops_per_texel": WORK["land_texel"], "fp64_flops_per_texel": WORK["land_texel_fp64"]},
     }
     # the second half of the metric and the planet times as SCALARS inside `roofline` (the driver's record keeps scalars there)
     roofline.update({
@@ -805,6 +814,10 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a CPU-side group: while rank 0 drives EVERY GPU of the job (the multi-device leg) the other ranks must wait without an NCCL
+        # kernel spinning on their GPUs
+        global _CPU_GROUP
+        _CPU_GROUP = dist.new_group(backend="gloo")
     try:
         run_ours(args, rank, world, local_rank)
     finally:

@@ -166,6 +166,20 @@ namespace upg
 #ifndef UPG_COLUMN_MIN_BLOCKS
 #define UPG_COLUMN_MIN_BLOCKS 5 // resident blocks per SM the register allocation aims at (A/B in profiles/)
 #endif
+	// the samples are written once and never read by this kernel: UPG_K1_STORE = 1 marks the stores streaming (st.global.cs, evict
+	// first), 0 = plain stores (A/B in profiles/: DRAM traffic per node and time)
+#ifndef UPG_K1_STORE
+#define UPG_K1_STORE 0
+#endif
+	__device__ __forceinline__ void store_sample(float *p, float v)
+	{
+#if UPG_K1_STORE == 1
+		__stcs(p, v);
+#else
+		*p = v;
+#endif
+	}
+
 	template<int SHAPE, int ELEV, int ARITH = UPG_ARITH_BUILD>
 	__global__ void __launch_bounds__(FIELD_BLOCK, UPG_COLUMN_MIN_BLOCKS) sdf_column_kernel(const __grid_constant__ PlanetParams P, const __grid_constant__ FieldLaunch L)
 	{
@@ -230,17 +244,17 @@ namespace upg
 				const float nav = base - fmax_(e10, 0.0f);
 				if (L.out)
 				{
-					L.out[idx] = land;
+					store_sample(L.out + idx, land);
 					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(land));
 				}
 				if (L.outWater)
 				{
-					L.outWater[idx] = base;
+					store_sample(L.outWater + idx, base);
 					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(base));
 				}
 				if (L.outNavigation)
 				{
-					L.outNavigation[idx] = nav;
+					store_sample(L.outNavigation + idx, nav);
 					asm("max.NaN.f32 %0, %0, %1;" : "+f"(nanAcc) : "f"(nav));
 				}
 			}
