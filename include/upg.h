@@ -387,6 +387,11 @@ int upg_texture_tail(int device, const uint8_t *special, const uint8_t *height_m
 uint64_t upg_png_bound(uint32_t width, uint32_t height, uint32_t channels);
 int upg_png_encode(int device, const uint8_t *pixels, uint32_t width, uint32_t height, uint32_t channels, uint8_t *out, uint64_t capacity, uint64_t *size);
 
+/* K5..K8 + K10 in one call: what a chunk task does between meshUnwrap and the end of its three exportFile calls (sources/generator.cpp:
+ * 131-139): bake, texture tail, and the PNG FILES of albedo (RGB / RGBA for water), pbr and normal map.  out3[k] (host memory, capacity3[k]
+ * >= upg_png_bound(width, height, channels)) receives file k, size3[k] its length.  The images exist uncompressed only in HBM. */
+int upg_bake_export_png(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint8_t *const out3[3], const uint64_t capacity3[3], uint64_t size3[3]);
+
 /* coverage statistics of the last upg_bake on this thread: texels written by the rasteriser (= terrainTile evaluations;
  * the reference evaluates every (triangle, texel) visit, this library only the winning one) */
 uint64_t upg_bake_last_covered_texels(void);

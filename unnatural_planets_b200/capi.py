@@ -166,6 +166,7 @@ def load_library():
     L.upg_png_bound.argtypes = [u32, u32, u32]
     L.upg_png_bound.restype = u64
     L.upg_png_encode.argtypes = [i32, fp, u32, u32, u32, fp, u64, C.POINTER(u64)]
+    L.upg_bake_export_png.argtypes = [vp, i32, fp, fp, fp, u32, fp, u32, u32, u32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     _lib = L
     return L
 

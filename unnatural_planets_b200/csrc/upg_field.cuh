@@ -60,6 +60,97 @@ namespace upg
 	}
 
 #if defined(__CUDACC__)
+	// ---- craters: the Voronoi points of a block's neighbourhood, computed once per block -------------------------------------------------
+	// Voronoi::evaluate (sources/voronoi.cpp:45-91) generates the feature points of the 27 cells around the sample from an integer hash
+	// chain -- 81 murmur mixes and 54 points per sample, ~7 000 instructions, nearly all of the `craters` elevation.  The 256 samples of
+	// a block are consecutive nodes of one grid row (8 units apart on the 500^3 grid against cells of 300 units): their neighbourhoods
+	// overlap almost entirely.  So the block computes the points of the UNION of its samples' neighbourhoods once (each thread hashes
+	// a cell or two) into shared memory, and every sample walks its own 27 cells in the reference's z / y / x / point order over that
+	// table: the same points, the same distances, the same strict-less comparisons -- bit-identical -- for ~1/30 of the hashing.
+	// Blocks whose samples span too many cells (the block that wraps from the end of one slice to the start of the next) and Voronoi
+	// instances with more than two points per cell take the per-sample search.
+	constexpr int CRATER_MAX_CELLS = 160;
+	constexpr int CRATER_MAX_POINTS = 2;
+	struct CraterTable
+	{
+		float x[CRATER_MAX_CELLS * CRATER_MAX_POINTS], y[CRATER_MAX_CELLS * CRATER_MAX_POINTS], z[CRATER_MAX_CELLS * CRATER_MAX_POINTS];
+		int32_t lo[3], hi[3]; // cell range of the block's samples (base cells), inclusive
+	};
+
+	// all threads of the block call this (barriers inside); `live` = the thread has a sample.  Returns false (for the whole block) when the
+	// table does not apply; otherwise `nearest` = what voronoi_nearest<1, false> returns for `pos`.
+	__device__ __forceinline__ bool craters_block_nearest(const VoronoiInst &v, V3 pos, bool live, CraterTable &T, V3 &nearest)
+	{
+		const V3 pf = pos * v.frequency;
+		const I3 base = I3{ (int32_t)pf.x, (int32_t)pf.y, (int32_t)pf.z };
+		if (threadIdx.x == 0)
+		{
+			T.lo[0] = T.lo[1] = T.lo[2] = 0x7fffffff;
+			T.hi[0] = T.hi[1] = T.hi[2] = (int32_t)0x80000000;
+		}
+		__syncthreads();
+		// warp-level extremes first, one shared atomic per warp and bound
+		const int32_t big = 0x7fffffff, small = (int32_t)0x80000000;
+		const int32_t c[3] = { base.x, base.y, base.z };
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+		{
+			const int32_t mn = __reduce_min_sync(0xffffffffu, live ? c[a] : big), mx = __reduce_max_sync(0xffffffffu, live ? c[a] : small);
+			if ((threadIdx.x & 31u) == 0)
+			{
+				atomicMin(&T.lo[a], mn);
+				atomicMax(&T.hi[a], mx);
+			}
+		}
+		__syncthreads();
+		// the union of the 27-cell neighbourhoods: [lo - 1, hi + 1] per axis
+		const int32_t ox = T.lo[0] - 1, oy = T.lo[1] - 1, oz = T.lo[2] - 1;
+		const int64_t nx = (int64_t)T.hi[0] - T.lo[0] + 3, ny = (int64_t)T.hi[1] - T.lo[1] + 3, nz = (int64_t)T.hi[2] - T.lo[2] + 3;
+		if (v.pointsPerCell > (uint32_t)CRATER_MAX_POINTS || nx * ny * nz > CRATER_MAX_CELLS || nx <= 0 || ny <= 0 || nz <= 0)
+			return false; // uniform: every thread read the same bounds
+		const int32_t cells = (int32_t)(nx * ny * nz);
+		for (int32_t k = (int32_t)threadIdx.x; k < cells; k += (int32_t)blockDim.x)
+		{
+			const int32_t cx = k % (int32_t)nx, cy = (k / (int32_t)nx) % (int32_t)ny, cz = k / (int32_t)(nx * ny);
+			const I3 cell = I3{ ox + cx, oy + cy, oz + cz };
+			I3 s = voronoi_mix(v, cell); // genCell: s = mix(cell); per point s = mix(s) (sources/voronoi.cpp:28-41)
+			for (uint32_t i = 0; i < v.pointsPerCell; i++)
+			{
+				s = voronoi_mix(v, s);
+				const V3 p = voronoi_point(v, s, cell);
+				T.x[k * CRATER_MAX_POINTS + i] = p.x;
+				T.y[k * CRATER_MAX_POINTS + i] = p.y;
+				T.z[k * CRATER_MAX_POINTS + i] = p.z;
+			}
+		}
+		__syncthreads();
+		// voronoi_nearest<1, false>: z, y, x, point order; strict less, so the earlier point keeps a tie
+		float best = INFINITY;
+		nearest = v3(0, 0, 0);
+		if (live)
+		{
+			for (int32_t dz = -1; dz < 2; dz++)
+				for (int32_t dy = -1; dy < 2; dy++)
+				{
+					const int32_t row = ((base.z + dz - oz) * (int32_t)ny + (base.y + dy - oy)) * (int32_t)nx + (base.x - 1 - ox);
+#pragma unroll
+					for (int32_t dx = 0; dx < 3; dx++)
+						for (uint32_t i = 0; i < v.pointsPerCell; i++)
+						{
+							const int32_t at = (row + dx) * CRATER_MAX_POINTS + (int32_t)i;
+							const V3 p = v3(T.x[at], T.y[at], T.z[at]);
+							const float d = distance_squared(p, pos);
+							if (d < best)
+							{
+								best = d;
+								nearest = p;
+							}
+						}
+				}
+		}
+		return true;
+	}
+
 	// status word: bit 0 = a NaN sample was produced (the reference throws "invalid ... sdf value",
 	// sources/modesConfiguration.cpp:255-256; the host layer turns the flag into UPG_ERR_INVALID_VALUE)
 	// ARITH = the arithmetic build of the translation unit (UPG_ARITH_BUILD): part of the kernel's TYPE, so that the exact and the contracted
@@ -70,10 +161,16 @@ namespace upg
 		grad_table_init<FIELD_BLOCK>(); // shared-memory gradient table of the Perlin / OpenSimplex generators (upg_noise.cuh)
 		__syncthreads();
 		const uint64_t idx = (uint64_t)blockIdx.x * FIELD_BLOCK + threadIdx.x;
-		if (idx >= L.count)
+		// grid launches of the `craters` mode keep every thread of the block until the shared Voronoi table is built
+		constexpr bool CRATERS = ELEV == EL_CRATERS;
+		const bool cratersGrid = CRATERS && !L.positions;
+		const bool live = idx < L.count;
+		if (!live && !cratersGrid)
 			return;
 		V3 pos;
-		if (L.positions)
+		if (!live)
+			pos = v3(0, 0, 0);
+		else if (L.positions)
 		{
 			// explicit positions (parity probes, water-vertex culling of sources/meshGeneration.cpp:62-68)
 			pos = v3(L.positions[idx * 3 + 0], L.positions[idx * 3 + 1], L.positions[idx * 3 + 2]);
@@ -92,10 +189,21 @@ namespace upg
 		// (sources/modesConfiguration.cpp:230-279).
 		const int field = L.field;
 		float base = 0, elev = 0;
+		const bool needElevation = field != FD_WATER && field != FD_ELEVATION;
+		V3 nearest = v3(0, 0, 0);
+		bool haveNearest = false;
+		if constexpr (CRATERS)
+		{
+			__shared__ CraterTable craterTable;
+			if (cratersGrid && needElevation) // block-uniform
+				haveNearest = craters_block_nearest(P.el.voronoi, pos, live, craterTable, nearest);
+			if (!live)
+				return;
+		}
 		if (field != FD_ELEVATION_RAW)
 			base = shape_sdf<SHAPE>(P, pos);
-		if (field != FD_WATER && field != FD_ELEVATION)
-			elev = elevation_raw<ELEV>(P, pos);
+		if (needElevation)
+			elev = haveNearest ? elevation_raw_given<ELEV>(P, pos, 0.0f, nullptr, nullptr, &nearest) : elevation_raw<ELEV>(P, pos);
 		if (field == FD_ALL)
 		{
 			// land, water and navigation of the same sample share the shape and the elevation: the generator asks for all three

@@ -583,4 +583,101 @@ extern "C"
 		cs.close();
 		return rc;
 	}
+
+	// K5..K8 + K10: the complete texture export of one chunk.  The three images never exist uncompressed in host memory: bake and texture
+	// tail write them to HBM, the encoder compresses them there, the files come down the link (about half the bytes of the raw images).
+	int upg_bake_export_png(upg_planet *planet, int water, const float *positions, const float *normals, const float *uvs, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, uint32_t width, uint32_t height, uint8_t *const out3[3], const uint64_t capacity3[3], uint64_t size3[3])
+	{
+		Planet *p = reinterpret_cast<Planet *>(planet);
+		if (!p || !positions || !normals || !out3 || !capacity3 || !size3 || !out3[0] || !out3[1] || !out3[2])
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		size3[0] = size3[1] = size3[2] = 0;
+		int rc = check_bake_mesh(uvs, vertex_count, indices, index_count, width, height);
+		if (rc)
+			return rc;
+		cudaError_t e = cudaSetDevice(p->device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		rc = cs.open();
+		if (rc)
+			return rc;
+		cudaStream_t s = cs.compute;
+		const uint32_t channels[3] = { water ? 4u : 3u, 3u, 3u };
+		const uint64_t texels = (uint64_t)width * height;
+		float *dpos = nullptr, *dnrm = nullptr, *duv = nullptr;
+		uint32_t *didx = nullptr;
+		uint8_t *image[3] = { nullptr, nullptr, nullptr }, *file[3] = { nullptr, nullptr, nullptr };
+		uint64_t *dsize = nullptr;
+		e = device_alloc(&dpos, sizeof(float) * 3 * (size_t)vertex_count, s);
+		if (e == cudaSuccess)
+			e = device_alloc(&dnrm, sizeof(float) * 3 * (size_t)vertex_count, s);
+		if (e == cudaSuccess)
+			e = device_alloc(&duv, sizeof(float) * 2 * (size_t)vertex_count, s);
+		if (e == cudaSuccess)
+			e = device_alloc(&didx, sizeof(uint32_t) * (size_t)index_count, s);
+		for (int k = 0; k < 3 && e == cudaSuccess; k++)
+		{
+			e = device_alloc(&image[k], texels * channels[k], s);
+			if (e == cudaSuccess)
+				e = device_alloc(&file[k], png_bound(width, height, channels[k]), s);
+		}
+		if (e == cudaSuccess)
+			e = device_alloc(&dsize, sizeof(uint64_t) * 3, s);
+		if (e != cudaSuccess)
+			rc = cuda_fail(e, "device_alloc(export)");
+		void *staging = nullptr;
+		size_t stagingCapacity = 0;
+		if (rc == UPG_OK)
+		{
+			const HostArray arrays[4] = { { duv, uvs, sizeof(float) * 2 * (size_t)vertex_count }, { didx, indices, sizeof(uint32_t) * (size_t)index_count }, { dpos, positions, sizeof(float) * 3 * (size_t)vertex_count }, { dnrm, normals, sizeof(float) * 3 * (size_t)vertex_count } };
+			rc = upload_host_arrays(arrays, 4, s, &staging, &stagingCapacity);
+		}
+		// albedo, pbr and normal map in HBM (bake_core's outputs may be device memory)
+		if (rc == UPG_OK)
+			rc = bake_core(planet, water, dpos, dnrm, duv, vertex_count, didx, index_count, width, height, 0, height, image[0], nullptr, nullptr, image[1], image[2], 1.f, s);
+		for (int k = 0; k < 3 && rc == UPG_OK; k++)
+			rc = png_encode_device(image[k], width, height, channels[k], file[k], dsize + k, s);
+		uint64_t sizes[3] = { 0, 0, 0 };
+		if (rc == UPG_OK)
+		{
+			e = cudaMemcpyAsync(sizes, dsize, sizeof(sizes), cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess)
+				e = stream_sync(s);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "PNG encoder");
+		}
+		for (int k = 0; k < 3 && rc == UPG_OK; k++)
+			if (sizes[k] > capacity3[k])
+				rc = fail(UPG_ERR_ARGUMENT, "PNG output buffer %d too small: %llu bytes needed, %llu given (upg_png_bound)", k, (unsigned long long)sizes[k], (unsigned long long)capacity3[k]);
+		for (int k = 0; k < 3 && rc == UPG_OK; k++)
+		{
+			e = cudaMemcpyAsync(out3[k], file[k], sizes[k] - 12, cudaMemcpyDefault, s);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "PNG download");
+		}
+		if (rc == UPG_OK)
+		{
+			e = stream_sync(s);
+			if (e != cudaSuccess)
+				rc = cuda_fail(e, "PNG download");
+		}
+		for (int k = 0; k < 3 && rc == UPG_OK; k++)
+		{
+			std::memcpy(out3[k] + sizes[k] - 12, pngIend, 12);
+			size3[k] = sizes[k];
+		}
+		if (staging)
+		{
+			stream_sync(s);
+			pinned_block_release(staging, stagingCapacity);
+		}
+		void *all[] = { dpos, dnrm, duv, didx, image[0], image[1], image[2], file[0], file[1], file[2], dsize };
+		for (void *q : all)
+			if (q)
+				device_free(q, s);
+		stream_sync(s);
+		cs.close();
+		return rc;
+	}
 }

@@ -648,8 +648,10 @@ namespace upg
 	};
 
 	// elevation_raw with that first noise value handed in (`first` is ignored by the other modes)
+	// `cratersNearest`: the nearest Voronoi point of `pos` when the caller already has it (the dense kernel finds it from a table of
+	// points its block shares, upg_field.cuh), or null = search the 27 cells here
 	template<int ELEV>
-	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first, PerlinColumn *maskColumn = nullptr, PerlinFbmColumn<3> *terraceColumn = nullptr)
+	UPG_HD float elevation_raw_given(const PlanetParams &P, V3 pos, float first, PerlinColumn *maskColumn = nullptr, PerlinFbmColumn<3> *terraceColumn = nullptr, const V3 *cratersNearest = nullptr)
 	{
 		const ElevationConsts &E = P.el;
 		switch (ELEV)
@@ -688,7 +690,10 @@ namespace upg
 			case EL_CRATERS:
 			{
 				V3 c;
-				voronoi_nearest<1, false>(E.voronoi, pos, v3(0, 0, 0), &c);
+				if (cratersNearest)
+					c = *cratersNearest;
+				else
+					voronoi_nearest<1, false>(E.voronoi, pos, v3(0, 0, 0), &c);
 				const float s = 100 + noise3<NT_VALUE, FT_NONE, 3>(E.n[0], c) * 50;
 				const float d = distance(pos, c);
 				const float x = saturate_(d / s);

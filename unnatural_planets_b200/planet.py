@@ -398,6 +398,26 @@ class Planet:
         self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
         return albedo, pbr, nmap
 
+    def bake_export_png(self, water, positions, normals, uvs, indices, w, h, out=None):
+        """upg_bake_export_png: the three PNG files of a chunk (albedo, pbr, normal map) as bytes.  `out`: three reusable uint8 host
+        arrays of at least upg_png_bound bytes (e.g. pinned torch tensors' numpy views); allocated when absent."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uvs, dtype=np.float32).reshape(-1, 2)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        chans = (4 if water else 3, 3, 3)
+        caps = [int(self._lib.upg_png_bound(w, h, c)) for c in chans]
+        if out is None:
+            out = [np.empty(c, dtype=np.uint8) for c in caps]
+        ptrs = (C.c_void_p * 3)(*[o.ctypes.data for o in out])
+        cap = (C.c_uint64 * 3)(*[min(c, o.size) for c, o in zip(caps, out)])
+        size = (C.c_uint64 * 3)()
+        t = time.perf_counter()
+        capi.check(self._lib.upg_bake_export_png(self._h, int(bool(water)), _ptr(pos), _ptr(nrm), _ptr(uv), len(pos), _ptr(idx), len(idx), w, h, ptrs, cap, size))
+        self.last_call_s = time.perf_counter() - t
+        self.last_covered_texels = int(self._lib.upg_bake_last_covered_texels())
+        return [o[: int(n)] for o, n in zip(out, size)]
+
     def bake_export_device(self, water, d_pos, d_nrm, d_uv, nverts, d_idx, nidx, w, h, row0, row1, d_albedo, d_pbr, d_normal, stream=0):
         """upg_bake_export_device: every pointer is an integer DEVICE address; synchronises `stream` before returning."""
         vp = C.c_void_p
