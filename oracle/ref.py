@@ -259,3 +259,22 @@ class RefPlanet:
         p, n, i = _Buf(), _Buf(), _Buf()
         self._check(self.lib.upref_water_cull(_fp(pos), _fp(nrm), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), C.byref(p), C.byref(n), C.byref(i)))
         return self._take(p, np.float32, 3), self._take(n, np.float32, 3), self._take(i, np.uint32, 1)
+
+    # --- chunking + unwrap (the serial geometry between stage 2 and stage 3; out of the product's scope) ---------------------------
+    def chunk_and_unwrap(self, positions, normals, indices, max_surface_area=800000.0, texels_per_unit=1.35, padding=6):
+        """meshSplit + meshUnwrap of sources/meshGeneration.cpp:173-197 (cage meshChunking, xatlas): a list of chunks, each a dict with
+        positions, normals, uvs, indices and the atlas `resolution` xatlas chose for it"""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        n = C.c_uint32(0)
+        self._check(self.lib.upref_chunking(_fp(pos), _fp(nrm), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), C.c_float(max_surface_area), C.byref(n)))
+        out = []
+        for i in range(n.value):
+            res, nv, ni = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+            self._check(self.lib.upref_chunk_unwrap(C.c_uint32(i), C.c_float(texels_per_unit), C.c_uint32(padding), C.byref(res), C.byref(nv), C.byref(ni)))
+            c = dict(positions=np.zeros((nv.value, 3), np.float32), normals=np.zeros((nv.value, 3), np.float32), uvs=np.zeros((nv.value, 2), np.float32), indices=np.zeros(ni.value, np.uint32), resolution=int(res.value))
+            self.lib.upref_chunk_copy(C.c_uint32(i), _fp(c["positions"]), _fp(c["normals"]), _fp(c["uvs"]), _fp(c["indices"]))
+            out.append(c)
+        return out
+

@@ -399,6 +399,56 @@ extern "C"
 			});
 	}
 
+	// ---- the serial geometry between stage 2 and stage 3, as the generator runs it (sources/meshGeneration.cpp:173-197): meshChunking
+	// (maxSurfaceArea 800000) and meshUnwrap (xatlas; texelsPerUnit 1.35 / 0.3 in debug builds, padding 6).  Out of the product's scope
+	// (SURVEY.md 8f n4); here so that the GPU bake can be checked on REAL chunk atlases instead of a synthetic chart.
+	static std::vector<Holder<Mesh>> heldChunks;
+	int upref_chunking(const float *pos, const float *nrm, uint32_t nv, const uint32_t *idx, uint32_t ni, float maxSurfaceArea, uint32_t *chunkCount)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> m = newMesh();
+				m->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nv));
+				m->normals(PointerRange<const Vec3>((const Vec3 *)nrm, (const Vec3 *)nrm + nv));
+				m->indices(PointerRange<const uint32>(idx, idx + ni));
+				MeshChunkingConfig cfg;
+				cfg.maxSurfaceArea = maxSurfaceArea;
+				cfg.parallelize = false;
+				auto r = meshChunking(+m, cfg);
+				heldChunks.clear();
+				for (auto &it : r)
+					heldChunks.push_back(std::move(it));
+				*chunkCount = (uint32_t)heldChunks.size();
+			});
+	}
+	// meshUnwrap(const Holder<Mesh> &) of sources/meshGeneration.cpp:184-197 on chunk i; returns the atlas resolution
+	int upref_chunk_unwrap(uint32_t i, float texelsPerUnit, uint32_t padding, uint32_t *resolution, uint32_t *nverts, uint32_t *nidx)
+	{
+		return guarded(
+			[&]()
+			{
+				MeshUnwrapConfig cfg;
+				cfg.maxChartIterations = 10;
+				cfg.maxChartBoundaryLength = 300;
+				cfg.chartRoundness = 0.3;
+				cfg.texelsPerUnit = texelsPerUnit;
+				cfg.padding = padding;
+				*resolution = meshUnwrap(+heldChunks[i], cfg);
+				*nverts = heldChunks[i]->verticesCount();
+				*nidx = heldChunks[i]->indicesCount();
+			});
+	}
+	void upref_chunk_copy(uint32_t i, float *pos, float *nrm, float *uv, uint32_t *idx)
+	{
+		const Mesh *m = +heldChunks[i];
+		std::memcpy(pos, m->positions().data(), sizeof(Vec3) * m->verticesCount());
+		std::memcpy(nrm, m->normals().data(), sizeof(Vec3) * m->normals().size());
+		if (uv)
+			std::memcpy(uv, m->uvs().data(), sizeof(Vec2) * m->uvs().size());
+		std::memcpy(idx, m->indices().data(), sizeof(uint32) * m->indicesCount());
+	}
+
 	// terrainTile (sources/modesConfiguration.cpp:281-286) on explicit position/normal pairs
 	// out per tile: albedo rgb, roughness, metallic, height, elevation, slope(rad), temperature, precipitation, opacity, biome, type  (13 floats)
 	int upref_tiles(int purpose /* 1 land, 2 water, 3 navigation */, const float *pos, const float *nrm, int n, float *out)
