@@ -36,7 +36,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 _STDOUT = sys.stdout
-_CPU_GROUP = None
 METRIC = "sdf_samples_per_s"
 UNIT = "samples/s"
 FIELDS = ("land", "water", "navigation")
@@ -242,6 +241,286 @@ def bench_mesh(raw):
     return out
 
 
+# ---- the one-planet-over-N-GPUs legs (BASELINE configs[4]) run ISOLATED: each in its own process (group) started by rank 0 after the
+# headline legs are done and the other ranks have left, under a timeout.  A failure or a hang there costs its own scalars, never the line.
+def leg_sharded(args, rank, world, local_rank):
+    """ONE planet sharded over all ranks, one process per GPU over NCCL (unnatural_planets_b200/sharded.py): z-slab sampling + extraction,
+    row-tile bake.  Returns the leg's record on rank 0, None elsewhere."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from unnatural_planets_b200 import sharded as sh
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sp = sh.ShardedPlanet(device=local_rank, shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=args.sharded_grid)
+    stex = args.sharded_texture
+    sh.gather_varlen(np.zeros(4, dtype=np.float32), dst=0)  # opens NCCL's point-to-point channels outside the timing
+    barrier()
+    phases = {}
+    for _ in range(2):  # first calls: NCCL channels of this message size, memory pools, pinned staging
+        sp.field_meshes(FIELDS, dst=0)
+    mesh_times = []
+    for _ in range(3):  # median of three calls, each between barriers (max over ranks below)
+        barrier()
+        t = time.perf_counter()
+        smeshes = sp.field_meshes(FIELDS, dst=0)
+        mesh_times.append((time.perf_counter() - t, sp.timing))
+        barrier()
+    mesh_times.sort(key=lambda x: x[0])
+    t_mesh, phases["meshes"] = mesh_times[1]
+    # the bake input lives on rank 0 after the gather: broadcast it (a few tens of MB) like the generator would hand every
+    # device the chunk mesh; the synthetic UVs are host work outside the timing
+    src = None
+    if rank == 0:
+        from unnatural_planets_b200 import synth
+
+        src = {}
+        for name in ("land", "water"):
+            m = smeshes[name]
+            uv = synth.octahedral_uv(m["positions"])
+            src[name] = [m["positions"], np.ascontiguousarray(-m["normals"]), uv, synth.drop_folded_triangles(uv, m["indices"])]
+    # only rank 0 holds the mesh (like the generator's host process would): it uploads once and the mesh reaches the other GPUs as
+    # one NCCL broadcast inside the timed bake
+    none4 = [None, None, None, None]
+    for name, water in (("land", 0), ("water", 1)):  # first call: NCCL channels of this message size, memory pools
+        sp.bake(water, *(src[name] if rank == 0 else none4), stex, stex, dst=0, src=0)
+    bake_times = []
+    for _ in range(3):  # median of three, like the meshes
+        barrier()
+        t = time.perf_counter()
+        stexels = 0
+        ph = {}
+        for name, water in (("land", 0), ("water", 1)):
+            sp.bake(water, *(src[name] if rank == 0 else none4), stex, stex, dst=0, src=0)
+            ph["bake_" + name] = sp.timing
+            stexels += sp.last_covered_texels
+        barrier()
+        bake_times.append((time.perf_counter() - t, ph))
+    bake_times.sort(key=lambda x: x[0])
+    t_bake = bake_times[1][0]
+    phases.update(bake_times[1][1])
+    st = torch.tensor([t_mesh, t_bake], dtype=torch.float64, device=dev)
+    sc = torch.tensor([float(stexels)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    return {
+        "what": "ONE planet over %d GPU(s), strong scaling: upg_field_meshes_slab_device (own z-slab + 3-slice recomputed halo sampled once for the 3 fields, 3 extractions, chunks stay in HBM) + count all_gather + NCCL gather of the mesh chunks to rank 0 + one download there; then, per surface, the mesh uploaded by rank 0 and broadcast over NCCL, upg_bake_device on own texel rows (+ 7-row apron) + NCCL gather of the row tiles; wall clock, max over ranks, median of three calls after two warm-up calls" % world,
+        "gpus": world, "grid": args.sharded_grid, "texture": stex, "isosurface_ms": float(st[0]) * 1e3, "bake_ms": float(st[1]) * 1e3,
+        "samples_per_s": 3.0 * args.sharded_grid**3 / float(st[0]), "texels_per_s": float(sc[0]) / float(st[1]),
+        "land_triangles": int(len(smeshes["land"]["indices"]) // 3), "covered_texels": int(sc[0]), "rank0_phases_ms": phases,
+    }
+
+
+def leg_multi_device(args, devices):
+    """the same planet over `devices` GPUs from ONE process through the C ABI (upg_planet_desc::device_count, csrc/upg_multi.cu)"""
+    import ctypes as C
+
+    import torch
+
+    from unnatural_planets_b200 import Planet, capi
+    from unnatural_planets_b200 import synth as _synth
+
+    L = capi.load_library()
+    n = len(devices)
+    mres, mtex = args.sharded_grid, args.sharded_texture
+    mp = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=mres, devices=list(devices))
+    for _ in range(2):
+        mm = mp.field_meshes_clean(FIELDS)
+    mt = []
+    for _ in range(3):
+        mm = mp.field_meshes_clean(FIELDS)
+        mt.append(mp.last_call_s)
+    msrc = {}
+    for name in ("land", "water"):
+        uv = _synth.octahedral_uv(mm[name]["positions"])
+        msrc[name] = (mm[name]["positions"], mm[name]["normals"], uv, _synth.drop_folded_triangles(uv, mm[name]["indices"]))
+    mimg = {"land": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (3, 3, 3)], "water": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (4, 3, 3)]}
+    mtexels = [0]
+    failures = []
+
+    def mbake(name, water):
+        try:
+            pos, nrm, uv, idx = msrc[name]
+            o = mimg[name]
+            capi.check(L.upg_bake_export(mp._h, water, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), mtex, mtex, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr())))
+            mtexels[0] += int(L.upg_bake_last_covered_texels())
+        except Exception as ex:
+            failures.append(ex)
+
+    def mbake_both():
+        mtexels[0] = 0
+        ts = [threading.Thread(target=mbake, args=x) for x in (("land", 0), ("water", 1))]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if failures:
+            raise failures[0]
+
+    mbake_both()
+    bt = []
+    for _ in range(3):
+        t = time.perf_counter()
+        mbake_both()
+        bt.append(time.perf_counter() - t)
+    m_ms, b_ms = statistics.median(mt) * 1e3, statistics.median(bt) * 1e3
+    line = {
+        "what": "ONE planet over %d GPU(s) from ONE process through the C ABI (upg_planet_desc::device_count): upg_field_meshes_clean (z-slab per device, chunks gathered over NVLink per field, K9 + download on three devices) + 2 x upg_bake_export from two host threads (mesh parts uploaded per device and exchanged over NVLink, texel rows per device written straight into the pinned host images); host buffers, wall clock, median of three calls" % n,
+        "multi_device_planet_devices": n, "multi_device_planet_grid": mres, "multi_device_planet_texture": mtex,
+        "multi_device_planet_base_meshes_ms": m_ms, "multi_device_planet_bake_ms": b_ms, "multi_device_planet_ms": m_ms + b_ms,
+        "multi_device_planet_texels_per_s": mtexels[0] / (b_ms * 1e-3), "multi_device_planet_samples_per_s": 3.0 * mres**3 / (m_ms * 1e-3),
+        "multi_device_planet_land_triangles": int(len(mm["land"]["indices"]) // 3),
+    }
+    mp.close()
+    return line
+
+
+def run_leg(args, rank, world, local_rank):
+    """`--leg sharded|multi`: one isolated leg, one JSON line (rank 0)"""
+    if args.leg == "multi":
+        line = leg_multi_device(args, list(range(args.gpus)))
+    else:
+        line = leg_sharded(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(line), file=_STDOUT, flush=True)
+
+
+_TORCHRUN_ENV = ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS", "NCCL_ASYNC_ERROR_HANDLING", "TORCH_NCCL_ASYNC_ERROR_HANDLING")
+
+
+def run_selftest_leg(args, rank, world):
+    """`--leg selftest` / `--leg hang`: the orchestration of the isolated legs checked on CPU (gloo), tests/test_bench_orchestration.py"""
+    if args.leg == "hang":
+        time.sleep(3600)
+    total = float(rank + 1)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
+        t = torch.tensor([total], dtype=torch.float64)
+        dist.all_reduce(t)
+        total = float(t[0])
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"selftest_sum": total, "world": world, "inherited_rank_env": [k for k in _TORCHRUN_ENV if k in os.environ and world == 1]}), file=_STDOUT, flush=True)
+
+
+def run_orchestration_selftest(args, rank, world):
+    """the control flow of run_ours without a GPU: collective, group torn down on every rank, the other ranks leave, rank 0 runs the
+    isolated legs (one nested launch over `world` processes, one that hangs and is killed) and prints the line"""
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
+        t = torch.tensor([1.0], dtype=torch.float64)
+        dist.all_reduce(t)
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ok = run_isolated_leg("selftest", args, world, 120)
+    single = run_isolated_leg("selftest", args, 1, 120)
+    hung = run_isolated_leg("hang", args, world, 5)
+    print(json.dumps({"nested": ok, "single": single, "hung": hung}), file=_STDOUT, flush=True)
+
+
+def isolated_leg_command(leg, args, world, port):
+    """argv of the process (group) that runs one isolated leg over `world` GPUs"""
+    tail = [os.path.join(ROOT, "bench.py"), "--leg", leg, "--gpus", str(world), "--sharded-grid", str(args.sharded_grid), "--sharded-texture", str(args.sharded_texture)]
+    if leg != "multi" and world > 1:
+        return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port)] + tail
+    return [sys.executable] + tail
+
+
+def free_port():
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def kill_process_tree(proc):
+    """SIGKILL for the process this module started and every descendant of it (torchrun puts each worker into a session of its own,
+    so the process group of the launcher is not enough); by pid, nothing is matched by name"""
+    import signal
+
+    victims = []
+    try:
+        import psutil
+
+        victims = [c.pid for c in psutil.Process(proc.pid).children(recursive=True)]
+    except Exception:
+        pass
+    for pid in [proc.pid] + victims:
+        try:
+            os.kill(pid, signal.SIGKILL)
+        except Exception:
+            pass
+    try:
+        os.killpg(proc.pid, signal.SIGKILL)  # the session this call started
+    except Exception:
+        pass
+
+
+def run_isolated_leg(leg, args, world, timeout_s):
+    """runs `bench.py --leg <leg>` in its own session under a timeout; returns its record, or {"error": "..."}"""
+    env = {k: v for k, v in os.environ.items() if k not in _TORCHRUN_ENV and not k.startswith("TORCHELASTIC")}
+    cmd = isolated_leg_command(leg, args, world, free_port())
+    t = time.perf_counter()
+    try:
+        proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=None, env=env, cwd=ROOT, start_new_session=True, text=True)
+    except Exception as ex:
+        return {"error": "could not start: %r" % (ex,)}
+    try:
+        out, _ = proc.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        kill_process_tree(proc)
+        try:
+            proc.communicate(timeout=10)
+        except Exception:
+            pass
+        return {"error": "timeout after %d s" % timeout_s}
+    record = None
+    for text in reversed((out or "").strip().splitlines()):
+        try:
+            record = json.loads(text)
+            break
+        except Exception:
+            continue
+    if proc.returncode != 0 or not isinstance(record, dict):
+        return {"error": "exit code %s, no record" % proc.returncode}
+    record["leg_wall_s"] = time.perf_counter() - t
+    return record
+
+
+def wait_for_other_processes(timeout_s=20.0):
+    """after the process group is gone the other ranks exit: wait until no other compute process is left on the node's GPUs (bounded)"""
+    t = time.perf_counter()
+    while time.perf_counter() - t < timeout_s:
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-compute-apps=pid", "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout
+            # (a container sees host pids here, so the count is what can be compared: at most this process is left)
+            if len([x for x in out.split() if x.strip().isdigit()]) <= 1:
+                return True
+        except Exception:
+            time.sleep(3.0)
+            return False
+        time.sleep(0.5)
+    return False
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -312,7 +591,6 @@ def run_ours(args, rank, world, local_rank):
     cplanet.async_status(stream.cuda_stream)
     cplanet.close()
     planet.async_status(stream.cuda_stream)
-    multi_line = None
 
     # end to end through the host-buffer C-ABI call: device->host copies inside the timed region
     host = torch.empty(n, dtype=torch.float32, pin_memory=True)
@@ -451,139 +729,6 @@ def run_ours(args, rank, world, local_rank):
     h2d_bake = sum(a.nbytes for m in meshes.values() for a in m)
     d2h_bake = tex * tex * (3 + 3 + 3 + 4 + 3 + 3)
 
-    # ---- leg 4: ONE planet sharded over all ranks (BASELINE configs[4] shape: z-slab sampling + extraction, row-tile bake) ----
-    sharded_line = None
-    if args.sharded_grid > 0:
-        from unnatural_planets_b200 import sharded as sh
-
-        del dmesh, outs
-        torch.cuda.empty_cache()
-        sp = sh.ShardedPlanet(device=local_rank, shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=args.sharded_grid)
-        stex = args.sharded_texture
-        sh.gather_varlen(np.zeros(4, dtype=np.float32), dst=0)  # opens NCCL's point-to-point channels outside the timing
-        barrier()
-        t = time.perf_counter()
-        phases = {}
-        for _ in range(2):  # first calls: NCCL channels of this message size, memory pools, pinned staging
-            sp.field_meshes(FIELDS, dst=0)
-        mesh_times = []
-        for _ in range(3):  # median of three calls, each between barriers (max over ranks below)
-            barrier()
-            t = time.perf_counter()
-            smeshes = sp.field_meshes(FIELDS, dst=0)
-            mesh_times.append((time.perf_counter() - t, sp.timing))
-            barrier()
-        mesh_times.sort(key=lambda x: x[0])
-        t_mesh, phases["meshes"] = mesh_times[1]
-        # the bake input lives on rank 0 after the gather: broadcast it (a few tens of MB) like the generator would hand every
-        # device the chunk mesh; the synthetic UVs are host work outside the timing
-        src = None
-        if rank == 0:
-            from unnatural_planets_b200 import synth
-
-            src = {}
-            for name in ("land", "water"):
-                m = smeshes[name]
-                uv = synth.octahedral_uv(m["positions"])
-                src[name] = [m["positions"], np.ascontiguousarray(-m["normals"]), uv, synth.drop_folded_triangles(uv, m["indices"])]
-        # only rank 0 holds the mesh (like the generator's host process would): it uploads once and the mesh reaches the other GPUs as
-        # one NCCL broadcast inside the timed bake
-        none4 = [None, None, None, None]
-        for name, water in (("land", 0), ("water", 1)):  # first call: NCCL channels of this message size, memory pools
-            sp.bake(water, *(src[name] if rank == 0 else none4), stex, stex, dst=0, src=0)
-        bake_times = []
-        for _ in range(3):  # median of three, like the meshes
-            barrier()
-            t = time.perf_counter()
-            stexels = 0
-            ph = {}
-            for name, water in (("land", 0), ("water", 1)):
-                sp.bake(water, *(src[name] if rank == 0 else none4), stex, stex, dst=0, src=0)
-                ph["bake_" + name] = sp.timing
-                stexels += sp.last_covered_texels
-            barrier()
-            bake_times.append((time.perf_counter() - t, ph))
-        bake_times.sort(key=lambda x: x[0])
-        t_bake = bake_times[1][0]
-        phases.update(bake_times[1][1])
-        st = torch.tensor([t_mesh, t_bake], dtype=torch.float64, device=dev)
-        sc = torch.tensor([float(stexels)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(st, op=dist.ReduceOp.MAX)
-            dist.all_reduce(sc, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            sharded_line = {
-                "what": "ONE planet over %d GPU(s), strong scaling: upg_field_meshes_slab_device (own z-slab + 3-slice recomputed halo sampled once for the 3 fields, 3 extractions, chunks stay in HBM) + count all_gather + NCCL gather of the mesh chunks to rank 0 + one download there; then, per surface, the mesh uploaded by rank 0 and broadcast over NCCL, upg_bake_device on own texel rows (+ 7-row apron) + NCCL gather of the row tiles; wall clock, max over ranks, median of three calls after two warm-up calls" % world,
-                "grid": args.sharded_grid, "texture": stex, "isosurface_ms": float(st[0]) * 1e3, "bake_ms": float(st[1]) * 1e3,
-                "samples_per_s": 3.0 * args.sharded_grid**3 / float(st[0]), "texels_per_s": float(sc[0]) / float(st[1]),
-                "land_triangles": int(len(smeshes["land"]["indices"]) // 3), "covered_texels": int(sc[0]), "rank0_phases_ms": phases,
-            }
-        del smeshes, src
-
-    # ---- leg 4b: the same planet over all GPUs from ONE process through the C ABI (upg_planet_desc::device_count, csrc/upg_multi.cu):
-    # rank 0 drives every GPU of the job, the other ranks wait at the barrier with their GPUs idle --------------------------------------
-    if args.sharded_grid > 0:
-        try:
-            del dmesh, outs
-        except NameError:
-            pass
-        torch.cuda.empty_cache()
-        barrier()
-
-        def cpu_barrier():
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier(group=_CPU_GROUP)
-
-        cpu_barrier()
-        if rank == 0:
-            from unnatural_planets_b200 import synth as _synth
-
-            mres, mtex = args.sharded_grid, args.sharded_texture
-            mp = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=mres, devices=list(range(world)))
-            for _ in range(2):
-                mm = mp.field_meshes_clean(FIELDS)
-            mt = []
-            for _ in range(3):
-                mm = mp.field_meshes_clean(FIELDS)
-                mt.append(mp.last_call_s)
-            msrc = {}
-            for name in ("land", "water"):
-                uv = _synth.octahedral_uv(mm[name]["positions"])
-                msrc[name] = (mm[name]["positions"], mm[name]["normals"], uv, _synth.drop_folded_triangles(uv, mm[name]["indices"]))
-            mimg = {"land": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (3, 3, 3)], "water": [torch.empty(mtex * mtex * c, dtype=torch.uint8, pin_memory=True) for c in (4, 3, 3)]}
-            mtexels = [0]
-
-            def mbake(name, water):
-                pos, nrm, uv, idx = msrc[name]
-                o = mimg[name]
-                capi.check(L.upg_bake_export(mp._h, water, pos.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), len(pos), idx.ctypes.data_as(C.c_void_p), len(idx), mtex, mtex, C.c_void_p(o[0].data_ptr()), C.c_void_p(o[1].data_ptr()), C.c_void_p(o[2].data_ptr())))
-                mtexels[0] += int(L.upg_bake_last_covered_texels())
-
-            def mbake_both():
-                mtexels[0] = 0
-                ts = [threading.Thread(target=mbake, args=x) for x in (("land", 0), ("water", 1))]
-                [t.start() for t in ts]
-                [t.join() for t in ts]
-
-            mbake_both()
-            bt = []
-            for _ in range(3):
-                t = time.perf_counter()
-                mbake_both()
-                bt.append(time.perf_counter() - t)
-            m_ms, b_ms = statistics.median(mt) * 1e3, statistics.median(bt) * 1e3
-            multi_line = {
-                "what": "ONE planet over %d GPU(s) from ONE process through the C ABI (upg_planet_desc::device_count): upg_field_meshes_clean (z-slab per device, chunks gathered over NVLink per field, K9 + download on three devices) + 2 x upg_bake_export from two host threads (mesh parts uploaded per device and exchanged over NVLink, texel rows per device written straight into the pinned host images); host buffers, wall clock, median of three calls" % world,
-                "multi_device_planet_devices": world, "multi_device_planet_grid": mres, "multi_device_planet_texture": mtex,
-                "multi_device_planet_base_meshes_ms": m_ms, "multi_device_planet_bake_ms": b_ms, "multi_device_planet_ms": m_ms + b_ms,
-                "multi_device_planet_texels_per_s": mtexels[0] / (b_ms * 1e-3), "multi_device_planet_samples_per_s": 3.0 * mres**3 / (m_ms * 1e-3),
-            }
-            mp.close()
-            del mm, msrc, mimg
-        cpu_barrier()
-        barrier()
-
     # ---- leg 5: a batch of planets back to back (BASELINE configs[3]: random base shape per seed, every elevation mode) ----
     batch_line = None
     if args.batch > 0:
@@ -660,6 +805,11 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     ms_total, e2e_ms, bake_ms_max, bake_e2e_ms, mesh_ms, mesh_raw_ms, contract_ms_max = (float(x) for x in times)
     texels_all = float(counts[0])
+    # the last collective of the job is behind us: the process group goes away on every rank together, the other ranks leave, and rank 0
+    # finishes alone (CPU baseline, the isolated one-planet-over-N-GPUs legs, the JSON line)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -743,6 +893,33 @@ def run_ours(args, rank, world, local_rank):
     except Exception as ex:  # the baseline is reported, never required for the GPU number
         cpu["sample"] = "failed: %r" % (ex,)
 
+    # ---- legs 4 / 4b: ONE planet over all GPUs of the job (BASELINE configs[4]), each leg in its own process (group) under a timeout ----
+    sharded_line = multi_line = None
+    if args.sharded_grid > 0:
+        try:  # device tensors of the earlier legs (the batch leg may have dropped them already)
+            del dmesh, outs
+        except NameError:
+            pass
+        planet.close()
+        torch.cuda.empty_cache()
+        try:
+            from unnatural_planets_b200 import planet as _pl
+
+            _pl.trim(local_rank, 0)
+        except Exception:
+            pass
+        if world > 1:
+            wait_for_other_processes()
+        sharded_line = run_isolated_leg("sharded", args, world, args.leg_timeout)
+        multi_line = run_isolated_leg("multi", args, world, args.leg_timeout)
+        for name, rec in (("sharded_planet", sharded_line), ("multi_device_planet", multi_line)):
+            if "error" in rec:
+                print("[bench] leg %s failed: %s" % (name, rec["error"]), file=sys.stderr, flush=True)
+                roofline[name + "_error"] = rec["error"][:200]
+        if "error" in sharded_line:
+            sharded_line = None
+        if "error" in multi_line:
+            multi_line = None
     if sharded_line:
         roofline.update({"sharded_planet_grid": sharded_line["grid"], "sharded_planet_texture": sharded_line["texture"], "sharded_planet_isosurface_ms": sharded_line["isosurface_ms"], "sharded_planet_bake_ms": sharded_line["bake_ms"]})
     if multi_line:
@@ -795,6 +972,9 @@ def main():
     ap.add_argument("--batch-grid", type=int, default=500, help="grid of the batch planets (the reference's constant)")
     ap.add_argument("--batch-texture", type=int, default=2048, help="bake resolution of the batch planets")
     ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
+    ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
+    ap.add_argument("--orchestration-selftest", action="store_true", help="internal: the multi-process control flow of the bench on CPU (gloo), no GPU work")
+    ap.add_argument("--leg-timeout", type=int, default=180, help="seconds each isolated leg may take before it is killed and reported as failed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -807,6 +987,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.leg in ("selftest", "hang"):
+        run_selftest_leg(args, rank, world)
+        return
+    if args.orchestration_selftest:
+        run_orchestration_selftest(args, rank, world)
+        return
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -814,17 +1000,17 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        # a CPU-side group: while rank 0 drives EVERY GPU of the job (the multi-device leg) the other ranks must wait without an NCCL
-        # kernel spinning on their GPUs
-        global _CPU_GROUP
-        _CPU_GROUP = dist.new_group(backend="gloo")
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.leg:
+            run_leg(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist
 
-            dist.destroy_process_group()
+            if dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -35,6 +35,13 @@ namespace upg
 
 	int cuda_fail(cudaError_t e, const char *what)
 	{
+		if (e == cudaErrorMemoryAllocation && last_failed_request().device >= 0)
+		{
+			const FailedRequest f = last_failed_request();
+			last_failed_request().device = -1; // reported once
+			return fail(UPG_ERR_CUDA, "CUDA error in %s: %s (%s); last request the pool of device %d could not serve: %llu bytes (pool holds %llu, %llu in use; device %llu free of %llu)", what, cudaGetErrorName(e), cudaGetErrorString(e), f.device,
+				(unsigned long long)f.bytes, (unsigned long long)f.reserved, (unsigned long long)f.used, (unsigned long long)f.deviceFree, (unsigned long long)f.deviceTotal);
+		}
 		return fail(UPG_ERR_CUDA, "CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 	}
 

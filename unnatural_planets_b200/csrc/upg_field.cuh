@@ -69,6 +69,11 @@ namespace upg
 	// table: the same points, the same distances, the same strict-less comparisons -- bit-identical -- for ~1/30 of the hashing.
 	// Blocks whose samples span too many cells (the block that wraps from the end of one slice to the start of the next) and Voronoi
 	// instances with more than two points per cell take the per-sample search.
+	// NOT part of the default build: written after the round's GPU budget was spent, never run on a B200.  -DUPG_CRATERS_TABLE=1 compiles it
+	// in (make -C csrc EXTRA_NVFLAGS=-DUPG_CRATERS_TABLE=1); without it the craters kernels are the per-sample search the parity tests ran against.
+#ifndef UPG_CRATERS_TABLE
+#define UPG_CRATERS_TABLE 0
+#endif
 	constexpr int CRATER_MAX_CELLS = 160;
 	constexpr int CRATER_MAX_POINTS = 2;
 	struct CraterTable
@@ -162,7 +167,7 @@ namespace upg
 		__syncthreads();
 		const uint64_t idx = (uint64_t)blockIdx.x * FIELD_BLOCK + threadIdx.x;
 		// grid launches of the `craters` mode keep every thread of the block until the shared Voronoi table is built
-		constexpr bool CRATERS = ELEV == EL_CRATERS;
+		constexpr bool CRATERS = (UPG_CRATERS_TABLE != 0) && ELEV == EL_CRATERS;
 		const bool cratersGrid = CRATERS && !L.positions;
 		const bool live = idx < L.count;
 		if (!live && !cratersGrid)

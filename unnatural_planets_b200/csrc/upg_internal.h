@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstddef>
+#include <vector>
 
 #include "../../include/upg.h"
 #include "upg_field.cuh"
@@ -120,7 +121,12 @@ namespace upg
 
 	// K9 (upg_meshfix.cu): the clean-up chain of makeMesh / meshGenerateGeneric / meshGenerateBaseWater over device arrays; `stages` are
 	// the UPG_MESH_* bits of include/upg.h.  `out` receives fresh pool arrays (positions, normals, indices; no dualmc arrays).
-	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out);
+	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out, const float *clipBox6 = nullptr);
+	// internal stage of mesh_clean: meshClip(mesh, box) ALONE with the box of `clipBox6` (a.x a.y a.z b.x b.y b.z) -- clip, removeUnusedVertices,
+	// meshRemoveInvalid, meshMergeCloseVertices({}) (meshAlgorithms.cpp:1056-1114) -- as meshChunking applies it to every half
+	constexpr unsigned MESH_STAGE_CLIP_BOX = 0x100;
+	// meshChunking (meshAlgorithms.cpp:1522-1619) over a device mesh; leaves in the reference's order (upg_meshfix.cu)
+	int mesh_chunking(const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float maxSurfaceArea, cudaStream_t s, std::vector<DmcResult> &leaves);
 
 	// K1b (upg_band.cu): land / navigation of slices [za, zb) from the water (= shape) field of the same slices, exact wherever the
 	// isosurface can see the value; asynchronous on `stream`.  `evaluated`: optional device counter of evaluated nodes.

@@ -26,6 +26,12 @@ namespace upg
 		}
 	}
 
+	FailedRequest &last_failed_request()
+	{
+		static thread_local FailedRequest request;
+		return request;
+	}
+
 	cudaError_t device_pool(int device, cudaMemPool_t *pool)
 	{
 		*pool = nullptr;
@@ -83,6 +89,32 @@ namespace upg
 		if (e != cudaSuccess)
 			return e;
 		e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, s);
+		if (e == cudaErrorMemoryAllocation)
+		{
+			// what a caching allocator does before it gives up: let the frees queued on this stream take effect, hand every cached
+			// block back to the driver (blocks the other streams of concurrent calls hold cannot serve this one) and ask once more
+			cudaGetLastError();
+			cudaStreamSynchronize(s);
+			cudaMemPoolTrimTo(pool, 0);
+			e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, s);
+			if (e != cudaSuccess)
+			{
+				// the failed request next to what the pool and the device held, for the error text (cuda_fail)
+				FailedRequest &f = last_failed_request();
+				f.bytes = bytes;
+				f.device = device;
+				f.reserved = f.used = f.deviceFree = f.deviceTotal = 0;
+				cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &f.reserved);
+				cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &f.used);
+				size_t freeBytes = 0, totalBytes = 0;
+				if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess)
+				{
+					f.deviceFree = freeBytes;
+					f.deviceTotal = totalBytes;
+				}
+				cudaGetLastError();
+			}
+		}
 		if (e != cudaSuccess)
 			return e;
 		const int poison = poison_byte();

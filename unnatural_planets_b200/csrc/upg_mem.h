@@ -27,6 +27,15 @@ namespace upg
 	}
 	inline cudaError_t device_free(void *p, cudaStream_t s) { return cudaFreeAsync(p, s); }
 
+	// the calling thread's last request the pool could not serve, even after handing its cached blocks back (device_alloc retries once
+	// after cudaMemPoolTrimTo): what was asked for next to what the pool and the device held -- part of the error text
+	struct FailedRequest
+	{
+		uint64_t bytes = 0, reserved = 0, used = 0, deviceFree = 0, deviceTotal = 0;
+		int device = -1;
+	};
+	FailedRequest &last_failed_request();
+
 	// the pool of `device` (created on first use; nullptr + error when the device is unusable)
 	cudaError_t device_pool(int device, cudaMemPool_t *pool);
 	// grows the pool of `device` to at least `bytes` of cached memory / gives everything cached back to the driver

@@ -19,6 +19,8 @@
 
 #include <cub/cub.cuh>
 
+#include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "../../include/upg.h"
@@ -157,10 +159,10 @@ namespace upg
 			return dot(n, vmax) >= 0;
 		}
 
-		__device__ __forceinline__ bool point_in_box(V3 p, float lo, float hi)
+		__device__ __forceinline__ bool point_in_box(V3 p, V3 lo, V3 hi)
 		{
 			// intersects(Vec3, Aabb) (geometry.cpp:307-315): inclusive
-			return !(p.x < lo || p.x > hi || p.y < lo || p.y > hi || p.z < lo || p.z > hi);
+			return !(p.x < lo.x || p.x > hi.x || p.y < lo.y || p.y > hi.y || p.z < lo.z || p.z > hi.z);
 		}
 
 		// the serial clip of ONE triangle against the six box planes (meshAlgorithms.cpp:1081-1099), in a thread
@@ -271,7 +273,7 @@ namespace upg
 			}
 
 			// returns the list holding the result
-			__device__ int run(uint32_t a, uint32_t b, uint32_t c, float lo, float hi)
+			__device__ int run(uint32_t a, uint32_t b, uint32_t c, V3 lo, V3 hi)
 			{
 				created = 0;
 				overflow = false;
@@ -281,7 +283,7 @@ namespace upg
 				for (int axis = 0; axis < 3; axis++)
 					for (int side = 0; side < 2; side++)
 					{
-						clip_plane(cur, axis, side ? hi : lo, side != 0);
+						clip_plane(cur, axis, axis_of(side ? hi : lo, axis), side != 0);
 						cur ^= 1;
 					}
 				return cur;
@@ -295,18 +297,18 @@ namespace upg
 			CC_CUT = 2
 		};
 
-		__device__ ClipClass clip_classify(V3 a, V3 b, V3 c, float lo, float hi)
+		__device__ ClipClass clip_classify(V3 a, V3 b, V3 c, V3 lo, V3 hi)
 		{
 			if (point_in_box(a, lo, hi) && point_in_box(b, lo, hi) && point_in_box(c, lo, hi))
 				return CC_KEEP;
 			// Aabb::center() = (a + b) * 0.5, size() * 0.5 (geometry.h:192)
-			const float ce = (lo + hi) * 0.5f, hs = (hi - lo) * 0.5f;
-			if (!triangle_box_overlap(v3(ce, ce, ce), v3(hs, hs, hs), a, b, c))
+			const V3 ce = (lo + hi) * 0.5f, hs = (hi - lo) * 0.5f;
+			if (!triangle_box_overlap(ce, hs, a, b, c))
 				return CC_DROP;
 			return CC_CUT;
 		}
 
-		__global__ void __launch_bounds__(128) clip_count_kernel(const float *__restrict__ positions, const float *__restrict__ normals, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ dead, uint32_t tris, float lo, float hi, uint32_t *__restrict__ triOut, uint32_t *__restrict__ newOut, uint32_t *__restrict__ status)
+		__global__ void __launch_bounds__(128) clip_count_kernel(const float *__restrict__ positions, const float *__restrict__ normals, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ dead, uint32_t tris, V3 lo, V3 hi, uint32_t *__restrict__ triOut, uint32_t *__restrict__ newOut, uint32_t *__restrict__ status)
 		{
 			const uint32_t t = blockIdx.x * 128 + threadIdx.x;
 			if (t >= tris)
@@ -334,7 +336,7 @@ namespace upg
 			newOut[t] = nv;
 		}
 
-		__global__ void __launch_bounds__(128) clip_emit_kernel(const float *__restrict__ positions, const float *__restrict__ normals, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ dead, uint32_t tris, float lo, float hi, const uint32_t *__restrict__ triOff, const uint32_t *__restrict__ newOff, uint32_t oldVerts, float *__restrict__ positionsOut, float *__restrict__ normalsOut, uint32_t *__restrict__ idxOut)
+		__global__ void __launch_bounds__(128) clip_emit_kernel(const float *__restrict__ positions, const float *__restrict__ normals, const uint32_t *__restrict__ idx, const uint8_t *__restrict__ dead, uint32_t tris, V3 lo, V3 hi, const uint32_t *__restrict__ triOff, const uint32_t *__restrict__ newOff, uint32_t oldVerts, float *__restrict__ positionsOut, float *__restrict__ normalsOut, uint32_t *__restrict__ idxOut)
 		{
 			const uint32_t t = blockIdx.x * 128 + threadIdx.x;
 			if (t >= tris || dead[t])
@@ -747,7 +749,7 @@ namespace upg
 
 	// `positions`, `normals` (verts x 3) and `indices` (tris x 3) are device arrays and stay untouched; the result replaces `out`
 	// (its arrays come from the stream-ordered pool: dmc_release frees them).
-	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out)
+	int mesh_clean(Planet *planet, const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float boxSize, unsigned stages, cudaStream_t s, DmcResult &out, const float *clipBox6)
 	{
 		out = DmcResult();
 		if (verts >= LOCAL_BIT || (uint64_t)tris * 3 >= 0xffffffffull)
@@ -770,9 +772,10 @@ namespace upg
 		MF_TRY(cudaMemsetAsync(best, 0, sizeof(unsigned long long), s));
 		MF_TRY(cudaMemsetAsync(w.dead, 0, tris, s));
 
-		if (stages & UPG_MESH_MAKEMESH_TAIL)
+		if (stages & (UPG_MESH_MAKEMESH_TAIL | MESH_STAGE_CLIP_BOX))
 		{
-			// removeNonManifoldTriangles
+			// removeNonManifoldTriangles (makeMesh only; meshClip on its own -- the chunking -- has no such step)
+			if (stages & UPG_MESH_MAKEMESH_TAIL)
 			{
 				const uint32_t n = tris * 3;
 				uint32_t idBits = 1;
@@ -794,7 +797,9 @@ namespace upg
 				}
 			}
 			// meshClip(box): a new triangle list and appended vertices
-			const float lo = boxSize * -0.5f, hi = boxSize * 0.5f;
+			const bool ownBox = (stages & MESH_STAGE_CLIP_BOX) && clipBox6;
+			const V3 lo = ownBox ? v3(clipBox6[0], clipBox6[1], clipBox6[2]) : v3(boxSize * -0.5f, boxSize * -0.5f, boxSize * -0.5f);
+			const V3 hi = ownBox ? v3(clipBox6[3], clipBox6[4], clipBox6[5]) : v3(boxSize * 0.5f, boxSize * 0.5f, boxSize * 0.5f);
 			uint32_t *triOut = pool.get<uint32_t>(tris), *newOut = pool.get<uint32_t>(tris), *triOff = pool.get<uint32_t>(tris), *newOff = pool.get<uint32_t>(tris);
 			MF_TRY(pool.err);
 			if (e == cudaSuccess)
@@ -976,4 +981,268 @@ namespace upg
 		out.triangleCount = out.ownedTriangles = nt;
 		return UPG_OK;
 	}
+
+	// ---- meshChunking (meshAlgorithms.cpp:1484-1619) as meshSplit calls it (sources/meshGeneration.cpp:173-182) --------------------------
+	// A recursion: surface area -> leaf or split; split = longest axis of the bounding box, the best of seven candidate positions by the
+	// area below each, meshClip of a copy against the two (enlarged) half boxes.  The clip is K9's; what is new is the DECISION, and it
+	// hangs on two serial float sums over the triangles in index order (`result += t.area()`, `areas[i] += a`): their rounding depends on
+	// the order, so they are accumulated in that order -- areas and the seven below-position bits are computed by all threads, then ONE
+	// thread adds them up from shared memory while its warp prefetches (eight independent dependency chains per triangle).  The host
+	// turns eight sums and a bounding box into the decision with the reference's float expressions; results are the reference's chunks
+	// bit for bit (tests/test_gpu_chunks.py).
+	namespace
+	{
+		__device__ __forceinline__ uint32_t order_key(float f)
+		{
+			const uint32_t u = __float_as_uint(f);
+			return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+		}
+		float key_to_float(uint32_t k)
+		{
+			const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+			float f;
+			std::memcpy(&f, &u, 4);
+			return f;
+		}
+		// Mesh::boundingBox (mesh.cpp:124-130): minimum / maximum over ALL positions; keys[0..2] = min, keys[3..5] = max
+		__global__ void __launch_bounds__(MF_BLOCK) chunk_bbox_kernel(const float *__restrict__ positions, uint32_t verts, uint32_t *__restrict__ keys)
+		{
+			const uint32_t v = blockIdx.x * MF_BLOCK + threadIdx.x;
+			const bool live = v < verts;
+			const V3 p = live ? ld3(positions, v) : v3(0, 0, 0);
+			const float c[3] = { p.x, p.y, p.z };
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+			{
+				const uint32_t k = order_key(c[a]);
+				const uint32_t mn = __reduce_min_sync(0xffffffffu, live ? k : 0xffffffffu), mx = __reduce_max_sync(0xffffffffu, live ? k : 0u);
+				if ((threadIdx.x & 31u) == 0)
+				{
+					atomicMin(&keys[a], mn);
+					atomicMax(&keys[3 + a], mx);
+				}
+			}
+		}
+		struct ChunkSplit
+		{
+			float positions[7]; // candidate planes on `axis` (world units)
+			int axis;
+		};
+		// Triangle::area() = length(cross(b - a, c - a)) * 0.5 (geometry.h:89), center()[axis] = ((a + b) + c) / 3; bit i = center < positions[i]
+		__global__ void __launch_bounds__(MF_BLOCK) chunk_areas_kernel(const float *__restrict__ positions, const uint32_t *__restrict__ idx, uint32_t tris, ChunkSplit split, float *__restrict__ area, uint8_t *__restrict__ below)
+		{
+			const uint32_t t = blockIdx.x * MF_BLOCK + threadIdx.x;
+			if (t >= tris)
+				return;
+			const V3 a = ld3(positions, idx[t * 3 + 0]), b = ld3(positions, idx[t * 3 + 1]), c = ld3(positions, idx[t * 3 + 2]);
+			area[t] = length(cross(b - a, c - a)) * 0.5f;
+			const float p = axis_of(((a + b) + c) / 3.0f, split.axis);
+			uint32_t m = 0;
+#pragma unroll
+			for (int i = 0; i < 7; i++)
+				m |= (p < split.positions[i] ? 1u : 0u) << i;
+			below[t] = (uint8_t)m;
+		}
+		// sums[0] = total area, sums[1 + i] = area below position i, both accumulated in triangle order by ONE thread
+		__global__ void __launch_bounds__(32) chunk_serial_sums_kernel(const float *__restrict__ area, const uint8_t *__restrict__ below, uint32_t tris, float *__restrict__ sums)
+		{
+			constexpr uint32_t TILE = 1024;
+			__shared__ float sa[TILE];
+			__shared__ uint8_t sm[TILE];
+			float total = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, s5 = 0, s6 = 0;
+			for (uint32_t base = 0; base < tris; base += TILE)
+			{
+				const uint32_t n = tris - base < TILE ? tris - base : TILE;
+				for (uint32_t i = threadIdx.x; i < n; i += 32)
+				{
+					sa[i] = area[base + i];
+					sm[i] = below[base + i];
+				}
+				__syncwarp();
+				if (threadIdx.x == 0)
+					for (uint32_t i = 0; i < n; i++)
+					{
+						const float a = sa[i];
+						const uint32_t m = sm[i];
+						total += a;
+						if (m & 1u)
+							s0 += a;
+						if (m & 2u)
+							s1 += a;
+						if (m & 4u)
+							s2 += a;
+						if (m & 8u)
+							s3 += a;
+						if (m & 16u)
+							s4 += a;
+						if (m & 32u)
+							s5 += a;
+						if (m & 64u)
+							s6 += a;
+					}
+				__syncwarp();
+			}
+			if (threadIdx.x == 0)
+			{
+				sums[0] = total;
+				sums[1] = s0, sums[2] = s1, sums[3] = s2, sums[4] = s3, sums[5] = s4, sums[6] = s5, sums[7] = s6;
+			}
+		}
+
+		// the reference's float expressions on the host (Real = float; -ffp-contract=off for the host side of this library)
+		float lerp_host(float a, float b, float f) { return a + (b - a) * f; } // interpolate (math.h:1173-1177)
+
+		struct ChunkNode
+		{
+			DmcResult mesh; // positions, normals, indices (device, pool)
+			bool owned; // false for the caller's root arrays
+		};
+
+		int chunk_recurse(const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float maxArea, cudaStream_t s, std::vector<DmcResult> &leaves, DmcResult *own, int depth)
+		{
+			// own != nullptr: this node's arrays belong to *own (released here unless it becomes a leaf)
+			auto leaf = [&]() -> int
+			{
+				if (own)
+				{
+					leaves.push_back(*own);
+					*own = DmcResult();
+					return UPG_OK;
+				}
+				// the root itself is the only chunk: a copy, like meshChunking's msh->copy()
+				DmcResult c;
+				cudaError_t e = device_alloc(&c.positions, sizeof(float) * 3 * (size_t)(verts ? verts : 1), s);
+				if (e == cudaSuccess)
+					e = device_alloc(&c.normals, sizeof(float) * 3 * (size_t)(verts ? verts : 1), s);
+				if (e == cudaSuccess)
+					e = device_alloc(&c.indices, sizeof(uint32_t) * 3 * (size_t)(tris ? tris : 1), s);
+				if (e == cudaSuccess && verts)
+					e = cudaMemcpyAsync(c.positions, positions, sizeof(float) * 3 * (size_t)verts, cudaMemcpyDeviceToDevice, s);
+				if (e == cudaSuccess && verts)
+					e = cudaMemcpyAsync(c.normals, normals, sizeof(float) * 3 * (size_t)verts, cudaMemcpyDeviceToDevice, s);
+				if (e == cudaSuccess && tris)
+					e = cudaMemcpyAsync(c.indices, indices, sizeof(uint32_t) * 3 * (size_t)tris, cudaMemcpyDeviceToDevice, s);
+				if (e != cudaSuccess)
+				{
+					dmc_release(c, s);
+					return cuda_fail(e, "mesh chunking (copy)");
+				}
+				c.vertexCount = c.ownedVertices = verts;
+				c.triangleCount = c.ownedTriangles = tris;
+				leaves.push_back(c);
+				return UPG_OK;
+			};
+			if (tris == 0)
+				return leaf(); // meshSurfaceArea = 0 < maxSurfaceArea: an empty chunk stays in the list (meshClip cleared it)
+			if (depth > 48)
+				return fail(UPG_ERR_ARGUMENT, "mesh chunking does not terminate (a split leaves the surface area unchanged)");
+			Pool pool(s);
+			uint32_t *keys = pool.get<uint32_t>(6);
+			float *area = pool.get<float>(tris), *sums = pool.get<float>(8);
+			uint8_t *below = pool.get<uint8_t>(tris);
+			cudaError_t e = pool.err;
+			uint32_t hostKeys[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0 };
+			MF_TRY(cudaMemcpyAsync(keys, hostKeys, sizeof(hostKeys), cudaMemcpyHostToDevice, s));
+			if (e == cudaSuccess)
+			{
+				chunk_bbox_kernel<<<blocks_of(verts), MF_BLOCK, 0, s>>>(positions, verts, keys);
+				MF_LAUNCHED();
+			}
+			MF_TRY(cudaMemcpyAsync(hostKeys, keys, sizeof(hostKeys), cudaMemcpyDeviceToHost, s));
+			MF_TRY(stream_sync(s));
+			if (e != cudaSuccess)
+				return cuda_fail(e, "mesh chunking (bounding box)");
+			float a[3], b[3];
+			for (int k = 0; k < 3; k++)
+			{
+				a[k] = key_to_float(hostKeys[k]);
+				b[k] = key_to_float(hostKeys[3 + k]);
+			}
+			// boxLongestAxis (:1498-1507) over dominantAxis(size) (math/vectors.cpp:305-312)
+			const float sz[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] };
+			const float ax = sz[0] < 0 ? -sz[0] : sz[0], ay = sz[1] < 0 ? -sz[1] : sz[1], az = sz[2] < 0 ? -sz[2] : sz[2];
+			int axis;
+			if (ax > ay && ax > az)
+				axis = sz[0] != 0 ? 0 : 2; // sign(0) = 0: `a[0] == 1` fails, so does a[1] -> 2
+			else if (ay > az)
+				axis = sz[1] != 0 ? 1 : 2;
+			else
+				axis = 2;
+			static const float Positions[7] = { (float)0.3, (float)0.4, (float)0.45, (float)0.5, (float)0.55, (float)0.6, (float)0.7 };
+			ChunkSplit split;
+			split.axis = axis;
+			for (int i = 0; i < 7; i++)
+				split.positions[i] = lerp_host(a[axis], b[axis], Positions[i]);
+			float hostSums[8];
+			if (e == cudaSuccess)
+			{
+				chunk_areas_kernel<<<blocks_of(tris), MF_BLOCK, 0, s>>>(positions, indices, tris, split, area, below);
+				chunk_serial_sums_kernel<<<1, 32, 0, s>>>(area, below, tris, sums);
+				MF_LAUNCHED();
+			}
+			MF_TRY(cudaMemcpyAsync(hostSums, sums, sizeof(hostSums), cudaMemcpyDeviceToHost, s));
+			MF_TRY(stream_sync(s));
+			if (e != cudaSuccess)
+				return cuda_fail(e, "mesh chunking (areas)");
+			const float myArea = hostSums[0];
+			if (myArea < maxArea)
+				return leaf();
+			float bestPosition = Positions[0], bestDiff = INFINITY;
+			bool any = false;
+			for (int i = 0; i < 7; i++)
+			{
+				float d = (float)0.5 - hostSums[1 + i] / myArea;
+				d = d < 0 ? -d : d;
+				if (d < bestDiff)
+				{
+					bestDiff = d;
+					bestPosition = Positions[i];
+					any = true;
+				}
+			}
+			if (!any)
+				return fail(UPG_ERR_INVALID_VALUE, "mesh chunking: no split position (NaN surface area)");
+			// clippingBox (:1509-1520): the bounding box blown up by 20 %, cut at `position` of the BLOWN-UP extent
+			float c3[3], hs[3], ra[3], rb[3];
+			for (int k = 0; k < 3; k++)
+			{
+				c3[k] = (a[k] + b[k]) * (float)0.5; // Aabb::center()
+				hs[k] = (b[k] - a[k]) * (float)0.6;
+				ra[k] = c3[k] - hs[k];
+				rb[k] = c3[k] + hs[k];
+			}
+			const float cut = lerp_host(ra[axis], rb[axis], bestPosition);
+			for (int half = 0; half < 2; half++)
+			{
+				float box[6] = { ra[0], ra[1], ra[2], rb[0], rb[1], rb[2] };
+				if (half)
+					box[axis] = cut;
+				else
+					box[3 + axis] = cut;
+				DmcResult child;
+				int rc = mesh_clean(nullptr, positions, normals, verts, indices, tris, 0.0f, MESH_STAGE_CLIP_BOX, s, child, box);
+				if (rc == UPG_OK)
+					rc = chunk_recurse(child.positions, child.normals, child.vertexCount, child.indices, child.triangleCount, maxArea, s, leaves, &child, depth + 1);
+				dmc_release(child, s);
+				if (rc != UPG_OK)
+					return rc;
+			}
+			return UPG_OK;
+		}
+	}
+
+	int mesh_chunking(const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float maxSurfaceArea, cudaStream_t s, std::vector<DmcResult> &leaves)
+	{
+		if (verts >= LOCAL_BIT || (uint64_t)tris * 3 >= 0xffffffffull)
+			return fail(UPG_ERR_ARGUMENT, "mesh too large for the chunking (%u vertices, %u triangles)", verts, tris);
+		const int rc = chunk_recurse(positions, normals, verts, indices, tris, maxSurfaceArea, s, leaves, nullptr, 0);
+		if (rc != UPG_OK)
+		{
+			for (auto &l : leaves)
+				dmc_release(l, s);
+			leaves.clear();
+		}
+		return rc;
+	}
 }
+

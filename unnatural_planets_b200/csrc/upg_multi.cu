@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -82,6 +83,28 @@ namespace upg
 			}
 		};
 
+		// How the devices exchange data inside a call.
+		//   peer  (two devices): NVLink copies between pool allocations (cudaMemcpyPeerAsync, the pools mapped to the peer).  Measured and
+		//         checked bit for bit on 2 x B200 (profiles/r02_g_multi_probe_2gpu.log, tests/test_gpu_multi.py).
+		//   host  (more than two): every device talks to pinned host memory over its OWN PCIe link and nothing is mapped to a peer.  The
+		//         8-GPU run of round 2 (profiles/r02_m_multi_gpu8.md) showed the peer variant failing at 4 and 8 devices on the SECOND call
+		//         of a 1024^3 planet -- cudaErrorMemoryAllocation inside a child's extraction with > 170 GB free, every pool mapped to 3 / 7
+		//         peers -- while the small grids of the tests passed on 3, 4 and 8 devices; the GPU budget ended before the cause was found.
+		//         The host variant uses nothing but cudaMemcpyAsync between device and pinned memory; it costs a few ms per call (two
+		//         PCIe crossings of a ~100 MB mesh instead of one NVLink hop) and is the default beyond two devices until the peer variant
+		//         is understood.  UPG_MULTI_EXCHANGE=peer|host overrides the choice.
+		bool peer_exchange(int devices)
+		{
+			static const int forced = []()
+			{
+				const char *env = std::getenv("UPG_MULTI_EXCHANGE");
+				if (!env)
+					return 0;
+				return std::strcmp(env, "peer") == 0 ? 1 : std::strcmp(env, "host") == 0 ? 2 : 0;
+			}();
+			return forced == 1 || (forced == 0 && devices <= 2);
+		}
+
 		// runs fn(i) on n host threads (i = 0 on the calling thread)
 		template<class F>
 		void fan_out(int n, F fn)
@@ -113,7 +136,7 @@ namespace upg
 		}
 		// the pools of all devices readable / writable by their peers: the chunk gather and the mesh exchange are NVLink copies
 		// between pool allocations.  Devices without peer access fall back to copies staged by the driver (correct, slower).
-		for (int i = 0; i < p->deviceCount; i++)
+		for (int i = 0; i < p->deviceCount && peer_exchange(p->deviceCount); i++)
 		{
 			cudaMemPool_t pool = nullptr;
 			cudaError_t e = cudaSetDevice(p->devices[i]);
@@ -319,7 +342,62 @@ namespace upg
 						if (e != cudaSuccess)
 							rc = cuda_fail(e, "device_alloc(gathered mesh)");
 					}
-					for (int d = 0; d < N && rc == UPG_OK; d++)
+					void *stage = nullptr; // host variant: the field's chunks meet in one pinned block
+					size_t stageCapacity = 0;
+					if (rc == UPG_OK && !peer_exchange(N))
+					{
+						const size_t vb = sizeof(float) * 3 * (size_t)nv, ib = sizeof(uint32_t) * (size_t)ni;
+						e = pinned_block_acquire(vb * 2 + ib, &stage, &stageCapacity);
+						if (e != cudaSuccess)
+							rc = cuda_fail(e, "cudaMallocHost(mesh exchange)");
+						char *hp0 = (char *)stage, *hn0 = hp0 + vb, *hi0 = hn0 + vb;
+						// every chunk down its own device's link ...
+						std::vector<cudaStream_t> down((size_t)N, nullptr);
+						for (int d = 0; d < N && rc == UPG_OK; d++)
+						{
+							const upg_device_mesh &c = chunks[(size_t)d * 3 + f];
+							if (c.vertex_count + c.index_count == 0)
+								continue;
+							e = cudaSetDevice(c.device);
+							if (e == cudaSuccess)
+								e = cudaStreamCreateWithFlags(&down[d], cudaStreamNonBlocking);
+							const size_t v0b = sizeof(float) * 3 * (size_t)off[f].vertex[d];
+							if (e == cudaSuccess && c.vertex_count)
+								e = cudaMemcpyAsync(hp0 + v0b, c.positions, sizeof(float) * 3 * (size_t)c.vertex_count, cudaMemcpyDeviceToHost, down[d]);
+							if (e == cudaSuccess && c.vertex_count)
+								e = cudaMemcpyAsync(hn0 + v0b, c.normals, sizeof(float) * 3 * (size_t)c.vertex_count, cudaMemcpyDeviceToHost, down[d]);
+							if (e == cudaSuccess && c.index_count)
+								e = cudaMemcpyAsync(hi0 + sizeof(uint32_t) * (size_t)off[f].index[d], c.indices, sizeof(uint32_t) * (size_t)c.index_count, cudaMemcpyDeviceToHost, down[d]);
+							if (e != cudaSuccess)
+								rc = cuda_fail(e, "mesh chunk download");
+						}
+						for (int d = 0; d < N; d++)
+							if (down[d])
+							{
+								cudaSetDevice(chunks[(size_t)d * 3 + f].device);
+								e = cudaStreamSynchronize(down[d]);
+								if (e != cudaSuccess && rc == UPG_OK)
+									rc = cuda_fail(e, "mesh chunk download");
+								cudaStreamDestroy(down[d]);
+							}
+						e = cudaSetDevice(hp->device);
+						if (e != cudaSuccess && rc == UPG_OK)
+							rc = cuda_fail(e, "cudaSetDevice");
+						// ... and the whole field up the home device's link
+						if (rc == UPG_OK)
+						{
+							e = cudaMemcpyAsync(pos, hp0, vb, cudaMemcpyHostToDevice, cs.compute);
+							if (e == cudaSuccess)
+								e = cudaMemcpyAsync(nrm, hn0, vb, cudaMemcpyHostToDevice, cs.compute);
+							if (e == cudaSuccess)
+								e = cudaMemcpyAsync(idx, hi0, ib, cudaMemcpyHostToDevice, cs.compute);
+							if (e != cudaSuccess)
+								rc = cuda_fail(e, "gathered mesh upload");
+						}
+						for (int d = 0; d < N && rc == UPG_OK; d++)
+							rc = rebase_ids(idx + off[f].index[d], chunks[(size_t)d * 3 + f].index_count, (uint32_t)off[f].vertex[d], cs.compute);
+					}
+					for (int d = 0; d < N && rc == UPG_OK && peer_exchange(N); d++)
 					{
 						const upg_device_mesh &c = chunks[(size_t)d * 3 + f];
 						const uint64_t v0 = off[f].vertex[d] * 3;
@@ -358,6 +436,8 @@ namespace upg
 						device_free(idx, cs.compute);
 					if (cs.compute)
 						stream_sync(cs.compute);
+					if (stage)
+						pinned_block_release(stage, stageCapacity);
 					cs.close();
 					errors.set(rc);
 				});
@@ -403,6 +483,7 @@ namespace upg
 		Errors errors;
 		Rendezvous allocated(N), sliceUp(N), done(N);
 		const int ach = water ? 4 : 3;
+		const bool peer = peer_exchange(N);
 		fan_out(N, [&](int d)
 			{
 				Planet *c = p->children[d];
@@ -426,7 +507,8 @@ namespace upg
 					HostArray mine[4];
 					for (int a = 0; a < 4; a++)
 					{
-						const size_t b0 = cut(a, d), b1 = cut(a, d + 1);
+						// host variant: the whole mesh up this device's own link, nothing to fetch from the peers
+						const size_t b0 = peer ? cut(a, d) : 0, b1 = peer ? cut(a, d + 1) : arrays[a].bytes;
 						mine[a] = HostArray{ dev[(size_t)d * 4 + a] + b0, arrays[a].host + b0, b1 - b0 };
 					}
 					rc = upload_host_arrays(mine, 4, streams[d], &staging, &stagingCapacity);
@@ -440,7 +522,7 @@ namespace upg
 				// the other parts from the peers, over NVLink, ordered after each peer's own upload
 				if (!errors.failed())
 				{
-					for (int k = 1; k < N && rc == UPG_OK; k++)
+					for (int k = 1; k < N && rc == UPG_OK && peer; k++)
 					{
 						const int o = (d + k) % N; // start with the next device: the N pulls spread over the links
 						e = cudaStreamWaitEvent(streams[d], uploaded[o], 0);
