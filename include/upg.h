@@ -249,6 +249,16 @@ int upg_field_meshes_clean(upg_planet *planet, unsigned field_mask, unsigned sta
  * `box_size` is the clip box edge (the generator's 4000).  The water culling needs the planet: not available here. */
 int upg_mesh_clean(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float box_size, unsigned stages, upg_mesh *out);
 
+/* meshChunking of cage (externals/cage/sources/libcore/mesh/meshAlgorithms.cpp:1484-1619) as the generator's meshSplit calls it
+ * (sources/meshGeneration.cpp:173-182, maxSurfaceArea 800000): the mesh is split recursively -- longest axis of the bounding box, the best of
+ * seven candidate planes by the surface area below each, meshClip of a copy against the two (20 % enlarged) half boxes -- until every part's
+ * surface area is below `max_surface_area`.  `*chunks` = the parts in the reference's order (first half before second half, depth first), each
+ * with positions, normals and indices (dmc_* NULL); parts the clip left empty stay in the list with zero counts, as in the reference.  An empty
+ * input mesh gives zero chunks.  Free with upg_mesh_chunks_free.  Host arrays in, host arrays out; SURVEY.md 8f n4.
+ * STATUS (round 2): written after the round's GPU time was spent -- compiled, never run on a B200; see DESIGN.md "not verified on hardware". */
+int upg_mesh_chunking(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float max_surface_area, upg_mesh **chunks, uint32_t *chunk_count);
+void upg_mesh_chunks_free(upg_mesh *chunks, uint32_t chunk_count);
+
 /*
  * Multi-GPU sharding of K1 + K2..K4 by z-slab ("grid sampling shards naturally by z-slab").  dualmc's scan over z in [0, res-2)
  * (dualmc.tpp:401) is split into `slab_count` contiguous ranges (upg_slab_range); slab k samples its slices plus a 3-slice halo on

@@ -261,6 +261,33 @@ class RefPlanet:
         return self._take(p, np.float32, 3), self._take(n, np.float32, 3), self._take(i, np.uint32, 1)
 
     # --- chunking + unwrap (the serial geometry between stage 2 and stage 3; out of the product's scope) ---------------------------
+    def chunking(self, positions, normals, indices, max_surface_area=800000.0):
+        """meshSplit of sources/meshGeneration.cpp:173-182 (cage meshChunking) alone: list of dict(positions, normals, indices)"""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        n = C.c_uint32(0)
+        self._check(self.lib.upref_chunking(_fp(pos), _fp(nrm), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), C.c_float(max_surface_area), C.byref(n)))
+        return [self._held_chunk(i) for i in range(n.value)]
+
+    def _held_chunk(self, i):
+        nv, ni = C.c_uint32(0), C.c_uint32(0)
+        self.lib.upref_chunk_size(C.c_uint32(i), C.byref(nv), C.byref(ni))
+        c = dict(positions=np.zeros((nv.value, 3), np.float32), normals=np.zeros((nv.value, 3), np.float32), indices=np.zeros(ni.value, np.uint32))
+        if nv.value or ni.value:
+            self.lib.upref_chunk_copy(C.c_uint32(i), _fp(c["positions"]), _fp(c["normals"]), None, _fp(c["indices"]))
+        return c
+
+    def clip_box(self, positions, normals, indices, box6):
+        """cage meshClip(mesh, Aabb) (meshAlgorithms.cpp:1056-1114) of a copy of the mesh: dict(positions, normals, indices)"""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+        box = np.ascontiguousarray(box6, dtype=np.float32).reshape(6)
+        nv, ni = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.upref_mesh_clip_box(_fp(pos), _fp(nrm), C.c_uint32(len(pos)), _fp(idx), C.c_uint32(len(idx)), _fp(box), C.byref(nv), C.byref(ni)))
+        return self._held_chunk(0)
+
     def chunk_and_unwrap(self, positions, normals, indices, max_surface_area=800000.0, texels_per_unit=1.35, padding=6):
         """meshSplit + meshUnwrap of sources/meshGeneration.cpp:173-197 (cage meshChunking, xatlas): a list of chunks, each a dict with
         positions, normals, uvs, indices and the atlas `resolution` xatlas chose for it"""

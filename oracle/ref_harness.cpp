@@ -422,6 +422,30 @@ extern "C"
 				*chunkCount = (uint32_t)heldChunks.size();
 			});
 	}
+	// chunk i as meshChunking left it (before any unwrap): its sizes; upref_chunk_copy(i, pos, nrm, NULL, idx) hands out the arrays
+	void upref_chunk_size(uint32_t i, uint32_t *nverts, uint32_t *nidx)
+	{
+		*nverts = heldChunks[i]->verticesCount();
+		*nidx = heldChunks[i]->indicesCount();
+	}
+	// meshClip(Mesh *, const Aabb &) (meshAlgorithms.cpp:1056-1114) of a copy of the mesh against box6 = { a.x, a.y, a.z, b.x, b.y, b.z }: the step the
+	// chunking recursion repeats.  The result is held as chunk 0 (upref_chunk_size / upref_chunk_copy).
+	int upref_mesh_clip_box(const float *pos, const float *nrm, uint32_t nv, const uint32_t *idx, uint32_t ni, const float *box6, uint32_t *nverts, uint32_t *nidx)
+	{
+		return guarded(
+			[&]()
+			{
+				Holder<Mesh> m = newMesh();
+				m->positions(PointerRange<const Vec3>((const Vec3 *)pos, (const Vec3 *)pos + nv));
+				m->normals(PointerRange<const Vec3>((const Vec3 *)nrm, (const Vec3 *)nrm + nv));
+				m->indices(PointerRange<const uint32>(idx, idx + ni));
+				meshClip(+m, Aabb(Vec3(box6[0], box6[1], box6[2]), Vec3(box6[3], box6[4], box6[5])));
+				heldChunks.clear();
+				heldChunks.push_back(std::move(m));
+				*nverts = heldChunks[0]->verticesCount();
+				*nidx = heldChunks[0]->indicesCount();
+			});
+	}
 	// meshUnwrap(const Holder<Mesh> &) of sources/meshGeneration.cpp:184-197 on chunk i; returns the atlas resolution
 	int upref_chunk_unwrap(uint32_t i, float texelsPerUnit, uint32_t padding, uint32_t *resolution, uint32_t *nverts, uint32_t *nidx)
 	{

@@ -134,20 +134,3 @@ def test_large_image_and_errors():
     assert rc == 1 and b"too small" in L.upg_last_error()
     assert L.upg_png_encode(0, small.ctypes.data_as(C.c_void_p), 8, 8, 5, out.ctypes.data_as(C.c_void_p), 64, C.byref(size)) == 1
     assert L.upg_png_encode(0, small.ctypes.data_as(C.c_void_p), 0, 8, 3, out.ctypes.data_as(C.c_void_p), 64, C.byref(size)) == 1
-
-
-def test_bake_export_png_equals_bake_export_then_decode():
-    """upg_bake_export_png = bake + texture tail + three PNG files in one call: decoding the files gives upg_bake_export's images"""
-    p = Planet(shape="sphere", elevation="lakes", grid=160)
-    for name, water in (("land", 0), ("water", 1)):
-        m = p.field_meshes_clean((name,))[name]
-        uv = synth.octahedral_uv(m["positions"])
-        idx = synth.drop_folded_triangles(uv, m["indices"])
-        want = p.bake_export(water, m["positions"], m["normals"], uv, idx, 1024, 768)
-        covered = p.last_covered_texels
-        files = p.bake_export_png(water, m["positions"], m["normals"], uv, idx, 1024, 768)
-        assert p.last_covered_texels == covered
-        for f, img in zip(files, want):
-            got = pil_decode(f.tobytes())
-            assert np.array_equal(got.reshape(img.shape), img), name
-            assert len(f) < img.nbytes

@@ -141,6 +141,9 @@ def load_library():
     L.upg_device_mesh_free.restype = None
     L.upg_field_meshes_clean.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(Mesh)]
     L.upg_mesh_clean.argtypes = [i32, fp, fp, C.c_uint32, fp, C.c_uint32, C.c_float, C.c_uint, C.POINTER(Mesh)]
+    L.upg_mesh_chunking.argtypes = [i32, fp, fp, C.c_uint32, fp, C.c_uint32, C.c_float, C.POINTER(C.POINTER(Mesh)), C.POINTER(C.c_uint32)]
+    L.upg_mesh_chunks_free.argtypes = [C.POINTER(Mesh), C.c_uint32]
+    L.upg_mesh_chunks_free.restype = None
     L.upg_field_points.argtypes = [vp, i32, fp, u64, fp]
     L.upg_field_mesh.argtypes = [vp, i32, C.POINTER(Mesh)]
     L.upg_field_mesh_slab.argtypes = [vp, i32, i32, i32, C.POINTER(Mesh)]

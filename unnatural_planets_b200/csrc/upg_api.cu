@@ -1546,6 +1546,90 @@ extern "C"
 		return rc;
 	}
 
+	int upg_mesh_chunking(int device, const float *positions, const float *normals, uint32_t vertex_count, const uint32_t *indices, uint32_t index_count, float max_surface_area, upg_mesh **chunks, uint32_t *chunk_count)
+	{
+		if (!chunks || !chunk_count)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		*chunks = nullptr;
+		*chunk_count = 0;
+		if ((!positions || !normals) && vertex_count)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (!indices && index_count)
+			return fail(UPG_ERR_ARGUMENT, "null argument");
+		if (index_count % 3 != 0)
+			return fail(UPG_ERR_ARGUMENT, "mesh chunking requires triangles mesh");
+		if (!(max_surface_area > 0))
+			return fail(UPG_ERR_ARGUMENT, "mesh chunking requires positive maxSurfaceArea");
+		if (index_count == 0)
+			return UPG_OK; // meshChunking: `if (msh->facesCount() == 0) return {};`
+		for (uint32_t i = 0; i < index_count; i++)
+			if (indices[i] >= vertex_count)
+				return fail(UPG_ERR_ARGUMENT, "index %u out of range (%u vertices)", indices[i], vertex_count);
+		cudaError_t e = cudaSetDevice(device);
+		if (e != cudaSuccess)
+			return cuda_fail(e, "cudaSetDevice");
+		CallStreams cs;
+		int rc = cs.open();
+		if (rc)
+			return rc;
+		cudaStream_t s = cs.compute;
+		float *dp = nullptr, *dn = nullptr;
+		uint32_t *di = nullptr;
+		e = device_alloc(&dp, sizeof(float) * 3 * (size_t)vertex_count, s);
+		if (e == cudaSuccess)
+			e = device_alloc(&dn, sizeof(float) * 3 * (size_t)vertex_count, s);
+		if (e == cudaSuccess)
+			e = device_alloc(&di, sizeof(uint32_t) * (size_t)index_count, s);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dp, positions, sizeof(float) * 3 * (size_t)vertex_count, cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(dn, normals, sizeof(float) * 3 * (size_t)vertex_count, cudaMemcpyHostToDevice, s);
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(di, indices, sizeof(uint32_t) * (size_t)index_count, cudaMemcpyHostToDevice, s);
+		if (e != cudaSuccess)
+			rc = cuda_fail(e, "upload mesh");
+		std::vector<DmcResult> leaves;
+		if (rc == UPG_OK)
+			rc = mesh_chunking(dp, dn, vertex_count, di, index_count / 3, max_surface_area, s, leaves);
+		upg_mesh *list = nullptr;
+		if (rc == UPG_OK)
+		{
+			list = static_cast<upg_mesh *>(std::calloc(leaves.size() ? leaves.size() : 1, sizeof(upg_mesh)));
+			if (!list)
+				rc = fail(UPG_ERR_ARGUMENT, "out of host memory");
+		}
+		for (size_t i = 0; i < leaves.size() && rc == UPG_OK; i++)
+			rc = mesh_to_host(leaves[i], s, &list[i]);
+		for (auto &l : leaves)
+			dmc_release(l, s);
+		if (dp)
+			cudaFreeAsync(dp, s);
+		if (dn)
+			cudaFreeAsync(dn, s);
+		if (di)
+			cudaFreeAsync(di, s);
+		stream_sync(s);
+		cs.close();
+		if (rc != UPG_OK)
+		{
+			if (list)
+				upg_mesh_chunks_free(list, (uint32_t)leaves.size());
+			return rc;
+		}
+		*chunks = list;
+		*chunk_count = (uint32_t)leaves.size();
+		return UPG_OK;
+	}
+
+	void upg_mesh_chunks_free(upg_mesh *chunks, uint32_t chunk_count)
+	{
+		if (!chunks)
+			return;
+		for (uint32_t i = 0; i < chunk_count; i++)
+			upg_mesh_free(&chunks[i]);
+		std::free(chunks);
+	}
+
 	void upg_slab_range(int grid_resolution, int slab, int slab_count, int *z0, int *z1)
 	{
 		// dualmc's z loop runs over [0, res - 2) (dualmc.tpp:401); split it evenly, earlier slabs take the remainder

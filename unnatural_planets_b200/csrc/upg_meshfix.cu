@@ -25,6 +25,7 @@
 
 #include "../../include/upg.h"
 #include "upg_internal.h"
+#include "upg_chunking_host.h"
 
 namespace upg
 {
@@ -1089,15 +1090,6 @@ namespace upg
 			}
 		}
 
-		// the reference's float expressions on the host (Real = float; -ffp-contract=off for the host side of this library)
-		float lerp_host(float a, float b, float f) { return a + (b - a) * f; } // interpolate (math.h:1173-1177)
-
-		struct ChunkNode
-		{
-			DmcResult mesh; // positions, normals, indices (device, pool)
-			bool owned; // false for the caller's root arrays
-		};
-
 		int chunk_recurse(const float *positions, const float *normals, uint32_t verts, const uint32_t *indices, uint32_t tris, float maxArea, cudaStream_t s, std::vector<DmcResult> &leaves, DmcResult *own, int depth)
 		{
 			// own != nullptr: this node's arrays belong to *own (released here unless it becomes a leaf)
@@ -1158,21 +1150,10 @@ namespace upg
 				a[k] = key_to_float(hostKeys[k]);
 				b[k] = key_to_float(hostKeys[3 + k]);
 			}
-			// boxLongestAxis (:1498-1507) over dominantAxis(size) (math/vectors.cpp:305-312)
-			const float sz[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] };
-			const float ax = sz[0] < 0 ? -sz[0] : sz[0], ay = sz[1] < 0 ? -sz[1] : sz[1], az = sz[2] < 0 ? -sz[2] : sz[2];
-			int axis;
-			if (ax > ay && ax > az)
-				axis = sz[0] != 0 ? 0 : 2; // sign(0) = 0: `a[0] == 1` fails, so does a[1] -> 2
-			else if (ay > az)
-				axis = sz[1] != 0 ? 1 : 2;
-			else
-				axis = 2;
-			static const float Positions[7] = { (float)0.3, (float)0.4, (float)0.45, (float)0.5, (float)0.55, (float)0.6, (float)0.7 };
 			ChunkSplit split;
-			split.axis = axis;
-			for (int i = 0; i < 7; i++)
-				split.positions[i] = lerp_host(a[axis], b[axis], Positions[i]);
+			split.axis = chunk_longest_axis(a, b);
+			const int axis = split.axis;
+			chunk_candidates(a, b, axis, split.positions);
 			float hostSums[8];
 			if (e == cudaSuccess)
 			{
@@ -1184,41 +1165,15 @@ namespace upg
 			MF_TRY(stream_sync(s));
 			if (e != cudaSuccess)
 				return cuda_fail(e, "mesh chunking (areas)");
-			const float myArea = hostSums[0];
-			if (myArea < maxArea)
+			float fraction = 0;
+			if (!chunk_wants_split(hostSums, maxArea, &fraction))
 				return leaf();
-			float bestPosition = Positions[0], bestDiff = INFINITY;
-			bool any = false;
-			for (int i = 0; i < 7; i++)
-			{
-				float d = (float)0.5 - hostSums[1 + i] / myArea;
-				d = d < 0 ? -d : d;
-				if (d < bestDiff)
-				{
-					bestDiff = d;
-					bestPosition = Positions[i];
-					any = true;
-				}
-			}
-			if (!any)
+			if (!(fraction == fraction))
 				return fail(UPG_ERR_INVALID_VALUE, "mesh chunking: no split position (NaN surface area)");
-			// clippingBox (:1509-1520): the bounding box blown up by 20 %, cut at `position` of the BLOWN-UP extent
-			float c3[3], hs[3], ra[3], rb[3];
-			for (int k = 0; k < 3; k++)
-			{
-				c3[k] = (a[k] + b[k]) * (float)0.5; // Aabb::center()
-				hs[k] = (b[k] - a[k]) * (float)0.6;
-				ra[k] = c3[k] - hs[k];
-				rb[k] = c3[k] + hs[k];
-			}
-			const float cut = lerp_host(ra[axis], rb[axis], bestPosition);
 			for (int half = 0; half < 2; half++)
 			{
-				float box[6] = { ra[0], ra[1], ra[2], rb[0], rb[1], rb[2] };
-				if (half)
-					box[axis] = cut;
-				else
-					box[3 + axis] = cut;
+				float box[6];
+				chunk_clipping_box(a, b, axis, fraction, half != 0, box);
 				DmcResult child;
 				int rc = mesh_clean(nullptr, positions, normals, verts, indices, tris, 0.0f, MESH_STAGE_CLIP_BOX, s, child, box);
 				if (rc == UPG_OK)

@@ -118,6 +118,28 @@ def mesh_clean(positions, normals, indices, box=4000.0, stages=7, device=0):
     return _mesh_to_numpy(L, m)
 
 
+def mesh_chunking(positions, normals, indices, max_surface_area=800000.0, device=0):
+    """cage's meshChunking as the generator's meshSplit calls it (upg_mesh_chunking) over a host triangle mesh -> list of
+    dict(positions, normals, indices), in the reference's order (empty parts included)."""
+    L = capi.load_library()
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    chunks, count = C.POINTER(capi.Mesh)(), C.c_uint32(0)
+    capi.check(L.upg_mesh_chunking(device, _ptr(pos), _ptr(nrm), len(pos), _ptr(idx), len(idx), max_surface_area, C.byref(chunks), C.byref(count)))
+    out = []
+    for i in range(count.value):
+        m = chunks[i]
+        nv, ni = m.vertex_count, m.index_count
+        out.append(dict(
+            positions=(np.ctypeslib.as_array(m.positions, shape=(nv * 3,)).astype(np.float32, copy=True) if nv else np.zeros(0, np.float32)).reshape(-1, 3),
+            normals=(np.ctypeslib.as_array(m.normals, shape=(nv * 3,)).astype(np.float32, copy=True) if nv else np.zeros(0, np.float32)).reshape(-1, 3),
+            indices=np.ctypeslib.as_array(m.indices, shape=(ni,)).astype(np.uint32, copy=True) if ni else np.zeros(0, np.uint32),
+        ))
+    L.upg_mesh_chunks_free(chunks, count)
+    return out
+
+
 def texture_tail(special=None, height=None, strength=1.0, device=0):
     """K8 alone (upg_texture_tail): special (h,w,2) u8 -> pbr (h,w,3); height (h,w[,1]) u8 -> normal map (h,w,3)."""
     L = capi.load_library()
