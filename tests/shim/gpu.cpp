@@ -20,6 +20,7 @@
 #include <cage-core/logger.h>
 #include <cage-core/math.h>
 #include <cage-core/memoryBuffer.h>
+#include <cage-core/pointerRangeHolder.h>
 #include <cage-core/mesh.h>
 #include <cage-core/random.h>
 #include <cage-core/string.h>
@@ -57,6 +58,7 @@ namespace unnatural
 		}
 
 		std::once_flag baseOnce;
+		int gpuHomeDevice = 0; // first device of unnatural-planets/gpu/devices
 		upg_mesh baseMeshes[3]; // UPG_FIELD_LAND, UPG_FIELD_WATER, UPG_FIELD_NAVIGATION
 		int baseRc = UPG_OK;
 		std::string baseError;
@@ -164,12 +166,39 @@ namespace unnatural
 		while (!devices.empty() && d.device_count < UPG_MAX_DEVICES)
 			d.devices[d.device_count++] = toSint32(split(devices, ","));
 		d.device = d.device_count ? d.devices[0] : 0;
+		gpuHomeDevice = d.device;
 		upgCheck(upg_planet_create(&d, &gpuPlanet));
 	}
 
 	Holder<Mesh> meshGenerateBaseLand() { return takeBaseMesh(UPG_FIELD_LAND, "land"); } // replaces sources/meshGeneration.cpp:47-55
 	Holder<Mesh> meshGenerateBaseWater() { return takeBaseMesh(UPG_FIELD_WATER, "water"); } // :57-98
 	Holder<Mesh> meshGenerateBaseNavigation() { return takeBaseMesh(UPG_FIELD_NAVIGATION, "navigation"); } // :100-107
+
+	// replaces meshSplit (sources/meshGeneration.cpp:173-182): cage's meshChunking(maxSurfaceArea 800000) on the device.  Same chunks in the same
+	// order (first half before second half, depth first; parts the clip left empty stay in the list).  Compiled here against cage's headers;
+	// the device side has not run on hardware yet, so the test entry does not call it.
+	Holder<PointerRange<Holder<Mesh>>> meshSplitGpu(const Holder<Mesh> &mesh)
+	{
+		upg_mesh *chunks = nullptr;
+		uint32_t count = 0;
+		upgCheck(upg_mesh_chunking(gpuHomeDevice, (const float *)mesh->positions().data(), (const float *)mesh->normals().data(), mesh->verticesCount(), mesh->indices().data(), mesh->indicesCount(), 800000.0f, &chunks, &count));
+		PointerRangeHolder<Holder<Mesh>> result;
+		result.reserve(count);
+		for (uint32_t i = 0; i < count; i++)
+		{
+			const upg_mesh &m = chunks[i];
+			Holder<Mesh> poly = newMesh();
+			if (m.index_count)
+			{
+				poly->positions(PointerRange<const Vec3>((const Vec3 *)m.positions, (const Vec3 *)m.positions + m.vertex_count));
+				poly->normals(PointerRange<const Vec3>((const Vec3 *)m.normals, (const Vec3 *)m.normals + m.vertex_count));
+				poly->indices(PointerRange<const uint32>(m.indices, m.indices + m.index_count));
+			}
+			result.push_back(std::move(poly));
+		}
+		upg_mesh_chunks_free(chunks, count);
+		return result;
+	}
 
 	void generateTexturesLandGpu(const Holder<Mesh> &renderMesh, uint32 width, uint32 height, Holder<Image> &albedo, Holder<Image> &special, Holder<Image> &heightMap)
 	{
