@@ -109,39 +109,60 @@ namespace upg
 		return hsv_to_rgb(hsv);
 	}
 
-	// ---- hsluv.c, double precision ---------------------------------------------------------------
+	// ---- hsluv.c ------------------------------------------------------------------------------------
+	// The reference evaluates HSLuv in DOUBLE (hsluv.c), and so does the default build: UPG_HSLUV_REAL = double.  -DUPG_HSLUV_REAL=float
+	// is an experiment switch, NOT a supported build: the same expressions in single precision (sinf / cosf / powf / cbrtf / atan2f),
+	// used by tools/hsluv_precision.py to count on the CPU how many texels of a bake an FP32 HSLuv would change.
+#ifndef UPG_HSLUV_REAL
+#define UPG_HSLUV_REAL double
+#endif
+	typedef UPG_HSLUV_REAL HR;
+	UPG_HD double hr_sin(double x) { return sin(x); }
+	UPG_HD double hr_cos(double x) { return cos(x); }
+	UPG_HD double hr_pow(double x, double y) { return pow(x, y); }
+	UPG_HD double hr_cbrt(double x) { return cbrt(x); }
+	UPG_HD double hr_sqrt(double x) { return sqrt(x); }
+	UPG_HD double hr_atan2(double y, double x) { return atan2(y, x); }
+	UPG_HD float hr_sin(float x) { return sinf(x); }
+	UPG_HD float hr_cos(float x) { return cosf(x); }
+	UPG_HD float hr_pow(float x, float y) { return powf(x, y); }
+	UPG_HD float hr_cbrt(float x) { return cbrtf(x); }
+	UPG_HD float hr_sqrt(float x) { return sqrtf(x); }
+	UPG_HD float hr_atan2(float y, float x) { return atan2f(y, x); }
+	UPG_HD double hr_max(double) { return DBL_MAX; }
+	UPG_HD float hr_max(float) { return FLT_MAX; }
 	struct D3
 	{
-		double a, b, c;
+		HR a, b, c;
 	};
 
 	namespace hsluv
 	{
 		struct Bounds
 		{
-			double a, b;
+			HR a, b;
 		};
 
-		UPG_HD void get_bounds(double l, Bounds *bounds)
+		UPG_HD void get_bounds(HR l, Bounds *bounds)
 		{
-			const double m[3][3] = {
-				{ 3.24096994190452134377, -1.53738317757009345794, -0.49861076029300328366 },
-				{ -0.96924363628087982613, 1.87596750150772066772, 0.04155505740717561247 },
-				{ 0.05563007969699360846, -0.20397695888897656435, 1.05697151424287856072 },
+			const HR m[3][3] = {
+				{ HR(3.24096994190452134377), HR(-1.53738317757009345794), HR(-0.49861076029300328366) },
+				{ HR(-0.96924363628087982613), HR(1.87596750150772066772), HR(0.04155505740717561247) },
+				{ HR(0.05563007969699360846), HR(-0.20397695888897656435), HR(1.05697151424287856072) },
 			};
-			const double kappa = 903.29629629629629629630;
-			const double epsilon = 0.00885645167903563082;
-			const double tl = l + 16.0;
-			const double sub1 = (tl * tl * tl) / 1560896.0;
-			const double sub2 = (sub1 > epsilon ? sub1 : (l / kappa));
+			const HR kappa = HR(903.29629629629629629630);
+			const HR epsilon = HR(0.00885645167903563082);
+			const HR tl = l + HR(16.0);
+			const HR sub1 = (tl * tl * tl) / HR(1560896.0);
+			const HR sub2 = (sub1 > epsilon ? sub1 : (l / kappa));
 			for (int channel = 0; channel < 3; channel++)
 			{
-				const double m1 = m[channel][0], m2 = m[channel][1], m3 = m[channel][2];
+				const HR m1 = m[channel][0], m2 = m[channel][1], m3 = m[channel][2];
 				for (int t = 0; t < 2; t++)
 				{
-					const double top1 = (284517.0 * m1 - 94839.0 * m3) * sub2;
-					const double top2 = (838422.0 * m3 + 769860.0 * m2 + 731718.0 * m1) * l * sub2 - 769860.0 * t * l;
-					const double bottom = (632260.0 * m3 - 126452.0 * m2) * sub2 + 126452.0 * t;
+					const HR top1 = (HR(284517.0) * m1 - HR(94839.0) * m3) * sub2;
+					const HR top2 = (HR(838422.0) * m3 + HR(769860.0) * m2 + HR(731718.0) * m1) * l * sub2 - HR(769860.0) * t * l;
+					const HR bottom = (HR(632260.0) * m3 - HR(126452.0) * m2) * sub2 + HR(126452.0) * t;
 					bounds[channel * 2 + t].a = top1 / bottom;
 					bounds[channel * 2 + t].b = top2 / bottom;
 				}
@@ -149,137 +170,137 @@ namespace upg
 		}
 
 		// `sn` / `cs` hand sin / cos of the hue back to hsluv2rgb, whose lch2luv step needs the same two values (hsluv.c computes them twice)
-		UPG_HD double max_chroma_for_lh(double l, double h, double &sn, double &cs)
+		UPG_HD HR max_chroma_for_lh(HR l, HR h, HR &sn, HR &cs)
 		{
-			double minLen = DBL_MAX;
-			const double hrad = h * 0.01745329251994329577;
+			HR minLen = hr_max(HR(0));
+			const HR hrad = h * HR(0.01745329251994329577);
 			Bounds bounds[6];
 			get_bounds(l, bounds);
-			sn = sin(hrad);
-			cs = cos(hrad);
+			sn = hr_sin(hrad);
+			cs = hr_cos(hrad);
 			for (int i = 0; i < 6; i++)
 			{
-				const double len = bounds[i].b / (sn - bounds[i].a * cs);
+				const HR len = bounds[i].b / (sn - bounds[i].a * cs);
 				if (len >= 0 && len < minLen)
 					minLen = len;
 			}
 			return minLen;
 		}
 
-		UPG_HD double from_linear(double c)
+		UPG_HD HR from_linear(HR c)
 		{
-			if (c <= 0.0031308)
-				return 12.92 * c;
-			return 1.055 * pow(c, 1.0 / 2.4) - 0.055;
+			if (c <= HR(0.0031308))
+				return HR(12.92) * c;
+			return HR(1.055) * hr_pow(c, HR(1.0) / HR(2.4)) - HR(0.055);
 		}
 
-		UPG_HD double to_linear(double c)
+		UPG_HD HR to_linear(HR c)
 		{
-			if (c > 0.04045)
-				return pow((c + 0.055) / 1.055, 2.4);
-			return c / 12.92;
+			if (c > HR(0.04045))
+				return hr_pow((c + HR(0.055)) / HR(1.055), HR(2.4));
+			return c / HR(12.92);
 		}
 
-		UPG_COLOR_OUTLINED D3 rgb2hsluv(double r, double g, double b)
+		UPG_COLOR_OUTLINED D3 rgb2hsluv(HR r, HR g, HR b)
 		{
-			const double kappa = 903.29629629629629629630;
-			const double epsilon = 0.00885645167903563082;
-			const double refU = 0.19783000664283680764, refV = 0.46831999493879100370;
+			const HR kappa = HR(903.29629629629629629630);
+			const HR epsilon = HR(0.00885645167903563082);
+			const HR refU = HR(0.19783000664283680764), refV = HR(0.46831999493879100370);
 			// rgb2xyz
-			const double lr = to_linear(r), lg = to_linear(g), lb = to_linear(b);
-			const double X = 0.41239079926595948129 * lr + 0.35758433938387796373 * lg + 0.18048078840183428751 * lb;
-			const double Y = 0.21263900587151035754 * lr + 0.71516867876775592746 * lg + 0.07219231536073371500 * lb;
-			const double Z = 0.01933081871559185069 * lr + 0.11919477979462598791 * lg + 0.95053215224966058086 * lb;
+			const HR lr = to_linear(r), lg = to_linear(g), lb = to_linear(b);
+			const HR X = HR(0.41239079926595948129) * lr + HR(0.35758433938387796373) * lg + HR(0.18048078840183428751) * lb;
+			const HR Y = HR(0.21263900587151035754) * lr + HR(0.71516867876775592746) * lg + HR(0.07219231536073371500) * lb;
+			const HR Z = HR(0.01933081871559185069) * lr + HR(0.11919477979462598791) * lg + HR(0.95053215224966058086) * lb;
 			// xyz2luv
-			const double varU = (4.0 * X) / (X + (15.0 * Y) + (3.0 * Z));
-			const double varV = (9.0 * Y) / (X + (15.0 * Y) + (3.0 * Z));
-			const double L = Y <= epsilon ? Y * kappa : 116.0 * cbrt(Y) - 16.0;
-			double U = 13.0 * L * (varU - refU);
-			double V = 13.0 * L * (varV - refV);
-			if (L < 0.00000001)
+			const HR varU = (HR(4.0) * X) / (X + (HR(15.0) * Y) + (HR(3.0) * Z));
+			const HR varV = (HR(9.0) * Y) / (X + (HR(15.0) * Y) + (HR(3.0) * Z));
+			const HR L = Y <= epsilon ? Y * kappa : HR(116.0) * hr_cbrt(Y) - HR(16.0);
+			HR U = HR(13.0) * L * (varU - refU);
+			HR V = HR(13.0) * L * (varV - refV);
+			if (L < HR(0.00000001))
 			{
-				U = 0.0;
-				V = 0.0;
+				U = HR(0.0);
+				V = HR(0.0);
 			}
 			// luv2lch
-			const double C = sqrt(U * U + V * V);
-			double H;
-			if (C < 0.00000001)
+			const HR C = hr_sqrt(U * U + V * V);
+			HR H;
+			if (C < HR(0.00000001))
 				H = 0;
 			else
 			{
-				H = atan2(V, U) * 57.29577951308232087680;
-				if (H < 0.0)
-					H += 360.0;
+				H = hr_atan2(V, U) * HR(57.29577951308232087680);
+				if (H < HR(0.0))
+					H += HR(360.0);
 			}
 			// lch2hsluv
-			double S;
-			if (L > 99.9999999 || L < 0.00000001)
-				S = 0.0;
+			HR S;
+			if (L > HR(99.9999999) || L < HR(0.00000001))
+				S = HR(0.0);
 			else
 			{
-				double sn, cs;
-				S = C / max_chroma_for_lh(L, H, sn, cs) * 100.0;
+				HR sn, cs;
+				S = C / max_chroma_for_lh(L, H, sn, cs) * HR(100.0);
 			}
-			if (C < 0.00000001)
-				H = 0.0;
+			if (C < HR(0.00000001))
+				H = HR(0.0);
 			return D3{ H, S, L };
 		}
 
-		UPG_COLOR_OUTLINED D3 hsluv2rgb(double h, double s, double l)
+		UPG_COLOR_OUTLINED D3 hsluv2rgb(HR h, HR s, HR l)
 		{
-			const double kappa = 903.29629629629629629630;
-			const double refU = 0.19783000664283680764, refV = 0.46831999493879100370;
+			const HR kappa = HR(903.29629629629629629630);
+			const HR refU = HR(0.19783000664283680764), refV = HR(0.46831999493879100370);
 			// hsluv2lch
-			double c, sn = 0.0, cs = 1.0;
+			HR c, sn = HR(0.0), cs = HR(1.0);
 			bool trig = false; // sn / cs hold sin / cos of h * pi / 180
-			if (l > 99.9999999 || l < 0.00000001)
-				c = 0.0;
+			if (l > HR(99.9999999) || l < HR(0.00000001))
+				c = HR(0.0);
 			else
 			{
-				c = max_chroma_for_lh(l, h, sn, cs) / 100.0 * s;
+				c = max_chroma_for_lh(l, h, sn, cs) / HR(100.0) * s;
 				trig = true;
 			}
-			if (s < 0.00000001)
+			if (s < HR(0.00000001))
 			{
-				h = 0.0;
-				sn = 0.0; // sin(0.0), cos(0.0): exact in every libm
-				cs = 1.0;
+				h = HR(0.0);
+				sn = HR(0.0); // hr_sin(HR(0.0)), hr_cos(HR(0.0)): exact in every libm
+				cs = HR(1.0);
 				trig = true;
 			}
 			// lch2luv
 			if (!trig)
 			{
-				const double hrad = h * 0.01745329251994329577;
-				sn = sin(hrad);
-				cs = cos(hrad);
+				const HR hrad = h * HR(0.01745329251994329577);
+				sn = hr_sin(hrad);
+				cs = hr_cos(hrad);
 			}
-			const double u = cs * c;
-			const double v = sn * c;
+			const HR u = cs * c;
+			const HR v = sn * c;
 			// luv2xyz
-			double X, Y, Z;
-			if (l <= 0.00000001)
+			HR X, Y, Z;
+			if (l <= HR(0.00000001))
 			{
-				X = Y = Z = 0.0;
+				X = Y = Z = HR(0.0);
 			}
 			else
 			{
-				const double varU = u / (13.0 * l) + refU;
-				const double varV = v / (13.0 * l) + refV;
-				if (l <= 8.0)
+				const HR varU = u / (HR(13.0) * l) + refU;
+				const HR varV = v / (HR(13.0) * l) + refV;
+				if (l <= HR(8.0))
 					Y = l / kappa;
 				else
 				{
-					const double x = (l + 16.0) / 116.0;
+					const HR x = (l + HR(16.0)) / HR(116.0);
 					Y = (x * x * x);
 				}
-				X = -(9.0 * Y * varU) / ((varU - 4.0) * varV - varU * varV);
-				Z = (9.0 * Y - (15.0 * varV * Y) - (varV * X)) / (3.0 * varV);
+				X = -(HR(9.0) * Y * varU) / ((varU - HR(4.0)) * varV - varU * varV);
+				Z = (HR(9.0) * Y - (HR(15.0) * varV * Y) - (varV * X)) / (HR(3.0) * varV);
 			}
 			// xyz2rgb
-			const double r = from_linear(3.24096994190452134377 * X + -1.53738317757009345794 * Y + -0.49861076029300328366 * Z);
-			const double g = from_linear(-0.96924363628087982613 * X + 1.87596750150772066772 * Y + 0.04155505740717561247 * Z);
-			const double b = from_linear(0.05563007969699360846 * X + -0.20397695888897656435 * Y + 1.05697151424287856072 * Z);
+			const HR r = from_linear(HR(3.24096994190452134377) * X + HR(-1.53738317757009345794) * Y + HR(-0.49861076029300328366) * Z);
+			const HR g = from_linear(HR(-0.96924363628087982613) * X + HR(1.87596750150772066772) * Y + HR(0.04155505740717561247) * Z);
+			const HR b = from_linear(HR(0.05563007969699360846) * X + HR(-0.20397695888897656435) * Y + HR(1.05697151424287856072) * Z);
 			return D3{ r, g, b };
 		}
 	}
@@ -287,14 +308,14 @@ namespace upg
 	// colorRgbToHsluv (color.cpp:165-174): h / 360, s / 100, l / 100 in double, narrowed to Real
 	UPG_HD V3 rgb_to_hsluv(V3 rgb)
 	{
-		const D3 r = hsluv::rgb2hsluv((double)rgb.x, (double)rgb.y, (double)rgb.z);
+		const D3 r = hsluv::rgb2hsluv((HR)rgb.x, (HR)rgb.y, (HR)rgb.z);
 		return v3((float)(r.a / 360), (float)(r.b / 100), (float)(r.c / 100));
 	}
 
 	// colorHsluvToRgb (color.cpp:176-183): the products are FLOAT products widened afterwards; result saturated
 	UPG_HD V3 hsluv_to_rgb(V3 hsl)
 	{
-		const double h = (double)(hsl.x * 360.0f), s = (double)(hsl.y * 100.0f), l = (double)(hsl.z * 100.0f);
+		const HR h = (HR)(hsl.x * 360.0f), s = (HR)(hsl.y * 100.0f), l = (HR)(hsl.z * 100.0f);
 		const D3 r = hsluv::hsluv2rgb(h, s, l);
 		return v3(saturate_((float)r.a), saturate_((float)r.b), saturate_((float)r.c));
 	}
