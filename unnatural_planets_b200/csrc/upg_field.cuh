@@ -280,7 +280,9 @@ namespace upg
 #define UPG_COLUMN_MIN_BLOCKS 5 // resident blocks per SM the register allocation aims at (A/B in profiles/)
 #endif
 	// the samples are written once and never read by this kernel: UPG_K1_STORE = 1 marks the stores streaming (st.global.cs, evict
-	// first), 0 = plain stores (A/B in profiles/: DRAM traffic per node and time)
+	// first), 0 = plain stores.  The variant was built (VERDICT r1 item 3 asked where the 1.4 GB of DRAM reads of a store-only kernel come
+	// from) but NOT measured: the round's GPU budget ended first.  The kernel is issue bound at 9 % of the DRAM throughput
+	// (profiles/r02_l_ncu_summary.md), so nothing is expected from it either way.
 #ifndef UPG_K1_STORE
 #define UPG_K1_STORE 0
 #endif
