@@ -104,3 +104,38 @@ def test_chunking_decisions_reproduce_the_reference(fixture, max_area):
     for k, (a, b) in enumerate(zip(got, want)):
         for name in ("positions", "normals", "indices"):
             assert a[name].shape == b[name].shape and np.array_equal(a[name].view(np.uint32), b[name].view(np.uint32)), (k, name)
+
+
+def _grid_mesh(nx, ny, sx, sy, height):
+    """a (nx x ny)-quad height field over [0, sx] x [0, sy]: positions, unit normals (0, 0, 1), triangle indices"""
+    xs, ys = np.meshgrid(np.linspace(0, sx, nx + 1, dtype=np.float32), np.linspace(0, sy, ny + 1, dtype=np.float32))
+    pos = np.stack([xs.ravel(), ys.ravel(), height(xs, ys).astype(np.float32).ravel()], axis=1).astype(np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (len(pos), 1))
+    i = (np.arange(ny)[:, None] * (nx + 1) + np.arange(nx)[None, :]).ravel()
+    idx = np.stack([i, i + 1, i + nx + 2, i, i + nx + 2, i + nx + 1], axis=1).astype(np.uint32).ravel()
+    return pos, nrm, idx
+
+
+@pytest.mark.parametrize("name", ["flat", "strip", "tilted", "equal_extents"])
+def test_chunking_decisions_on_degenerate_boxes(name):
+    """bounding boxes with a zero extent, two equal extents (dominantAxis' strict comparisons), a long strip"""
+    from oracle import ref as oref
+
+    if not oref.available():
+        pytest.skip("oracle/_ref not present on this box")
+    ref = oref.RefPlanet(init=False)
+    if name == "flat":  # zero extent in z
+        pos, nrm, idx = _grid_mesh(40, 30, 2000.0, 1500.0, lambda x, y: 0 * x + 7.0)
+    elif name == "strip":  # x dominates
+        pos, nrm, idx = _grid_mesh(200, 3, 9000.0, 90.0, lambda x, y: np.sin(x * 0.01) * 20)
+    elif name == "tilted":  # z extent close to y extent
+        pos, nrm, idx = _grid_mesh(30, 30, 1000.0, 1400.0, lambda x, y: y * 1.0001)
+    else:  # x and y extents equal: neither `>` holds first, the third test decides
+        pos, nrm, idx = _grid_mesh(32, 32, 1600.0, 1600.0, lambda x, y: 0.25 * x)
+    for max_area in (300000.0, 60000.0):
+        want = ref.chunking(pos, nrm, idx, max_surface_area=max_area)
+        got = _emulated_chunking(_hostchunking(), ref, pos, nrm, idx, max_area)
+        assert len(got) == len(want) and len(want) >= 4, (name, len(got), len(want))
+        for k, (a, b) in enumerate(zip(got, want)):
+            for key in ("positions", "normals", "indices"):
+                assert a[key].shape == b[key].shape and np.array_equal(a[key].view(np.uint32), b[key].view(np.uint32)), (name, max_area, k, key)

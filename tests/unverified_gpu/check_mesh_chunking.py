@@ -59,3 +59,21 @@ def test_empty_mesh_and_arguments():
         mesh_chunking(tri, tri, np.array([0, 1, 2], np.uint32), max_surface_area=0.0)
     one = mesh_chunking(tri, tri, np.array([0, 1, 2], np.uint32), max_surface_area=10.0)
     assert len(one) == 1 and np.array_equal(one[0]["positions"], tri) and list(one[0]["indices"]) == [0, 1, 2]
+
+
+@pytest.mark.parametrize("name", ["flat", "strip", "tilted", "equal_extents"])
+def test_chunks_of_degenerate_boxes(name):
+    """the meshes of tests/test_oracle_chunks.py::test_chunking_decisions_on_degenerate_boxes through the device path"""
+    from test_oracle_chunks import _grid_mesh
+
+    ref = ref_or_skip()
+    if name == "flat":
+        pos, nrm, idx = _grid_mesh(40, 30, 2000.0, 1500.0, lambda x, y: 0 * x + 7.0)
+    elif name == "strip":
+        pos, nrm, idx = _grid_mesh(200, 3, 9000.0, 90.0, lambda x, y: np.sin(x * 0.01) * 20)
+    elif name == "tilted":
+        pos, nrm, idx = _grid_mesh(30, 30, 1000.0, 1400.0, lambda x, y: y * 1.0001)
+    else:
+        pos, nrm, idx = _grid_mesh(32, 32, 1600.0, 1600.0, lambda x, y: 0.25 * x)
+    for max_area in (300000.0, 60000.0):
+        same_chunks(mesh_chunking(pos, nrm, idx, max_surface_area=max_area), ref.chunking(pos, nrm, idx, max_surface_area=max_area), (name, max_area))
