@@ -384,10 +384,79 @@ def leg_multi_device(args, devices):
     return line
 
 
+def leg_export(args):
+    """one chunk's export: the land bake of a 500^3 planet at the bench's texture size as three PNG FILES (albedo, pbr, normal map) --
+    what chunkEntry does with three Image::exportFile calls (sources/generator.cpp:135-139; libpng + zlib on one host thread per image).
+    Every part reports on its own: a failure of one costs its scalars only."""
+    import io
+
+    import numpy as np
+    import torch
+
+    from unnatural_planets_b200 import Planet, png_encode, synth
+
+    T = args.texture
+    p = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=500)
+    m = p.field_meshes_clean(("land",))["land"]
+    uv = synth.octahedral_uv(m["positions"])
+    idx = synth.drop_folded_triangles(uv, m["indices"])
+    images = p.bake_export(0, m["positions"], m["normals"], uv, idx, T, T)
+    t = time.perf_counter()
+    images = p.bake_export(0, m["positions"], m["normals"], uv, idx, T, T)
+    line = {"chunk_export_texture": T, "chunk_export_bake_ms": (time.perf_counter() - t) * 1e3, "chunk_export_raw_mb": sum(i.nbytes for i in images) / 1e6}
+    try:  # K10 on images that are already on the device (tests/test_gpu_png.py checks the files byte for byte through two decoders)
+        dev = [torch.from_numpy(i).cuda() for i in images]
+        files = [png_encode(d) for d in dev]
+        ts = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            files = [png_encode(d) for d in dev]
+            ts.append((time.perf_counter() - t) * 1e3)
+        line.update({"chunk_export_png_encode_ms": statistics.median(ts), "chunk_export_png_mb": sum(len(f) for f in files) / 1e6})
+        from PIL import Image
+
+        line["chunk_export_png_decodes_equal"] = bool(all(np.array_equal(np.asarray(Image.open(io.BytesIO(f))), i) for f, i in zip(files, images)))
+        del dev
+    except Exception as ex:
+        line["chunk_export_png_error"] = repr(ex)[:200]
+    try:  # bake + tail + PNG in one call, host mesh in, three files out (first run on hardware is the driver's: DESIGN.md section 9)
+        out = [torch.empty(int(capi_bound(T, T, c)), dtype=torch.uint8, pin_memory=True).numpy() for c in (3, 3, 3)]
+        p.bake_export_png(0, m["positions"], m["normals"], uv, idx, T, T, out=out)
+        ts = []
+        for _ in range(3):
+            files1 = p.bake_export_png(0, m["positions"], m["normals"], uv, idx, T, T, out=out)
+            ts.append(p.last_call_s * 1e3)
+        from PIL import Image
+
+        line.update({"chunk_export_one_call_ms": statistics.median(ts), "chunk_export_one_call_decodes_equal": bool(all(np.array_equal(np.asarray(Image.open(io.BytesIO(f.tobytes()))), i) for f, i in zip(files1, images)))})
+    except Exception as ex:
+        line["chunk_export_one_call_error"] = repr(ex)[:200]
+    try:  # the host side of the comparison: libpng (PIL: zlib level 6, adaptive filters -- cage's exportFile settings) on ONE image, one thread
+        from PIL import Image
+
+        t = time.perf_counter()
+        buf = io.BytesIO()
+        Image.fromarray(images[0]).save(buf, format="PNG")
+        line.update({"chunk_export_libpng_albedo_ms": (time.perf_counter() - t) * 1e3, "chunk_export_libpng_albedo_mb": buf.tell() / 1e6})
+    except Exception as ex:
+        line["chunk_export_libpng_error"] = repr(ex)[:200]
+    p.close()
+    return line
+
+
+def capi_bound(w, h, ch):
+    from unnatural_planets_b200 import capi
+
+    return capi.load_library().upg_png_bound(w, h, ch)
+
+
 def run_leg(args, rank, world, local_rank):
     """`--leg sharded|multi`: one isolated leg, one JSON line (rank 0)"""
     if args.leg == "multi":
         line = leg_multi_device(args, list(range(args.gpus)))
+    elif args.leg == "export":
+        line = leg_export(args)
     else:
         line = leg_sharded(args, rank, world, local_rank)
     if rank == 0:
@@ -438,6 +507,8 @@ def run_orchestration_selftest(args, rank, world):
 def isolated_leg_command(leg, args, world, port):
     """argv of the process (group) that runs one isolated leg over `world` GPUs"""
     tail = [os.path.join(ROOT, "bench.py"), "--leg", leg, "--gpus", str(world), "--sharded-grid", str(args.sharded_grid), "--sharded-texture", str(args.sharded_texture)]
+    if leg == "export":
+        return [sys.executable, os.path.join(ROOT, "bench.py"), "--leg", "export", "--gpus", "1", "--texture", str(args.texture)]
     if leg != "multi" and world > 1:
         return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port)] + tail
     return [sys.executable] + tail
@@ -912,7 +983,8 @@ def run_ours(args, rank, world, local_rank):
             wait_for_other_processes()
         sharded_line = run_isolated_leg("sharded", args, world, args.leg_timeout)
         multi_line = run_isolated_leg("multi", args, world, args.leg_timeout)
-        for name, rec in (("sharded_planet", sharded_line), ("multi_device_planet", multi_line)):
+        export_line = run_isolated_leg("export", args, 1, args.leg_timeout)
+        for name, rec in (("sharded_planet", sharded_line), ("multi_device_planet", multi_line), ("chunk_export", export_line)):
             if "error" in rec:
                 print("[bench] leg %s failed: %s" % (name, rec["error"]), file=sys.stderr, flush=True)
                 roofline[name + "_error"] = rec["error"][:200]
@@ -920,6 +992,8 @@ def run_ours(args, rank, world, local_rank):
             sharded_line = None
         if "error" in multi_line:
             multi_line = None
+        if "error" not in export_line:
+            roofline.update({k: v for k, v in export_line.items() if isinstance(v, (int, float, bool, str)) and k != "leg_wall_s"})
     if sharded_line:
         roofline.update({"sharded_planet_grid": sharded_line["grid"], "sharded_planet_texture": sharded_line["texture"], "sharded_planet_isosurface_ms": sharded_line["isosurface_ms"], "sharded_planet_bake_ms": sharded_line["bake_ms"]})
     if multi_line:
@@ -972,7 +1046,7 @@ def main():
     ap.add_argument("--batch-grid", type=int, default=500, help="grid of the batch planets (the reference's constant)")
     ap.add_argument("--batch-texture", type=int, default=2048, help="bake resolution of the batch planets")
     ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
-    ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
+    ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "export", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
     ap.add_argument("--orchestration-selftest", action="store_true", help="internal: the multi-process control flow of the bench on CPU (gloo), no GPU work")
     ap.add_argument("--leg-timeout", type=int, default=180, help="seconds each isolated leg may take before it is killed and reported as failed")
     args = ap.parse_args()
