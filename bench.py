@@ -445,6 +445,85 @@ def leg_export(args):
     return line
 
 
+def leg_experiments(args):
+    """dense K1 launches of whichever build of the library UPG_LIBRARY names (the parent runs this leg once per build and compares):
+    config 3 (sphere + lakes, column kernel) and config 2 (torus + craters at 500^3, sample kernel), exact and tolerance arithmetic --
+    time per fused launch (CUDA events) and two 64-bit checksums of the three sample fields"""
+    import torch
+
+    from unnatural_planets_b200 import Planet, library_path
+
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    line = {"library": os.path.basename(library_path())}
+
+    def checksums(bufs):
+        a = b = 0
+        step = 1 << 24
+        w = torch.arange(1, step + 1, dtype=torch.int64, device=dev)
+        for buf in bufs:
+            v = buf.view(torch.int32)
+            for at in range(0, v.numel(), step):
+                c = v[at:at + step].to(torch.int64)
+                a = (a + int(c.sum())) & ((1 << 64) - 1)
+                b = (b + int((c * w[: c.numel()]).sum())) & ((1 << 64) - 1)
+        return "%016x%016x" % (a, b)
+
+    for tag, shape, elevation, res in (("lakes", "sphere", "lakes", args.grid), ("craters", "torus", "craters", 500)):
+        bufs = [torch.empty(res**3, dtype=torch.float32, device=dev) for _ in FIELDS]
+        for mode in ("exact", "contract"):
+            p = Planet(shape=shape, elevation=elevation, grid=res, arithmetic=mode)
+
+            def step():
+                p.fields_samples_device(0, res, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), stream.cuda_stream)
+
+            step()
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                step()
+            e1.record(stream)
+            e1.synchronize()
+            p.async_status(stream.cuda_stream)
+            line["%s_%s_ms" % (tag, mode)] = e0.elapsed_time(e1) / 5
+            line["%s_%s_checksum" % (tag, mode)] = checksums(bufs)
+            p.close()
+        del bufs
+        torch.cuda.empty_cache()
+    return line
+
+
+def leg_chunking(args):
+    """upg_mesh_chunking (cage's meshChunking as meshSplit calls it, maxSurfaceArea 800000) on the cleaned land mesh of a 500^3 planet, next to
+    the reference's own meshChunking compiled from the reference tree (oracle/_ref: the timed CPU baseline and the checker of this leg)"""
+    import numpy as np
+
+    from unnatural_planets_b200 import Planet, mesh_chunking
+
+    m = Planet(shape=SHAPE, elevation=ELEVATION, grid=500).field_meshes_clean(("land",))["land"]
+    got = mesh_chunking(m["positions"], m["normals"], m["indices"], max_surface_area=800000.0)
+    ts = []
+    for _ in range(3):
+        t = time.perf_counter()
+        got = mesh_chunking(m["positions"], m["normals"], m["indices"], max_surface_area=800000.0)
+        ts.append((time.perf_counter() - t) * 1e3)
+    line = {"chunking_triangles": int(len(m["indices"]) // 3), "chunking_chunks": len(got), "chunking_ms": statistics.median(ts)}
+    try:
+        from oracle import ref as oref
+
+        if oref.available():
+            r = oref.RefPlanet(init=False)
+            t = time.perf_counter()
+            want = r.chunking(m["positions"], m["normals"], m["indices"], max_surface_area=800000.0)
+            line["chunking_reference_cpu_ms"] = (time.perf_counter() - t) * 1e3
+            line["chunking_equals_reference"] = bool(len(got) == len(want) and all(a[k].shape == b[k].shape and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)) for a, b in zip(got, want) for k in ("positions", "normals", "indices")))
+    except Exception as ex:
+        line["chunking_reference_error"] = repr(ex)[:200]
+    return line
+
+
 def capi_bound(w, h, ch):
     from unnatural_planets_b200 import capi
 
@@ -457,6 +536,10 @@ def run_leg(args, rank, world, local_rank):
         line = leg_multi_device(args, list(range(args.gpus)))
     elif args.leg == "export":
         line = leg_export(args)
+    elif args.leg == "experiments":
+        line = leg_experiments(args)
+    elif args.leg == "chunking":
+        line = leg_chunking(args)
     else:
         line = leg_sharded(args, rank, world, local_rank)
     if rank == 0:
@@ -507,8 +590,8 @@ def run_orchestration_selftest(args, rank, world):
 def isolated_leg_command(leg, args, world, port):
     """argv of the process (group) that runs one isolated leg over `world` GPUs"""
     tail = [os.path.join(ROOT, "bench.py"), "--leg", leg, "--gpus", str(world), "--sharded-grid", str(args.sharded_grid), "--sharded-texture", str(args.sharded_texture)]
-    if leg == "export":
-        return [sys.executable, os.path.join(ROOT, "bench.py"), "--leg", "export", "--gpus", "1", "--texture", str(args.texture)]
+    if leg in ("export", "experiments", "chunking"):  # one process on one GPU whatever the size of the job
+        return [sys.executable, os.path.join(ROOT, "bench.py"), "--leg", leg, "--gpus", "1", "--grid", str(args.grid), "--texture", str(args.texture)]
     if leg != "multi" and world > 1:
         return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1", "--master-port", str(port)] + tail
     return [sys.executable] + tail
@@ -545,9 +628,10 @@ def kill_process_tree(proc):
         pass
 
 
-def run_isolated_leg(leg, args, world, timeout_s):
+def run_isolated_leg(leg, args, world, timeout_s, extra_env=None):
     """runs `bench.py --leg <leg>` in its own session under a timeout; returns its record, or {"error": "..."}"""
     env = {k: v for k, v in os.environ.items() if k not in _TORCHRUN_ENV and not k.startswith("TORCHELASTIC")}
+    env.update(extra_env or {})
     cmd = isolated_leg_command(leg, args, world, free_port())
     t = time.perf_counter()
     try:
@@ -994,6 +1078,29 @@ def run_ours(args, rank, world, local_rank):
             multi_line = None
         if "error" not in export_line:
             roofline.update({k: v for k, v in export_line.items() if isinstance(v, (int, float, bool, str)) and k != "leg_wall_s"})
+        if world == 1:
+            # measurements the round could not take itself (its GPU budget ended with the 8-GPU run): the device meshChunking next to the
+            # reference's, and the two unmeasured K1 experiments (streaming stores, block-shared Voronoi table) as an alternative build of
+            # the library next to the shipped one -- each in its own process, none of them on the path of any number above
+            rec = run_isolated_leg("chunking", args, 1, args.leg_timeout)
+            if "error" in rec:
+                roofline["chunking_error"] = rec["error"][:200]
+            else:
+                roofline.update({k: v for k, v in rec.items() if isinstance(v, (int, float, bool, str)) and k != "leg_wall_s"})
+            variant = os.path.join(ROOT, "unnatural_planets_b200", "libupg_experiments.so")
+            if os.path.exists(variant):
+                shipped = run_isolated_leg("experiments", args, 1, args.leg_timeout)
+                other = run_isolated_leg("experiments", args, 1, args.leg_timeout, extra_env={"UPG_LIBRARY": variant})
+                for label, rec in (("shipped", shipped), ("experiments_build", other)):
+                    if "error" in rec:
+                        roofline["k1_%s_error" % label] = rec["error"][:200]
+                    else:
+                        roofline.update({"k1_%s_%s" % (label, k): v for k, v in rec.items() if k.endswith("_ms")})
+                if "error" not in shipped and "error" not in other:
+                    for k in shipped:
+                        if k.endswith("_checksum"):
+                            roofline["k1_experiments_build_%s_identical" % k[: -len("_checksum")]] = bool(shipped[k] == other.get(k))
+                    roofline["k1_experiments_build_what"] = "libupg_experiments.so = -DUPG_K1_STORE=1 (st.global.cs in the column kernel: lakes) -DUPG_CRATERS_TABLE=1 (block-shared Voronoi points in the sample kernel: craters)"
     if sharded_line:
         roofline.update({"sharded_planet_grid": sharded_line["grid"], "sharded_planet_texture": sharded_line["texture"], "sharded_planet_isosurface_ms": sharded_line["isosurface_ms"], "sharded_planet_bake_ms": sharded_line["bake_ms"]})
     if multi_line:
@@ -1046,7 +1153,7 @@ def main():
     ap.add_argument("--batch-grid", type=int, default=500, help="grid of the batch planets (the reference's constant)")
     ap.add_argument("--batch-texture", type=int, default=2048, help="bake resolution of the batch planets")
     ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
-    ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "export", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
+    ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "export", "experiments", "chunking", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
     ap.add_argument("--orchestration-selftest", action="store_true", help="internal: the multi-process control flow of the bench on CPU (gloo), no GPU work")
     ap.add_argument("--leg-timeout", type=int, default=180, help="seconds each isolated leg may take before it is killed and reported as failed")
     args = ap.parse_args()

@@ -35,11 +35,11 @@ def test_isolated_leg_commands():
 
     import bench
 
-    a = argparse.Namespace(sharded_grid=1024, sharded_texture=8192, texture=4096)
+    a = argparse.Namespace(sharded_grid=1024, sharded_texture=8192, texture=4096, grid=1000)
     multi = bench.isolated_leg_command("multi", a, 8, 1234)
     assert multi[0] == sys.executable and "torch.distributed.run" not in multi and multi[-6:] == ["--gpus", "8", "--sharded-grid", "1024", "--sharded-texture", "8192"]
     sharded = bench.isolated_leg_command("sharded", a, 8, 1234)
     assert sharded[1:3] == ["-m", "torch.distributed.run"] and "--nproc-per-node" in sharded and sharded[sharded.index("--nproc-per-node") + 1] == "8" and "127.0.0.1" in sharded
     assert "torch.distributed.run" not in bench.isolated_leg_command("sharded", a, 1, 1234)
     export = bench.isolated_leg_command("export", a, 8, 1234)  # one process on one GPU whatever the size of the job
-    assert "torch.distributed.run" not in export and export[-6:] == ["--leg", "export", "--gpus", "1", "--texture", "4096"]
+    assert "torch.distributed.run" not in export and export[2:6] == ["--leg", "export", "--gpus", "1"] and export[-2:] == ["--texture", "4096"]
