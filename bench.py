@@ -492,7 +492,49 @@ def leg_experiments(args):
             p.close()
         del bufs
         torch.cuda.empty_cache()
+    # the land bake of the bench planet (K5 raster + K6 colouring + K7 dilation / quantisation, everything resident in HBM): time per call and the
+    # albedo written to UPG_EXPERIMENT_DUMP for the parent to compare between the builds (the experiments build evaluates HSLuv in single precision)
+    import numpy as np
+
+    from unnatural_planets_b200 import synth
+
+    tex = args.texture
+    p = Planet(shape=SHAPE, elevation=ELEVATION, coloring=COLORING, grid=500)
+    m = p.field_meshes_clean(("land",))["land"]
+    uv = synth.octahedral_uv(m["positions"])
+    idx = synth.drop_folded_triangles(uv, m["indices"])
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (m["positions"], -m["normals"], uv, idx.view(np.int32))]
+    o = [torch.empty(tex * tex * c, dtype=torch.uint8, device=dev) for c in (3, 2, 1)]
+
+    def bake():
+        p.bake_device(0, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[0].shape[0], d[3].data_ptr(), d[3].shape[0], tex, tex, 0, tex, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), stream.cuda_stream)
+
+    bake()
+    bake()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        bake()
+    e1.record(stream)
+    e1.synchronize()
+    line["land_bake_ms"] = e0.elapsed_time(e1) / 5
+    line["land_bake_covered_texels"] = int(p.last_covered_texels)
+    dump = os.environ.get("UPG_EXPERIMENT_DUMP")
+    if dump:
+        np.save(dump, o[0].cpu().numpy())
+    p.close()
     return line
+
+
+def compare_albedo_dumps(a_path, b_path):
+    """share of texels whose albedo differs between two dumps of leg_experiments, and by how much"""
+    import numpy as np
+
+    a, b = np.load(a_path).reshape(-1, 3).astype(np.int16), np.load(b_path).reshape(-1, 3).astype(np.int16)
+    step = np.abs(a - b).max(axis=1)
+    covered = (a != 0).any(axis=1) | (b != 0).any(axis=1)
+    n = max(1, int(covered.sum()))
+    return {"texels": int(covered.sum()), "differing_share": float((step > 0).sum() / n), "more_than_one_step_share": float((step > 1).sum() / n), "max_step": int(step.max())}
 
 
 def leg_chunking(args):
@@ -1089,18 +1131,31 @@ def run_ours(args, rank, world, local_rank):
                 roofline.update({k: v for k, v in rec.items() if isinstance(v, (int, float, bool, str)) and k != "leg_wall_s"})
             variant = os.path.join(ROOT, "unnatural_planets_b200", "libupg_experiments.so")
             if os.path.exists(variant):
-                shipped = run_isolated_leg("experiments", args, 1, args.leg_timeout)
-                other = run_isolated_leg("experiments", args, 1, args.leg_timeout, extra_env={"UPG_LIBRARY": variant})
+                import tempfile
+
+                dumps = tempfile.mkdtemp(prefix="upg_bench_")
+                da, db = os.path.join(dumps, "shipped.npy"), os.path.join(dumps, "experiments.npy")
+                shipped = run_isolated_leg("experiments", args, 1, args.leg_timeout, extra_env={"UPG_EXPERIMENT_DUMP": da})
+                other = run_isolated_leg("experiments", args, 1, args.leg_timeout, extra_env={"UPG_LIBRARY": variant, "UPG_EXPERIMENT_DUMP": db})
                 for label, rec in (("shipped", shipped), ("experiments_build", other)):
                     if "error" in rec:
-                        roofline["k1_%s_error" % label] = rec["error"][:200]
+                        roofline["ab_%s_error" % label] = rec["error"][:200]
                     else:
-                        roofline.update({"k1_%s_%s" % (label, k): v for k, v in rec.items() if k.endswith("_ms")})
+                        roofline.update({"ab_%s_%s" % (label, k): v for k, v in rec.items() if k.endswith("_ms")})
                 if "error" not in shipped and "error" not in other:
                     for k in shipped:
                         if k.endswith("_checksum"):
-                            roofline["k1_experiments_build_%s_identical" % k[: -len("_checksum")]] = bool(shipped[k] == other.get(k))
-                    roofline["k1_experiments_build_what"] = "libupg_experiments.so = -DUPG_K1_STORE=1 (st.global.cs in the column kernel: lakes) -DUPG_CRATERS_TABLE=1 (block-shared Voronoi points in the sample kernel: craters)"
+                            roofline["ab_experiments_build_%s_samples_identical" % k[: -len("_checksum")]] = bool(shipped[k] == other.get(k))
+                    roofline["ab_experiments_build_what"] = "libupg_experiments.so = -DUPG_K1_STORE=1 (st.global.cs in the column kernel: lakes) -DUPG_CRATERS_TABLE=1 (block-shared Voronoi points in the sample kernel: craters) -DUPG_HSLUV_REAL=float (HSLuv of the colouring kernel in single precision: land_bake)"
+                    try:
+                        roofline.update({"ab_experiments_build_albedo_" + k: v for k, v in compare_albedo_dumps(da, db).items()})
+                    except Exception as ex:
+                        roofline["ab_experiments_build_albedo_error"] = repr(ex)[:200]
+                for f in (da, db):
+                    try:
+                        os.remove(f)
+                    except OSError:
+                        pass
     if sharded_line:
         roofline.update({"sharded_planet_grid": sharded_line["grid"], "sharded_planet_texture": sharded_line["texture"], "sharded_planet_isosurface_ms": sharded_line["isosurface_ms"], "sharded_planet_bake_ms": sharded_line["bake_ms"]})
     if multi_line:
