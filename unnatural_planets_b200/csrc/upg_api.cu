@@ -1030,12 +1030,21 @@ namespace upg
 			ev.event = nullptr;
 			e = cudaEventCreateWithFlags(&ev.event, cudaEventBlockingSync | cudaEventDisableTiming);
 			if (e != cudaSuccess)
-				return e;
+			{
+				// sleeping is an optimisation, never a reason to fail a call: without the event (the driver reports every resource it
+				// cannot create for one as cudaErrorMemoryAllocation) wait the plain way
+				ev.event = nullptr;
+				cudaGetLastError();
+				return cudaStreamSynchronize(s);
+			}
 			ev.device = device;
 		}
 		e = cudaEventRecord(ev.event, s);
 		if (e != cudaSuccess)
-			return e;
+		{
+			cudaGetLastError();
+			return cudaStreamSynchronize(s);
+		}
 		return cudaEventSynchronize(ev.event);
 	}
 
