@@ -445,6 +445,24 @@ def leg_export(args):
     return line
 
 
+def tensor_checksums(bufs, step=1 << 24):
+    """two 64-bit checksums (plain and position-weighted sum of the bit patterns, modulo 2^64) of float32 tensors, computed where they live"""
+    import torch
+
+    a = b = 0
+    mask = (1 << 64) - 1
+    w = None
+    for buf in bufs:
+        v = buf.view(torch.int32)
+        if w is None:
+            w = torch.arange(1, step + 1, dtype=torch.int64, device=v.device)
+        for at in range(0, v.numel(), step):
+            c = v[at:at + step].to(torch.int64)
+            a = (a + int(c.sum())) & mask
+            b = (b + int((c * w[: c.numel()]).sum())) & mask
+    return "%016x%016x" % (a, b)
+
+
 def leg_experiments(args):
     """dense K1 launches of whichever build of the library UPG_LIBRARY names (the parent runs this leg once per build and compares):
     config 3 (sphere + lakes, column kernel) and config 2 (torus + craters at 500^3, sample kernel), exact and tolerance arithmetic --
@@ -456,18 +474,6 @@ def leg_experiments(args):
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream()
     line = {"library": os.path.basename(library_path())}
-
-    def checksums(bufs):
-        a = b = 0
-        step = 1 << 24
-        w = torch.arange(1, step + 1, dtype=torch.int64, device=dev)
-        for buf in bufs:
-            v = buf.view(torch.int32)
-            for at in range(0, v.numel(), step):
-                c = v[at:at + step].to(torch.int64)
-                a = (a + int(c.sum())) & ((1 << 64) - 1)
-                b = (b + int((c * w[: c.numel()]).sum())) & ((1 << 64) - 1)
-        return "%016x%016x" % (a, b)
 
     for tag, shape, elevation, res in (("lakes", "sphere", "lakes", args.grid), ("craters", "torus", "craters", 500)):
         bufs = [torch.empty(res**3, dtype=torch.float32, device=dev) for _ in FIELDS]
@@ -488,7 +494,7 @@ def leg_experiments(args):
             e1.synchronize()
             p.async_status(stream.cuda_stream)
             line["%s_%s_ms" % (tag, mode)] = e0.elapsed_time(e1) / 5
-            line["%s_%s_checksum" % (tag, mode)] = checksums(bufs)
+            line["%s_%s_checksum" % (tag, mode)] = tensor_checksums(bufs)
             p.close()
         del bufs
         torch.cuda.empty_cache()

@@ -43,3 +43,35 @@ def test_isolated_leg_commands():
     assert "torch.distributed.run" not in bench.isolated_leg_command("sharded", a, 1, 1234)
     export = bench.isolated_leg_command("export", a, 8, 1234)  # one process on one GPU whatever the size of the job
     assert "torch.distributed.run" not in export and export[2:6] == ["--leg", "export", "--gpus", "1"] and export[-2:] == ["--texture", "4096"]
+
+
+def test_bench_helpers_of_the_ab_leg():
+    """the pure helpers of bench.py's A/B leg (the leg itself needs a GPU): checksums of sample fields, comparison of two albedo dumps"""
+    sys.path.insert(0, ROOT)
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    import bench
+
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=5000).astype(np.float32)
+    y = x.copy()
+    y[1234] = np.nextafter(y[1234], np.float32(10))
+    cx = bench.tensor_checksums([torch.from_numpy(x), torch.from_numpy(x[:100].copy())], step=1024)
+    assert cx == bench.tensor_checksums([torch.from_numpy(x.copy()), torch.from_numpy(x[:100].copy())], step=1024) and len(cx) == 32
+    assert cx != bench.tensor_checksums([torch.from_numpy(y), torch.from_numpy(x[:100].copy())], step=1024)  # one ulp in one sample shows
+    bits = x.view(np.int32).astype(np.int64)
+    plain = (int(bits.sum()) + int(bits[:100].sum())) & ((1 << 64) - 1)
+    assert cx[:16] == "%016x" % plain
+    d = tempfile.mkdtemp()
+    a = rng.integers(0, 255, size=(64, 64, 3)).astype(np.uint8)
+    b = a.copy()
+    b[3, 4, 1] += 1
+    b[7, 7, 2] = (int(b[7, 7, 2]) + 9) % 256 if b[7, 7, 2] < 200 else b[7, 7, 2] - 9
+    np.save(os.path.join(d, "a.npy"), a.reshape(-1))
+    np.save(os.path.join(d, "b.npy"), b.reshape(-1))
+    r = bench.compare_albedo_dumps(os.path.join(d, "a.npy"), os.path.join(d, "b.npy"))
+    assert r["max_step"] == 9 and abs(r["differing_share"] * r["texels"] - 2) < 1e-6 and abs(r["more_than_one_step_share"] * r["texels"] - 1) < 1e-6
+
