@@ -676,8 +676,17 @@ def kill_process_tree(proc):
         pass
 
 
+_LEGS_DEADLINE = [None]  # wall-clock instant after which no isolated leg is started or kept running (args.legs_budget after the first one)
+
+
 def run_isolated_leg(leg, args, world, timeout_s, extra_env=None):
     """runs `bench.py --leg <leg>` in its own session under a timeout; returns its record, or {"error": "..."}"""
+    if _LEGS_DEADLINE[0] is None:
+        _LEGS_DEADLINE[0] = time.perf_counter() + getattr(args, "legs_budget", 420)
+    left = _LEGS_DEADLINE[0] - time.perf_counter()
+    if left < 15:
+        return {"error": "skipped: the time budget of the isolated legs is spent"}
+    timeout_s = min(timeout_s, left)
     env = {k: v for k, v in os.environ.items() if k not in _TORCHRUN_ENV and not k.startswith("TORCHELASTIC")}
     env.update(extra_env or {})
     cmd = isolated_leg_command(leg, args, world, free_port())
@@ -694,7 +703,7 @@ def run_isolated_leg(leg, args, world, timeout_s, extra_env=None):
             proc.communicate(timeout=10)
         except Exception:
             pass
-        return {"error": "timeout after %d s" % timeout_s}
+        return {"error": "timeout after %d s" % int(timeout_s)}
     record = None
     for text in reversed((out or "").strip().splitlines()):
         try:
@@ -1215,6 +1224,7 @@ def main():
     ap.add_argument("--batch-texture", type=int, default=2048, help="bake resolution of the batch planets")
     ap.add_argument("--sharded-texture", type=int, default=8192, help="bake resolution of that leg (BASELINE configs[4]: 8192)")
     ap.add_argument("--leg", default="", choices=["", "sharded", "multi", "export", "experiments", "chunking", "selftest", "hang"], help="internal: run ONE of the isolated one-planet-over-N-GPUs legs and print its record (selftest / hang: CPU checks of the orchestration)")
+    ap.add_argument("--legs-budget", type=int, default=420, help="seconds all isolated legs together may take; legs that do not fit are skipped and reported as such")
     ap.add_argument("--orchestration-selftest", action="store_true", help="internal: the multi-process control flow of the bench on CPU (gloo), no GPU work")
     ap.add_argument("--leg-timeout", type=int, default=180, help="seconds each isolated leg may take before it is killed and reported as failed")
     args = ap.parse_args()
